@@ -1,0 +1,135 @@
+"""ctypes loader for libb381.so (include/b381.h) -- the only way Python reaches the engine.
+
+There is no Python or CPU fallback: if the shared library is missing or no CUDA device is
+usable, construction fails loudly.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import layout as L
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb381.so")
+
+B381_OK = 0
+ERRORS = {-1: "B381_ERR_ARG", -2: "B381_ERR_CUDA", -3: "B381_ERR_NOMEM", -4: "B381_ERR_NO_DEVICE"}
+
+
+class B381Error(RuntimeError):
+    def __init__(self, code, msg=""):
+        super().__init__("%s (%d) %s" % (ERRORS.get(code, "?"), code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """dlopen libb381.so; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError("%s is not built; run __graft_entry__.build() (nvcc, sm_100a)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.b381_last_error.restype = ctypes.c_char_p
+        lib.b381_launch_count.restype = ctypes.c_uint64
+        _lib = lib
+    return _lib
+
+
+def _hp(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+class Ctx:
+    """one engine context bound to one CUDA device (b381_init / b381_free)"""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        self._h = ctypes.c_void_p()
+        rc = self.lib.b381_init(int(device), ctypes.byref(self._h))
+        if rc != B381_OK:
+            raise B381Error(rc, "b381_init(device=%d)" % device)
+        self.device = device
+
+    def close(self):
+        if self._h:
+            self.lib.b381_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != B381_OK:
+            raise B381Error(rc, (self.lib.b381_last_error(self._h) or b"").decode())
+
+    def call(self, name, *args):
+        self._ck(getattr(self.lib, name)(self._h, *args))
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_handle):
+        self.call("b381_set_stream", ctypes.c_void_p(cuda_stream_handle or 0))
+
+    def sync(self):
+        self.call("b381_sync")
+
+    @property
+    def launch_count(self):
+        return int(self.lib.b381_launch_count(self._h))
+
+    # -- host-buffer entry points (numpy in / numpy out) ------------------------------------
+    def pairing_batch(self, p, q):
+        p = np.ascontiguousarray(p, dtype=L.G1_AFFINE); q = np.ascontiguousarray(q, dtype=L.G2_AFFINE)
+        assert p.size == q.size
+        out = np.empty(p.size, dtype=L.FP12)
+        self.call("b381_pairing_batch", _hp(p), _hp(q), ctypes.c_size_t(p.size), _hp(out))
+        return out
+
+    def miller_loop_batch(self, p, q):
+        p = np.ascontiguousarray(p, dtype=L.G1_AFFINE); q = np.ascontiguousarray(q, dtype=L.G2_AFFINE)
+        assert p.size == q.size
+        out = np.empty(p.size, dtype=L.FP12)
+        self.call("b381_miller_loop_batch", _hp(p), _hp(q), ctypes.c_size_t(p.size), _hp(out))
+        return out
+
+    def final_exp_batch(self, f):
+        f = np.ascontiguousarray(f, dtype=np.uint64).reshape(-1, 2, 3, 2, 6)
+        out = np.empty_like(f); ok = np.empty(f.shape[0], np.uint8)
+        self.call("b381_final_exp_batch", _hp(f), ctypes.c_size_t(f.shape[0]), _hp(out), _hp(ok))
+        return out, ok
+
+    def pairing_product_is_one(self, p, q, group_off):
+        p = np.ascontiguousarray(p, dtype=L.G1_AFFINE); q = np.ascontiguousarray(q, dtype=L.G2_AFFINE)
+        off = np.ascontiguousarray(group_off, dtype=np.uint32)
+        ok = np.empty(off.size - 1, np.uint8)
+        self.call("b381_pairing_product_is_one", _hp(p), _hp(q), ctypes.c_size_t(p.size), _hp(off),
+                  ctypes.c_size_t(off.size - 1), _hp(ok))
+        return ok
+
+    def g1_sum(self, p):
+        p = np.ascontiguousarray(p, dtype=L.G1_AFFINE); out = np.zeros(1, dtype=L.G1_JAC)
+        self.call("b381_g1_sum", _hp(p), ctypes.c_size_t(p.size), _hp(out))
+        return out
+
+    def g2_sum(self, p):
+        p = np.ascontiguousarray(p, dtype=L.G2_AFFINE); out = np.zeros(1, dtype=L.G2_JAC)
+        self.call("b381_g2_sum", _hp(p), ctypes.c_size_t(p.size), _hp(out))
+        return out
+
+    def g1_msm(self, p, k):
+        p = np.ascontiguousarray(p, dtype=L.G1_AFFINE); k = np.ascontiguousarray(k, dtype=np.uint64).reshape(-1, 4)
+        assert p.size == k.shape[0]
+        out = np.zeros(1, dtype=L.G1_JAC)
+        self.call("b381_g1_msm", _hp(p), _hp(k), ctypes.c_size_t(p.size), _hp(out))
+        return out
+
+    # -- device-pointer entry points (ints are raw device addresses, e.g. torch .data_ptr()) --
+    def dev(self, name, *args):
+        conv = [ctypes.c_void_p(a) if isinstance(a, int) and not isinstance(a, bool) and a > 0xFFFF else a for a in args]
+        self.call(name, *conv)

@@ -1,0 +1,343 @@
+// b381.cu -- kernels and C ABI (include/b381.h) of the B200 BLS12-381 engine.
+// One TU on purpose: the __constant__ tables and the out-of-line Fq2 routines are shared by
+// every kernel.  There is no CPU fallback in this library: without a CUDA device b381_init
+// returns B381_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+#include "../../include/b381.h"
+#include "pairing.cuh"
+#include "curve.cuh"
+
+using namespace b381;
+
+static_assert(sizeof(b381_g1_affine) == sizeof(g1_affine_pod) && sizeof(b381_g1_affine) == 104, "layout");
+static_assert(sizeof(b381_g2_affine) == sizeof(g2_affine_pod) && sizeof(b381_g2_affine) == 200, "layout");
+static_assert(sizeof(b381_fp12) == 576 && sizeof(fp12) == 576, "layout");
+static_assert(sizeof(b381_g1_jac) == 144 && sizeof(b381_g2_jac) == 288, "layout");
+
+// ---------------------------------------------------------------------------------------------
+// kernels: one thread per independent unit
+// ---------------------------------------------------------------------------------------------
+#define PAIRING_BLOCK 128
+
+// out[i] = MillerLoop(p[i], q[i])   (pairing.go:16-75 fused with g2.go:650-801)
+__global__ void __launch_bounds__(PAIRING_BLOCK) k_miller_loop(const g1_affine_pod *__restrict__ p,
+                                                                 const g2_affine_pod *__restrict__ q, size_t n,
+                                                                 uint64_t *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp12 f;
+    miller_loop_one(&f, p + i, q + i);
+    fp12_store_u64(out + 72 * i, &f);
+}
+
+// out[i] = FinalExponentiation(in[i])   (pairing.go:79-129); in-place allowed
+__global__ void __launch_bounds__(PAIRING_BLOCK) k_final_exp(const uint64_t *in, size_t n, uint64_t *out,
+                                                               uint8_t *ok) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp12 f, r;
+    fp12_load_u64(&f, in + 72 * i);
+    fp12_set_one(&r);
+    bool good = final_exp_one(&r, &f);
+    fp12_store_u64(out + 72 * i, &r);
+    if (ok) ok[i] = good ? 1 : 0;
+}
+
+// prod[g] = product of ml[group_off[g] .. group_off[g+1])   (the shared accumulator f of pairing.go:40-69)
+__global__ void __launch_bounds__(PAIRING_BLOCK) k_group_product(const uint64_t *__restrict__ ml,
+                                                                   const uint32_t *__restrict__ group_off,
+                                                                   size_t ngroups, uint64_t *__restrict__ prod) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    fp12 acc, t;
+    fp12_set_one(&acc);
+    uint32_t lo = group_off[g], hi = group_off[g + 1];
+    for (uint32_t i = lo; i < hi; i++) {
+        fp12_load_u64(&t, ml + 72 * (size_t)i);
+        if (i == lo) fp12_copy(&acc, &t);
+        else fp12_mul(&acc, &acc, &t);
+    }
+    fp12_store_u64(prod + 72 * g, &acc);
+}
+
+// ok[g] = FinalExponentiation(prod[g]) == 1   (pairing.go:143-146)
+__global__ void __launch_bounds__(PAIRING_BLOCK) k_final_exp_is_one(const uint64_t *__restrict__ prod, size_t n,
+                                                                      uint8_t *__restrict__ ok) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp12 f, r;
+    fp12_load_u64(&f, prod + 72 * i);
+    bool good = final_exp_one(&r, &f);
+    ok[i] = (good && fp12_is_one(&r)) ? 1 : 0;
+}
+
+// Roofline denominator: sustained issue rate of IMAD.WIDE.U32 (the 32x32->64 multiply-accumulate
+// every Fq multiplication is made of).  8 independent chains per thread; each thread executes
+// iters * 8 wide MACs.
+__global__ void k_imad_probe(uint32_t *out, int iters) {
+    uint32_t b = blockIdx.x * 40503u + threadIdx.x * 2654435761u + 7u;
+    uint64_t acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = (uint64_t)(b + j) * 0x9E3779B97F4A7C15ull;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            uint32_t x = (uint32_t)acc[(j + 1) & 7];
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(x), "r"(b));
+        }
+    }
+    uint64_t r = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) r ^= acc[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)r ^ (uint32_t)(r >> 32);
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct b381_ctx {
+    int device;
+    cudaStream_t own_stream;
+    cudaStream_t stream;
+    uint64_t launches;
+    char err[256];
+    // grow-only device scratch
+    void *scratch[4];
+    size_t scratch_bytes[4];
+};
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            snprintf(ctx->err, sizeof ctx->err, "%s failed: %s", #call, cudaGetErrorString(e_));      \
+            return e_ == cudaErrorMemoryAllocation ? B381_ERR_NOMEM : B381_ERR_CUDA;                  \
+        }                                                                                             \
+    } while (0)
+
+static int scratch_get(b381_ctx *ctx, int slot, size_t bytes, void **out) {
+    if (ctx->scratch_bytes[slot] < bytes) {
+        if (ctx->scratch[slot]) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaFree(ctx->scratch[slot]));
+            ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0;
+        }
+        CK(cudaMalloc(&ctx->scratch[slot], bytes));
+        ctx->scratch_bytes[slot] = bytes;
+    }
+    *out = ctx->scratch[slot];
+    return B381_OK;
+}
+
+static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+extern "C" {
+
+int b381_init(int device, b381_ctx **out) {
+    if (!out) return B381_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return B381_ERR_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return B381_ERR_NO_DEVICE;
+    b381_ctx *ctx = new (std::nothrow) b381_ctx();
+    if (!ctx) return B381_ERR_NOMEM;
+    memset(ctx, 0, sizeof *ctx);
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B381_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
+    // the tower state of a pairing lives in local memory: prefer L1 over shared memory
+    cudaFuncSetAttribute(k_miller_loop, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_final_exp, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_final_exp_is_one, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_group_product, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    *out = ctx;
+    return B381_OK;
+}
+
+void b381_free(b381_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 4; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char *b381_last_error(const b381_ctx *ctx) { return ctx ? ctx->err : "null ctx"; }
+
+int b381_set_stream(b381_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return B381_ERR_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return B381_OK;
+}
+int b381_sync(b381_ctx *ctx) {
+    if (!ctx) return B381_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B381_OK;
+}
+uint64_t b381_launch_count(const b381_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int b381_dev_alloc(b381_ctx *ctx, size_t bytes, void **dptr) {
+    if (!ctx || !dptr) return B381_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMalloc(dptr, bytes ? bytes : 1));
+    return B381_OK;
+}
+int b381_dev_free(b381_ctx *ctx, void *dptr) {
+    if (!ctx) return B381_ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(dptr));
+    return B381_OK;
+}
+int b381_h2d(b381_ctx *ctx, void *dptr, const void *host, size_t bytes) {
+    if (!ctx || (bytes && (!dptr || !host))) return B381_ERR_ARG;
+    CK(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return B381_OK;
+}
+int b381_d2h(b381_ctx *ctx, void *host, const void *dptr, size_t bytes) {
+    if (!ctx || (bytes && (!dptr || !host))) return B381_ERR_ARG;
+    CK(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B381_OK;
+}
+
+// ---- measurement ---------------------------------------------------------------------------------
+int b381_imad_probe_dev(b381_ctx *ctx, uint32_t *d_out, int blocks, int threads, int iters) {
+    if (!ctx || !d_out || blocks <= 0 || threads <= 0 || threads > 1024 || iters <= 0) return B381_ERR_ARG;
+    k_imad_probe<<<blocks, threads, 0, ctx->stream>>>(d_out, iters);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+
+// ---- pairing, device-resident ------------------------------------------------------------------
+int b381_miller_loop_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_affine *d_q, size_t n,
+                               b381_fp12 *d_out) {
+    if (!ctx || (n && (!d_p || !d_q || !d_out))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    k_miller_loop<<<grid_for(n, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>(
+        (const g1_affine_pod *)d_p, (const g2_affine_pod *)d_q, n, (uint64_t *)d_out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+int b381_final_exp_batch_dev(b381_ctx *ctx, const b381_fp12 *d_in, size_t n, b381_fp12 *d_out, uint8_t *d_ok) {
+    if (!ctx || (n && (!d_in || !d_out))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    k_final_exp<<<grid_for(n, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>((const uint64_t *)d_in, n,
+                                                                              (uint64_t *)d_out, d_ok);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+int b381_pairing_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_affine *d_q, size_t n,
+                           b381_fp12 *d_out) {
+    int rc = b381_miller_loop_batch_dev(ctx, d_p, d_q, n, d_out);
+    if (rc) return rc;
+    return b381_final_exp_batch_dev(ctx, d_out, n, d_out, nullptr);
+}
+int b381_pairing_product_is_one_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_affine *d_q,
+                                    size_t npairs, const uint32_t *d_group_off, size_t ngroups, uint8_t *d_ok) {
+    if (!ctx || (ngroups && (!d_group_off || !d_ok)) || (npairs && (!d_p || !d_q))) return B381_ERR_ARG;
+    if (!ngroups) return B381_OK;
+    void *ml = nullptr, *prod = nullptr;
+    int rc = scratch_get(ctx, 0, (npairs ? npairs : 1) * sizeof(b381_fp12), &ml);
+    if (rc) return rc;
+    rc = scratch_get(ctx, 1, ngroups * sizeof(b381_fp12), &prod);
+    if (rc) return rc;
+    rc = b381_miller_loop_batch_dev(ctx, d_p, d_q, npairs, (b381_fp12 *)ml);
+    if (rc) return rc;
+    k_group_product<<<grid_for(ngroups, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>(
+        (const uint64_t *)ml, d_group_off, ngroups, (uint64_t *)prod);
+    ctx->launches++;
+    k_final_exp_is_one<<<grid_for(ngroups, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>((const uint64_t *)prod,
+                                                                                          ngroups, d_ok);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+
+// ---- pairing, host buffers (copies inside) -------------------------------------------------------
+static int staged_pq(b381_ctx *ctx, const b381_g1_affine *p, const b381_g2_affine *q, size_t n, void **dp, void **dq) {
+    int rc = scratch_get(ctx, 2, n * sizeof(b381_g1_affine), dp);
+    if (rc) return rc;
+    rc = scratch_get(ctx, 3, n * sizeof(b381_g2_affine), dq);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(*dp, p, n * sizeof(b381_g1_affine), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(*dq, q, n * sizeof(b381_g2_affine), cudaMemcpyHostToDevice, ctx->stream));
+    return B381_OK;
+}
+static int pairing_host(b381_ctx *ctx, const b381_g1_affine *p, const b381_g2_affine *q, size_t n, b381_fp12 *out,
+                        bool final_exp) {
+    if (!ctx || (n && (!p || !q || !out))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    CK(cudaSetDevice(ctx->device));
+    void *dp, *dq, *dout;
+    int rc = staged_pq(ctx, p, q, n, &dp, &dq);
+    if (rc) return rc;
+    rc = scratch_get(ctx, 0, n * sizeof(b381_fp12), &dout);
+    if (rc) return rc;
+    rc = final_exp ? b381_pairing_batch_dev(ctx, (b381_g1_affine *)dp, (b381_g2_affine *)dq, n, (b381_fp12 *)dout)
+                   : b381_miller_loop_batch_dev(ctx, (b381_g1_affine *)dp, (b381_g2_affine *)dq, n, (b381_fp12 *)dout);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, dout, n * sizeof(b381_fp12), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B381_OK;
+}
+int b381_pairing_batch(b381_ctx *ctx, const b381_g1_affine *p, const b381_g2_affine *q, size_t n, b381_fp12 *out) {
+    return pairing_host(ctx, p, q, n, out, true);
+}
+int b381_miller_loop_batch(b381_ctx *ctx, const b381_g1_affine *p, const b381_g2_affine *q, size_t n, b381_fp12 *out) {
+    return pairing_host(ctx, p, q, n, out, false);
+}
+int b381_final_exp_batch(b381_ctx *ctx, const b381_fp12 *in, size_t n, b381_fp12 *out, uint8_t *ok) {
+    if (!ctx || (n && (!in || !out))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    CK(cudaSetDevice(ctx->device));
+    void *d, *dok;
+    int rc = scratch_get(ctx, 0, n * sizeof(b381_fp12), &d);
+    if (rc) return rc;
+    rc = scratch_get(ctx, 1, n, &dok);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(d, in, n * sizeof(b381_fp12), cudaMemcpyHostToDevice, ctx->stream));
+    rc = b381_final_exp_batch_dev(ctx, (b381_fp12 *)d, n, (b381_fp12 *)d, (uint8_t *)dok);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, d, n * sizeof(b381_fp12), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ok) CK(cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B381_OK;
+}
+int b381_pairing_product_is_one(b381_ctx *ctx, const b381_g1_affine *p, const b381_g2_affine *q, size_t npairs,
+                                const uint32_t *group_off, size_t ngroups, uint8_t *ok) {
+    if (!ctx || (ngroups && (!group_off || !ok)) || (npairs && (!p || !q))) return B381_ERR_ARG;
+    if (!ngroups) return B381_OK;
+    if (group_off[0] != 0 || group_off[ngroups] != npairs) return B381_ERR_ARG;
+    for (size_t g = 0; g < ngroups; g++) if (group_off[g] > group_off[g + 1]) return B381_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    void *dp = nullptr, *dq = nullptr;
+    int rc = staged_pq(ctx, p, q, npairs ? npairs : 1, &dp, &dq);
+    if (rc) return rc;
+    // offsets and result flags live behind the product scratch (slot 1 is sized by the _dev call)
+    uint32_t *doff = nullptr; uint8_t *dok = nullptr;
+    CK(cudaMalloc(&doff, (ngroups + 1) * sizeof(uint32_t)));
+    cudaError_t e = cudaMalloc(&dok, ngroups);
+    if (e != cudaSuccess) { cudaFree(doff); snprintf(ctx->err, sizeof ctx->err, "cudaMalloc: %s", cudaGetErrorString(e)); return B381_ERR_NOMEM; }
+    rc = B381_OK;
+    do {
+        if (cudaMemcpyAsync(doff, group_off, (ngroups + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = B381_ERR_CUDA; break; }
+        rc = b381_pairing_product_is_one_dev(ctx, (b381_g1_affine *)dp, (b381_g2_affine *)dq, npairs, doff, ngroups, dok);
+        if (rc) break;
+        if (cudaMemcpyAsync(ok, dok, ngroups, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { rc = B381_ERR_CUDA; break; }
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = B381_ERR_CUDA; break; }
+    } while (0);
+    if (rc == B381_ERR_CUDA) snprintf(ctx->err, sizeof ctx->err, "pairing_product_is_one: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(doff); cudaFree(dok);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,237 @@
+// fp.cuh -- BLS12-381 base field Fq on the device: 12 x u32 limbs in registers, Montgomery form
+// (R = 2^384), every value canonical in [0, Q) exactly like the reference keeps it
+// (fq.go:41-45).  Replaces the reference's L0/L1 layers on the hot path:
+//   MultiplyFQRepr + MontReduce (stub_fallback.go:11-116, primitivefuncs_amd64.s) -> fp_mul
+//   FQ.AddAssign/SubAssign/NegAssign/DoubleAssign (fq.go:65-143)                 -> fp_add/...
+//   FQ.Inverse (fq.go:224-266, binary Euclid)        -> fp_inv (Fermat, fixed chain, same value)
+// Memory layout of an element is the reference's FQRepr: 6 x u64 little-endian limbs = 12 x u32.
+//
+// The arithmetic bodies are __host__ __device__: the device path is inline PTX (carry chains that
+// ptxas turns into IMAD.WIDE.U32 + carry); the host path is portable C used ONLY by the CPU unit
+// tests of this logic (tests/emu), never by the product library.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define HD __host__ __device__ __forceinline__
+#define HDN __host__ __device__ __noinline__
+#else
+#define HD inline
+#define HDN __attribute__((noinline))
+#define __align__(n) __attribute__((aligned(n)))
+#endif
+
+#include "fp_mul_asm.inc"
+
+namespace b381 {
+
+struct __align__(16) fp { uint32_t l[12]; };
+
+#define B381_Q_LIMBS                                                                                  \
+    0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu,        \
+        0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau
+// R mod Q = FQOne (fq.go:23)
+#define B381_ONE_LIMBS                                                                                \
+    0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u, 0x70525745u,        \
+        0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u
+
+HD void fp_set_zero(fp &r) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = 0;
+}
+HD void fp_set_one(fp &r) {
+    const uint32_t one[12] = {B381_ONE_LIMBS};
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = one[i];
+}
+HD bool fp_is_zero(const fp &a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) o |= a.l[i];
+    return o == 0;
+}
+HD bool fp_eq(const fp &a, const fp &b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) o |= a.l[i] ^ b.l[i];
+    return o == 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host reference bodies (CPU unit tests of the device logic only)
+// ---------------------------------------------------------------------------------------------
+#if !defined(__CUDA_ARCH__)
+namespace hostimpl {
+static inline void cond_sub_q(uint32_t x[12], uint32_t top) {
+    const uint32_t q[12] = {B381_Q_LIMBS};
+    uint32_t d[12];
+    int64_t br = 0;
+    for (int i = 0; i < 12; i++) {
+        int64_t t = (int64_t)x[i] - q[i] + br;
+        d[i] = (uint32_t)t;
+        br = t >> 32;
+    }
+    if (top || br == 0)
+        for (int i = 0; i < 12; i++) x[i] = d[i];
+}
+static inline void mul(uint32_t r[12], const uint32_t a[12], const uint32_t b[12]) {
+    const uint32_t q[12] = {B381_Q_LIMBS};
+    uint32_t t[14] = {0};
+    for (int i = 0; i < 12; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < 12; j++) {
+            uint64_t v = (uint64_t)a[j] * b[i] + t[j] + c;
+            t[j] = (uint32_t)v; c = v >> 32;
+        }
+        uint64_t v = (uint64_t)t[12] + c;
+        t[12] = (uint32_t)v; t[13] = (uint32_t)(v >> 32);
+        uint32_t m = t[0] * 0xfffcfffdu;
+        c = ((uint64_t)m * q[0] + t[0]) >> 32;
+        for (int j = 1; j < 12; j++) {
+            uint64_t w = (uint64_t)m * q[j] + t[j] + c;
+            t[j - 1] = (uint32_t)w; c = w >> 32;
+        }
+        v = (uint64_t)t[12] + c;
+        t[11] = (uint32_t)v;
+        t[12] = t[13] + (uint32_t)(v >> 32);
+    }
+    for (int i = 0; i < 12; i++) r[i] = t[i];
+    cond_sub_q(r, t[12]);
+}
+}  // namespace hostimpl
+#endif
+
+// r = a + b mod Q   (fq.go:65-68)
+HD void fp_add(fp &r, const fp &a, const fp &b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t s[12], d[12], bw;
+    asm("add.cc.u32 %0, %12, %24;\n\t"
+        "addc.cc.u32 %1, %13, %25;\n\t"
+        "addc.cc.u32 %2, %14, %26;\n\t"
+        "addc.cc.u32 %3, %15, %27;\n\t"
+        "addc.cc.u32 %4, %16, %28;\n\t"
+        "addc.cc.u32 %5, %17, %29;\n\t"
+        "addc.cc.u32 %6, %18, %30;\n\t"
+        "addc.cc.u32 %7, %19, %31;\n\t"
+        "addc.cc.u32 %8, %20, %32;\n\t"
+        "addc.cc.u32 %9, %21, %33;\n\t"
+        "addc.cc.u32 %10, %22, %34;\n\t"
+        "addc.u32 %11, %23, %35;\n\t"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]),
+          "=r"(s[8]), "=r"(s[9]), "=r"(s[10]), "=r"(s[11])
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(a.l[8]), "r"(a.l[9]), "r"(a.l[10]), "r"(a.l[11]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]),
+          "r"(b.l[8]), "r"(b.l[9]), "r"(b.l[10]), "r"(b.l[11]));
+    asm("sub.cc.u32 %0, %13, 0xffffaaab;\n\t"
+        "subc.cc.u32 %1, %14, 0xb9feffff;\n\t"
+        "subc.cc.u32 %2, %15, 0xb153ffff;\n\t"
+        "subc.cc.u32 %3, %16, 0x1eabfffe;\n\t"
+        "subc.cc.u32 %4, %17, 0xf6b0f624;\n\t"
+        "subc.cc.u32 %5, %18, 0x6730d2a0;\n\t"
+        "subc.cc.u32 %6, %19, 0xf38512bf;\n\t"
+        "subc.cc.u32 %7, %20, 0x64774b84;\n\t"
+        "subc.cc.u32 %8, %21, 0x434bacd7;\n\t"
+        "subc.cc.u32 %9, %22, 0x4b1ba7b6;\n\t"
+        "subc.cc.u32 %10, %23, 0x397fe69a;\n\t"
+        "subc.cc.u32 %11, %24, 0x1a0111ea;\n\t"
+        "subc.u32 %12, 0, 0;\n\t"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]),
+          "=r"(d[8]), "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(bw)
+        : "r"(s[0]), "r"(s[1]), "r"(s[2]), "r"(s[3]), "r"(s[4]), "r"(s[5]), "r"(s[6]), "r"(s[7]),
+          "r"(s[8]), "r"(s[9]), "r"(s[10]), "r"(s[11]));
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = bw ? s[i] : d[i];
+#else
+    uint32_t s[12];
+    uint64_t c = 0;
+    for (int i = 0; i < 12; i++) { uint64_t v = (uint64_t)a.l[i] + b.l[i] + c; s[i] = (uint32_t)v; c = v >> 32; }
+    hostimpl::cond_sub_q(s, (uint32_t)c);
+    for (int i = 0; i < 12; i++) r.l[i] = s[i];
+#endif
+}
+
+// r = a - b mod Q   (fq.go:82-87)
+HD void fp_sub(fp &r, const fp &a, const fp &b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t d[12], bw;
+    asm("sub.cc.u32 %0, %13, %25;\n\t"
+        "subc.cc.u32 %1, %14, %26;\n\t"
+        "subc.cc.u32 %2, %15, %27;\n\t"
+        "subc.cc.u32 %3, %16, %28;\n\t"
+        "subc.cc.u32 %4, %17, %29;\n\t"
+        "subc.cc.u32 %5, %18, %30;\n\t"
+        "subc.cc.u32 %6, %19, %31;\n\t"
+        "subc.cc.u32 %7, %20, %32;\n\t"
+        "subc.cc.u32 %8, %21, %33;\n\t"
+        "subc.cc.u32 %9, %22, %34;\n\t"
+        "subc.cc.u32 %10, %23, %35;\n\t"
+        "subc.cc.u32 %11, %24, %36;\n\t"
+        "subc.u32 %12, 0, 0;\n\t"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]),
+          "=r"(d[8]), "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(bw)
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(a.l[8]), "r"(a.l[9]), "r"(a.l[10]), "r"(a.l[11]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]),
+          "r"(b.l[8]), "r"(b.l[9]), "r"(b.l[10]), "r"(b.l[11]));
+    // add Q back under the borrow mask
+    asm("add.cc.u32 %0, %0, %12;\n\t"
+        "addc.cc.u32 %1, %1, %13;\n\t"
+        "addc.cc.u32 %2, %2, %14;\n\t"
+        "addc.cc.u32 %3, %3, %15;\n\t"
+        "addc.cc.u32 %4, %4, %16;\n\t"
+        "addc.cc.u32 %5, %5, %17;\n\t"
+        "addc.cc.u32 %6, %6, %18;\n\t"
+        "addc.cc.u32 %7, %7, %19;\n\t"
+        "addc.cc.u32 %8, %8, %20;\n\t"
+        "addc.cc.u32 %9, %9, %21;\n\t"
+        "addc.cc.u32 %10, %10, %22;\n\t"
+        "addc.u32 %11, %11, %23;\n\t"
+        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]), "+r"(d[4]), "+r"(d[5]), "+r"(d[6]), "+r"(d[7]),
+          "+r"(d[8]), "+r"(d[9]), "+r"(d[10]), "+r"(d[11])
+        : "r"(bw & 0xffffaaabu), "r"(bw & 0xb9feffffu), "r"(bw & 0xb153ffffu), "r"(bw & 0x1eabfffeu),
+          "r"(bw & 0xf6b0f624u), "r"(bw & 0x6730d2a0u), "r"(bw & 0xf38512bfu), "r"(bw & 0x64774b84u),
+          "r"(bw & 0x434bacd7u), "r"(bw & 0x4b1ba7b6u), "r"(bw & 0x397fe69au), "r"(bw & 0x1a0111eau));
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = d[i];
+#else
+    const uint32_t q[12] = {B381_Q_LIMBS};
+    uint32_t d[12];
+    int64_t br = 0;
+    for (int i = 0; i < 12; i++) { int64_t t = (int64_t)a.l[i] - b.l[i] + br; d[i] = (uint32_t)t; br = t >> 32; }
+    if (br) {
+        uint64_t c = 0;
+        for (int i = 0; i < 12; i++) { uint64_t v = (uint64_t)d[i] + q[i] + c; d[i] = (uint32_t)v; c = v >> 32; }
+    }
+    for (int i = 0; i < 12; i++) r.l[i] = d[i];
+#endif
+}
+
+HD void fp_dbl(fp &r, const fp &a) { fp_add(r, a, a); }   // fq.go:140-143
+
+// r = -a mod Q, with -0 = 0   (fq.go:121-127)
+HD void fp_neg(fp &r, const fp &a) {
+    fp z;
+    fp_set_zero(z);
+    fp_sub(r, z, a);   // 0 - a borrows iff a != 0, and then adds Q
+}
+
+// r = a * b * 2^-384 mod Q   (fq.go:76-79)
+HD void fp_mul(fp &r, const fp &a, const fp &b) {
+#if defined(__CUDA_ARCH__)
+    asm(FP_MUL_PTX
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]),
+          "=r"(r.l[7]), "=r"(r.l[8]), "=r"(r.l[9]), "=r"(r.l[10]), "=r"(r.l[11])
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(a.l[8]), "r"(a.l[9]), "r"(a.l[10]), "r"(a.l[11]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]),
+          "r"(b.l[8]), "r"(b.l[9]), "r"(b.l[10]), "r"(b.l[11]));
+#else
+    uint32_t t[12];
+    hostimpl::mul(t, a.l, b.l);
+    for (int i = 0; i < 12; i++) r.l[i] = t[i];
+#endif
+}
+HD void fp_sqr(fp &r, const fp &a) { fp_mul(r, a, a); }   // fq.go:151-198
+
+}  // namespace b381

@@ -1,0 +1,209 @@
+// pairing.cuh -- optimal ate pairing on BLS12-381, one pairing (or one Miller-loop factor) per
+// thread.  Replaces G2AffineToPrepared + MillerLoop + FinalExponentiation (g2.go:634-801,
+// pairing.go:16-129) on the hot path.
+//
+// Differences in schedule, not in values:
+//  * the 68 line-coefficient triples are never stored (the reference materialises 19.6 KB per G2
+//    point, g2.go:774-800): each doubling/addition step feeds its line straight into the sparse
+//    Fq12 multiplication.  The step formulas are the reference's, so the Miller value before the
+//    final exponentiation is bit-identical too.
+//  * ExpByX squares with the cyclotomic formula instead of FQ12.Exp's generic multiply
+//    (fq12.go:108-120); the addition chain (pairing.go:100-128) is unchanged.
+#pragma once
+#include "tower.cuh"
+
+namespace b381 {
+
+// C-ABI PODs (include/b381.h): Go's G1Affine / G2Affine structs incl. padding (g1.go:10-14, g2.go:12-16)
+struct g1_affine_pod { uint64_t x[6], y[6]; uint8_t inf; uint8_t pad[7]; };
+struct g2_affine_pod { uint64_t x[12], y[12]; uint8_t inf; uint8_t pad[7]; };
+
+HD void fp_load_u64(fp &r, const uint64_t *p) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) { uint64_t v = p[i]; r.l[2 * i] = (uint32_t)v; r.l[2 * i + 1] = (uint32_t)(v >> 32); }
+}
+HD void fp_store_u64(uint64_t *p, const fp &a) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) p[i] = (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32);
+}
+
+struct g2_jac { fp2 x, y, z; };
+
+// doubling step of the Miller loop: r <- 2r, line coefficients out   (g2.go:655-708)
+HDN void line_double(g2_jac *r, fp2 *o0, fp2 *o1, fp2 *o2) {
+    fp2 t0, t1, t2, t3, t4, t5, t6, zsq;
+    fp2_sqr(&t0, &r->x);
+    fp2_sqr(&t1, &r->y);
+    fp2_sqr(&t2, &t1);
+    fp2_add(t3, t1, r->x);
+    fp2_sqr(&t3, &t3);
+    fp2_sub(t3, t3, t0);
+    fp2_sub(t3, t3, t2);
+    fp2_dbl(t3, t3);
+    fp2_dbl(t4, t0);
+    fp2_add(t4, t4, t0);
+    fp2_add(t6, r->x, t4);
+    fp2_sqr(&t5, &t4);
+    fp2_sqr(&zsq, &r->z);
+    fp2_sub(r->x, t5, t3);
+    fp2_sub(r->x, r->x, t3);
+    fp2_add(r->z, r->z, r->y);
+    fp2_sqr(&r->z, &r->z);
+    fp2_sub(r->z, r->z, t1);
+    fp2_sub(r->z, r->z, zsq);
+    fp2_sub(r->y, t3, r->x);
+    fp2_mul(&r->y, &r->y, &t4);
+    fp2_dbl(t2, t2); fp2_dbl(t2, t2); fp2_dbl(t2, t2);
+    fp2_sub(r->y, r->y, t2);
+    fp2_mul(&t3, &t4, &zsq);
+    fp2_dbl(t3, t3);
+    fp2_neg(*o1, t3);
+    fp2_sqr(&t6, &t6);
+    fp2_sub(t6, t6, t0);
+    fp2_sub(t6, t6, t5);
+    fp2_dbl(t1, t1); fp2_dbl(t1, t1);
+    fp2_sub(*o2, t6, t1);
+    fp2_mul(&t0, &r->z, &zsq);
+    fp2_dbl(*o0, t0);
+}
+
+// addition step: r <- r + q, line coefficients out   (g2.go:710-772)
+HDN void line_add(g2_jac *r, const fp2 *qx, const fp2 *qy, fp2 *o0, fp2 *o1, fp2 *o2) {
+    fp2 zsq, ysq, t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10;
+    fp2_sqr(&zsq, &r->z);
+    fp2_sqr(&ysq, qy);
+    fp2_mul(&t0, &zsq, qx);
+    fp2_add(t1, *qy, r->z);
+    fp2_sqr(&t1, &t1);
+    fp2_sub(t1, t1, ysq);
+    fp2_sub(t1, t1, zsq);
+    fp2_mul(&t1, &t1, &zsq);
+    fp2_sub(t2, t0, r->x);
+    fp2_sqr(&t3, &t2);
+    fp2_dbl(t4, t3); fp2_dbl(t4, t4);
+    fp2_mul(&t5, &t4, &t2);
+    fp2_sub(t6, t1, r->y);
+    fp2_sub(t6, t6, r->y);
+    fp2_mul(&t9, &t6, qx);
+    fp2_mul(&t7, &t4, &r->x);
+    fp2_sqr(&r->x, &t6);
+    fp2_sub(r->x, r->x, t5);
+    fp2_sub(r->x, r->x, t7);
+    fp2_sub(r->x, r->x, t7);
+    fp2_add(r->z, r->z, t2);
+    fp2_sqr(&r->z, &r->z);
+    fp2_sub(r->z, r->z, zsq);
+    fp2_sub(r->z, r->z, t3);
+    fp2_add(t10, *qy, r->z);
+    fp2_sub(t8, t7, r->x);
+    fp2_mul(&t8, &t8, &t6);
+    fp2_mul(&t0, &r->y, &t5);
+    fp2_dbl(t0, t0);
+    fp2_sub(r->y, t8, t0);
+    fp2_sqr(&t10, &t10);
+    fp2_sub(t10, t10, ysq);
+    fp2_sqr(&zsq, &r->z);
+    fp2_sub(t10, t10, zsq);
+    fp2_dbl(t9, t9);
+    fp2_sub(*o2, t9, t10);
+    fp2_dbl(*o0, r->z);
+    fp2_neg(t6, t6);
+    fp2_dbl(*o1, t6);
+}
+
+// f <- f * line(P)   (the `ell` closure, pairing.go:28-39)
+HD void ell(fp12 *f, fp2 *c0, fp2 *c1, const fp2 *c2, const fp *px, const fp *py) {
+    fp2_mul_fp(c0, c0, py);
+    fp2_mul_fp(c1, c1, px);
+    fp12_mul_by_014(f, c2, c1, c0);
+}
+
+// Miller loop of ONE pair, f_{|x|,Q}(P) conjugated   (pairing.go:16-75 with len(items) == 1).
+// Infinity on either side contributes the factor 1 (the reference panics there).
+HD void miller_loop_one(fp12 *f, const g1_affine_pod *P, const g2_affine_pod *Q) {
+    fp12_set_one(f);
+    if (P->inf || Q->inf) return;
+    fp px, py;
+    fp2 qx, qy;
+    g2_jac r;
+    fp_load_u64(px, P->x); fp_load_u64(py, P->y);
+    fp_load_u64(qx.c0, Q->x); fp_load_u64(qx.c1, Q->x + 6);
+    fp_load_u64(qy.c0, Q->y); fp_load_u64(qy.c1, Q->y + 6);
+    r.x = qx; r.y = qy; fp2_set_one(r.z);
+    fp2 c0, c1, c2;
+    const uint64_t xr = 0xd201000000010000ULL >> 1;   // blsX >> 1, g2.go:634, pairing.go:44-45
+#pragma unroll 1
+    for (int bit = 61; bit >= 0; bit--) {              // the 62 bits below the leading one
+        line_double(&r, &c0, &c1, &c2);
+        ell(f, &c0, &c1, &c2, &px, &py);
+        if ((xr >> bit) & 1) {
+            line_add(&r, &qx, &qy, &c0, &c1, &c2);
+            ell(f, &c0, &c1, &c2, &px, &py);
+        }
+        fp12_sqr(f, f);
+    }
+    line_double(&r, &c0, &c1, &c2);
+    ell(f, &c0, &c1, &c2, &px, &py);
+    fp12_conj(f, f);                                    // blsIsNegative, pairing.go:71-73
+}
+
+// conj(f^x) for f in the cyclotomic subgroup   (ExpByX, pairing.go:92-98)
+HDN void exp_by_x(fp12 *r, const fp12 *f, uint64_t x) {
+    fp12 acc;
+    fp12_copy(&acc, f);
+    int top = 63;
+    while (!((x >> top) & 1)) top--;
+#pragma unroll 1
+    for (int bit = top - 1; bit >= 0; bit--) {
+        fp12_cyclotomic_sqr(&acc, &acc);
+        if ((x >> bit) & 1) fp12_mul(&acc, &acc, f);
+    }
+    fp12_conj(r, &acc);
+}
+
+// FinalExponentiation   (pairing.go:79-129).  Returns false for f == 0 (the reference returns nil).
+HD bool final_exp_one(fp12 *out, const fp12 *in) {
+    const uint64_t X = 0xd201000000010000ULL;
+    fp12 r, y0, y1, y2, y3;
+    fp12_conj(&y0, in);                 // f1
+    if (!fp12_inv(&y1, in)) return false;   // f2
+    fp12_mul(&r, &y0, &y1);
+    fp12_copy(&y1, &r);
+    fp12_frobenius(&r, &r, 2);
+    fp12_mul(&r, &r, &y1);              // r = f^((q^6-1)(q^2+1)), cyclotomic from here on
+    fp12_cyclotomic_sqr(&y0, &r);
+    exp_by_x(&y1, &y0, X);
+    exp_by_x(&y2, &y1, X >> 1);
+    fp12_conj(&y3, &r);
+    fp12_mul(&y1, &y1, &y3);
+    fp12_conj(&y1, &y1);
+    fp12_mul(&y1, &y1, &y2);
+    exp_by_x(&y2, &y1, X);
+    exp_by_x(&y3, &y2, X);
+    fp12_conj(&y1, &y1);
+    fp12_mul(&y3, &y3, &y1);
+    fp12_conj(&y1, &y1);
+    fp12_frobenius(&y1, &y1, 3);
+    fp12_frobenius(&y2, &y2, 2);
+    fp12_mul(&y1, &y1, &y2);
+    exp_by_x(&y2, &y3, X);
+    fp12_mul(&y2, &y2, &y0);
+    fp12_mul(&y2, &y2, &r);
+    fp12_mul(&y1, &y1, &y2);
+    fp12_frobenius(&y3, &y3, 1);
+    fp12_mul(out, &y1, &y3);
+    return true;
+}
+
+HD void fp12_store_u64(uint64_t *dst, const fp12 *a) {
+    const fp *p = &a->c0.c0.c0;
+#pragma unroll 1
+    for (int i = 0; i < 12; i++) { fp x = p[i]; fp_store_u64(dst + 6 * i, x); }
+}
+HD void fp12_load_u64(fp12 *a, const uint64_t *src) {
+    fp *p = &a->c0.c0.c0;
+#pragma unroll 1
+    for (int i = 0; i < 12; i++) { fp x; fp_load_u64(x, src + 6 * i); p[i] = x; }
+}
+
+}  // namespace b381

@@ -1,0 +1,387 @@
+// tower.cuh -- Fq2 = Fq[u]/(u^2+1), Fq6 = Fq2[v]/(v^3-(1+u)), Fq12 = Fq6[w]/(w^2-v) on the device.
+// Replaces the reference's L2 layer on the hot path (fq2.go, fq6.go, fq12.go); every function
+// cites the reference operation whose value it reproduces.  Values are exact field elements in
+// canonical Montgomery form, so any correct formula yields the reference's bits.
+//
+// Layout: elements live in per-thread local memory (L1/L2 resident) as the reference's flattened
+// structs (fq12 = c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2; fq2 = c0 || c1; 48 B per Fq).  Fq2
+// multiplication/squaring are the call granularity: operands are pulled into registers with
+// 128-bit loads, ~900 IMAD.WIDE of work are done on them, and the result is written back.
+#pragma once
+#include "fp.cuh"
+#include "constants.inc"
+
+namespace b381 {
+
+struct fp2 { fp c0, c1; };
+struct fp6 { fp2 c0, c1, c2; };
+struct fp12 { fp6 c0, c1; };
+
+// ---- constant tables -------------------------------------------------------------------------
+#if defined(__CUDACC__)
+__device__ __constant__ uint32_t d_frob6_c1[6 * 24] = B381_FROB6_C1_INIT;
+__device__ __constant__ uint32_t d_frob6_c2[6 * 24] = B381_FROB6_C2_INIT;
+__device__ __constant__ uint32_t d_frob12_c1[12 * 24] = B381_FROB12_C1_INIT;
+__device__ __constant__ uint32_t d_q_minus_2[12] = {B381_Q_MINUS_2_LIMBS};
+#endif
+#if !defined(__CUDA_ARCH__)
+static const uint32_t h_frob6_c1[6 * 24] = B381_FROB6_C1_INIT;
+static const uint32_t h_frob6_c2[6 * 24] = B381_FROB6_C2_INIT;
+static const uint32_t h_frob12_c1[12 * 24] = B381_FROB12_C1_INIT;
+static const uint32_t h_q_minus_2[12] = {B381_Q_MINUS_2_LIMBS};
+#endif
+#if defined(__CUDA_ARCH__)
+#define B381_TAB(name) d_##name
+#else
+#define B381_TAB(name) h_##name
+#endif
+
+HD void fp_load_tab(fp &r, const uint32_t *t) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = t[i];
+}
+
+// ---- Fq out-of-line multiplies (call granularity for Fq-only callers) --------------------------
+HDN void fp_mul_n(fp *r, const fp *a, const fp *b) { fp x = *a, y = *b, z; fp_mul(z, x, y); *r = z; }
+HDN void fp_sqr_n(fp *r, const fp *a) { fp x = *a, z; fp_sqr(z, x); *r = z; }
+
+// a^(Q-2): FQ.Inverse (fq.go:224-266) returns the same canonical value; 0 -> 0 here (the
+// reference returns "no inverse").  Fixed exponent => no divergence inside a warp.
+HDN void fp_inv(fp *r, const fp *a) {
+    fp x = *a, acc;
+    fp_set_one(acc);
+    const uint32_t *e = B381_TAB(q_minus_2);
+    bool started = false;
+#pragma unroll 1
+    for (int i = 380; i >= 0; i--) {
+        if (started) fp_sqr(acc, acc);
+        if ((e[i >> 5] >> (i & 31)) & 1) {
+            if (started) fp_mul(acc, acc, x);
+            else { acc = x; started = true; }
+        }
+    }
+    *r = acc;
+}
+
+// ---- Fq2 (fq2.go) ----------------------------------------------------------------------------
+HD void fp2_add(fp2 &r, const fp2 &a, const fp2 &b) { fp_add(r.c0, a.c0, b.c0); fp_add(r.c1, a.c1, b.c1); }  // fq2.go:104-107
+HD void fp2_sub(fp2 &r, const fp2 &a, const fp2 &b) { fp_sub(r.c0, a.c0, b.c0); fp_sub(r.c1, a.c1, b.c1); }  // fq2.go:110-113
+HD void fp2_dbl(fp2 &r, const fp2 &a) { fp_dbl(r.c0, a.c0); fp_dbl(r.c1, a.c1); }                            // fq2.go:92-95
+HD void fp2_neg(fp2 &r, const fp2 &a) { fp_neg(r.c0, a.c0); fp_neg(r.c1, a.c1); }                            // fq2.go:98-101
+HD void fp2_conj(fp2 &r, const fp2 &a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }
+HD bool fp2_is_zero(const fp2 &a) { return fp_is_zero(a.c0) && fp_is_zero(a.c1); }
+HD bool fp2_eq(const fp2 &a, const fp2 &b) { return fp_eq(a.c0, b.c0) && fp_eq(a.c1, b.c1); }
+HD void fp2_set_zero(fp2 &r) { fp_set_zero(r.c0); fp_set_zero(r.c1); }
+HD void fp2_set_one(fp2 &r) { fp_set_one(r.c0); fp_set_zero(r.c1); }
+// r = a * (1 + u)   (fq2.go:41-45)
+HD void fp2_mul_nr(fp2 &r, const fp2 &a) {
+    fp t0, t1;
+    fp_sub(t0, a.c0, a.c1);
+    fp_add(t1, a.c0, a.c1);
+    r.c0 = t0; r.c1 = t1;
+}
+
+// r = a * b   (fq2.go:116-130; Karatsuba, 3 Fq mul)
+HDN void fp2_mul(fp2 *r, const fp2 *a, const fp2 *b) {
+    fp a0 = a->c0, a1 = a->c1, b0 = b->c0, b1 = b->c1;
+    fp aa, bb, sa, sb, cr;
+    fp_mul(aa, a0, b0);
+    fp_mul(bb, a1, b1);
+    fp_add(sa, a0, a1);
+    fp_add(sb, b0, b1);
+    fp_mul(cr, sa, sb);
+    fp_sub(cr, cr, aa);
+    fp_sub(cr, cr, bb);
+    fp_sub(aa, aa, bb);
+    r->c0 = aa; r->c1 = cr;
+}
+// r = a^2   (fq2.go:75-89; complex squaring, 2 Fq mul)
+HDN void fp2_sqr(fp2 *r, const fp2 *a) {
+    fp a0 = a->c0, a1 = a->c1, s, d, p;
+    fp_add(s, a0, a1);
+    fp_sub(d, a0, a1);
+    fp_mul(p, a0, a1);
+    fp_mul(s, s, d);
+    fp_dbl(p, p);
+    r->c0 = s; r->c1 = p;
+}
+// r = a * s with s in Fq   (the c0.c0/c0.c1 *= p.y scaling of pairing.go:33-36)
+HDN void fp2_mul_fp(fp2 *r, const fp2 *a, const fp *s) {
+    fp a0 = a->c0, a1 = a->c1, k = *s;
+    fp_mul(a0, a0, k);
+    fp_mul(a1, a1, k);
+    r->c0 = a0; r->c1 = a1;
+}
+// r = a^-1, 0 -> 0   (fq2.go:133-147)
+HDN void fp2_inv(fp2 *r, const fp2 *a) {
+    fp t0, t1;
+    fp_sqr_n(&t0, &a->c0);
+    fp_sqr_n(&t1, &a->c1);
+    fp_add(t0, t0, t1);
+    fp_inv(&t0, &t0);
+    fp_mul_n(&r->c0, &a->c0, &t0);
+    fp_mul_n(&t1, &a->c1, &t0);
+    fp_neg(r->c1, t1);
+}
+
+// ---- Fq6 (fq6.go) ------------------------------------------------------------------------------
+HDN void fp6_add(fp6 *r, const fp6 *a, const fp6 *b) {   // fq6.go:123-127
+    const fp *pa = &a->c0.c0, *pb = &b->c0.c0; fp *pr = &r->c0.c0;
+#pragma unroll 1
+    for (int i = 0; i < 6; i++) { fp x = pa[i], y = pb[i]; fp_add(x, x, y); pr[i] = x; }
+}
+HDN void fp6_sub(fp6 *r, const fp6 *a, const fp6 *b) {   // fq6.go:130-134
+    const fp *pa = &a->c0.c0, *pb = &b->c0.c0; fp *pr = &r->c0.c0;
+#pragma unroll 1
+    for (int i = 0; i < 6; i++) { fp x = pa[i], y = pb[i]; fp_sub(x, x, y); pr[i] = x; }
+}
+HDN void fp6_neg(fp6 *r, const fp6 *a) {                  // fq6.go:116-120
+    const fp *pa = &a->c0.c0; fp *pr = &r->c0.c0;
+#pragma unroll 1
+    for (int i = 0; i < 6; i++) { fp x = pa[i]; fp_neg(x, x); pr[i] = x; }
+}
+// r = a * v   (fq6.go:34-37)
+HD void fp6_mul_nr(fp6 *r, const fp6 *a) {
+    fp2 t = a->c2, c0 = a->c0, c1 = a->c1;
+    fp2_mul_nr(t, t);
+    r->c0 = t; r->c1 = c0; r->c2 = c1;
+}
+HD bool fp6_is_zero(const fp6 *a) { return fp2_is_zero(a->c0) && fp2_is_zero(a->c1) && fp2_is_zero(a->c2); }
+
+// r = a * b   (fq6.go:255-292; 6 Fq2 mul)
+HDN void fp6_mul(fp6 *r, const fp6 *a, const fp6 *b) {
+    fp2 v0, v1, v2, s, t, x;
+    fp2_mul(&v0, &a->c0, &b->c0);
+    fp2_mul(&v1, &a->c1, &b->c1);
+    fp2_mul(&v2, &a->c2, &b->c2);
+    // c0 = v0 + xi*((a1+a2)(b1+b2) - v1 - v2)
+    fp2_add(s, a->c1, a->c2);
+    fp2_add(t, b->c1, b->c2);
+    fp2_mul(&x, &s, &t);
+    fp2_sub(x, x, v1);
+    fp2_sub(x, x, v2);
+    fp2_mul_nr(x, x);
+    fp2_add(x, x, v0);
+    // c1 = (a0+a1)(b0+b1) - v0 - v1 + xi*v2
+    fp2 y;
+    fp2_add(s, a->c0, a->c1);
+    fp2_add(t, b->c0, b->c1);
+    fp2_mul(&y, &s, &t);
+    fp2_sub(y, y, v0);
+    fp2_sub(y, y, v1);
+    fp2_mul_nr(s, v2);
+    fp2_add(y, y, s);
+    // c2 = (a0+a2)(b0+b2) - v0 - v2 + v1
+    fp2 z;
+    fp2_add(s, a->c0, a->c2);
+    fp2_add(t, b->c0, b->c2);
+    fp2_mul(&z, &s, &t);
+    fp2_sub(z, z, v0);
+    fp2_sub(z, z, v2);
+    fp2_add(z, z, v1);
+    r->c0 = x; r->c1 = y; r->c2 = z;
+}
+// r = a * (b0 + b1 v)   (fq6.go:60-90; 5 Fq2 mul)
+HDN void fp6_mul_by_01(fp6 *r, const fp6 *a, const fp2 *b0, const fp2 *b1) {
+    fp2 v0, v1, s, t, x, y, z;
+    fp2_mul(&v0, &a->c0, b0);
+    fp2_mul(&v1, &a->c1, b1);
+    // c0 = v0 + xi*((a1+a2)*b1 - v1)
+    fp2_add(s, a->c1, a->c2);
+    fp2_mul(&x, &s, b1);
+    fp2_sub(x, x, v1);
+    fp2_mul_nr(x, x);
+    fp2_add(x, x, v0);
+    // c1 = (a0+a1)(b0+b1) - v0 - v1
+    fp2_add(s, a->c0, a->c1);
+    fp2_add(t, *b0, *b1);
+    fp2_mul(&y, &s, &t);
+    fp2_sub(y, y, v0);
+    fp2_sub(y, y, v1);
+    // c2 = (a0+a2)*b0 - v0 + v1
+    fp2_add(s, a->c0, a->c2);
+    fp2_mul(&z, &s, b0);
+    fp2_sub(z, z, v0);
+    fp2_add(z, z, v1);
+    r->c0 = x; r->c1 = y; r->c2 = z;
+}
+// r = a * (b1 v)   (fq6.go:40-57; 3 Fq2 mul)
+HDN void fp6_mul_by_1(fp6 *r, const fp6 *a, const fp2 *b1) {
+    fp2 x, y, z;
+    fp2_mul(&x, &a->c2, b1);
+    fp2_mul_nr(x, x);
+    fp2_mul(&y, &a->c0, b1);
+    fp2_mul(&z, &a->c1, b1);
+    r->c0 = x; r->c1 = y; r->c2 = z;
+}
+// r = a^-1, 0 -> 0   (fq6.go:295-336)
+HDN void fp6_inv(fp6 *r, const fp6 *a) {
+    fp2 k0, k1, k2, t, u;
+    // k0 = a0^2 - xi*a1*a2
+    fp2_sqr(&k0, &a->c0);
+    fp2_mul(&t, &a->c1, &a->c2);
+    fp2_mul_nr(t, t);
+    fp2_sub(k0, k0, t);
+    // k1 = xi*a2^2 - a0*a1
+    fp2_sqr(&k1, &a->c2);
+    fp2_mul_nr(k1, k1);
+    fp2_mul(&t, &a->c0, &a->c1);
+    fp2_sub(k1, k1, t);
+    // k2 = a1^2 - a0*a2
+    fp2_sqr(&k2, &a->c1);
+    fp2_mul(&t, &a->c0, &a->c2);
+    fp2_sub(k2, k2, t);
+    // t = a0*k0 + xi*(a2*k1 + a1*k2)
+    fp2_mul(&t, &a->c2, &k1);
+    fp2_mul(&u, &a->c1, &k2);
+    fp2_add(t, t, u);
+    fp2_mul_nr(t, t);
+    fp2_mul(&u, &a->c0, &k0);
+    fp2_add(t, t, u);
+    fp2_inv(&t, &t);
+    fp2_mul(&r->c0, &k0, &t);
+    fp2_mul(&r->c1, &k1, &t);
+    fp2_mul(&r->c2, &k2, &t);
+}
+// r = a^(q^power), power in {1,2,3}   (fq6.go:211-218)
+HDN void fp6_frobenius(fp6 *r, const fp6 *a, int power) {
+    fp2 c0 = a->c0, c1 = a->c1, c2 = a->c2, k;
+    if (power & 1) { fp2_conj(c0, c0); fp2_conj(c1, c1); fp2_conj(c2, c2); }   // fq2.go:156-158
+    r->c0 = c0;
+    fp_load_tab(k.c0, B381_TAB(frob6_c1) + power * 24); fp_load_tab(k.c1, B381_TAB(frob6_c1) + power * 24 + 12);
+    fp2_mul(&r->c1, &c1, &k);
+    fp_load_tab(k.c0, B381_TAB(frob6_c2) + power * 24); fp_load_tab(k.c1, B381_TAB(frob6_c2) + power * 24 + 12);
+    fp2_mul(&r->c2, &c2, &k);
+}
+
+// ---- Fq12 (fq12.go) ----------------------------------------------------------------------------
+HD void fp12_set_one(fp12 *r) {
+    fp *p = &r->c0.c0.c0;
+    fp z; fp_set_zero(z);
+#pragma unroll 1
+    for (int i = 1; i < 12; i++) p[i] = z;
+    fp_set_one(z); p[0] = z;
+}
+HD void fp12_copy(fp12 *r, const fp12 *a) {
+    const fp *pa = &a->c0.c0.c0; fp *pr = &r->c0.c0.c0;
+#pragma unroll 1
+    for (int i = 0; i < 12; i++) { fp x = pa[i]; pr[i] = x; }
+}
+HD void fp12_conj(fp12 *r, const fp12 *a) {   // fq12.go:27-29
+    if (r != a) r->c0 = a->c0;
+    fp6_neg(&r->c1, &a->c1);
+}
+HD bool fp12_is_one(const fp12 *a) {           // fq12.go:56-58 against FQ12One
+    const fp *p = &a->c0.c0.c0;
+    fp one; fp_set_one(one);
+    bool ok = fp_eq(p[0], one);
+#pragma unroll 1
+    for (int i = 1; i < 12; i++) ok = ok && fp_is_zero(p[i]);
+    return ok;
+}
+HD bool fp12_is_zero(const fp12 *a) {
+    const fp *p = &a->c0.c0.c0;
+    bool z = true;
+#pragma unroll 1
+    for (int i = 0; i < 12; i++) z = z && fp_is_zero(p[i]);
+    return z;
+}
+// r = a * b   (fq12.go:198-213; 3 Fq6 mul)
+HDN void fp12_mul(fp12 *r, const fp12 *a, const fp12 *b) {
+    fp6 aa, bb, s, t;
+    fp6_mul(&aa, &a->c0, &b->c0);
+    fp6_mul(&bb, &a->c1, &b->c1);
+    fp6_add(&s, &a->c0, &a->c1);
+    fp6_add(&t, &b->c0, &b->c1);
+    fp6_mul(&s, &s, &t);
+    fp6_sub(&s, &s, &aa);
+    fp6_sub(&r->c1, &s, &bb);
+    fp6_mul_nr(&bb, &bb);
+    fp6_add(&r->c0, &bb, &aa);
+}
+// r = a^2   (fq12.go:180-195; complex squaring, 2 Fq6 mul)
+HDN void fp12_sqr(fp12 *r, const fp12 *a) {
+    fp6 ab, s, t;
+    fp6_mul(&ab, &a->c0, &a->c1);
+    fp6_add(&s, &a->c0, &a->c1);
+    fp6_mul_nr(&t, &a->c1);
+    fp6_add(&t, &t, &a->c0);
+    fp6_mul(&s, &s, &t);
+    fp6_sub(&s, &s, &ab);
+    fp6_add(&r->c1, &ab, &ab);
+    fp6_mul_nr(&ab, &ab);
+    fp6_sub(&r->c0, &s, &ab);
+}
+// f *= (d0 + d1 v) + (d4 v) w   (fq12.go:32-47; 13 Fq2 mul)
+HDN void fp12_mul_by_014(fp12 *f, const fp2 *d0, const fp2 *d1, const fp2 *d4) {
+    fp6 aa, bb, s;
+    fp2 o;
+    fp6_mul_by_01(&aa, &f->c0, d0, d1);
+    fp6_mul_by_1(&bb, &f->c1, d4);
+    fp2_add(o, *d1, *d4);
+    fp6_add(&s, &f->c1, &f->c0);
+    fp6_mul_by_01(&s, &s, d0, &o);
+    fp6_sub(&s, &s, &aa);
+    fp6_sub(&f->c1, &s, &bb);
+    fp6_mul_nr(&bb, &bb);
+    fp6_add(&f->c0, &bb, &aa);
+}
+// r = a^-1; returns false (and leaves r untouched) for a == 0   (fq12.go:216-237)
+HDN bool fp12_inv(fp12 *r, const fp12 *a) {
+    fp6 t0, t1;
+    fp6_mul(&t0, &a->c0, &a->c0);
+    fp6_mul(&t1, &a->c1, &a->c1);
+    fp6_mul_nr(&t1, &t1);
+    fp6_sub(&t0, &t0, &t1);
+    if (fp6_is_zero(&t0)) return false;
+    fp6_inv(&t0, &t0);
+    fp6_mul(&t1, &a->c1, &t0);
+    fp6_mul(&r->c0, &a->c0, &t0);
+    fp6_neg(&r->c1, &t1);
+    return true;
+}
+// r = a^(q^power), power in {1,2,3}   (fq12.go:171-177)
+HDN void fp12_frobenius(fp12 *r, const fp12 *a, int power) {
+    fp6_frobenius(&r->c0, &a->c0, power);
+    fp6_frobenius(&r->c1, &a->c1, power);
+    fp2 k;
+    fp_load_tab(k.c0, B381_TAB(frob12_c1) + power * 24); fp_load_tab(k.c1, B381_TAB(frob12_c1) + power * 24 + 12);
+    fp2_mul(&r->c1.c0, &r->c1.c0, &k);
+    fp2_mul(&r->c1.c1, &r->c1.c1, &k);
+    fp2_mul(&r->c1.c2, &r->c1.c2, &k);
+}
+
+// Squaring in the cyclotomic subgroup (Granger-Scott): valid after the easy part of the final
+// exponentiation (pairing.go:80-90).  Same value as fq12.go:180-195 on such inputs at 18 Fq mul
+// instead of 36; the reference squares generically inside FQ12.Exp (fq12.go:108-120).
+HD void fp4_sqr(fp2 &o0, fp2 &o1, const fp2 &a, const fp2 &b) {
+    fp2 t0, t1, s;
+    fp2_sqr(&t0, &a);
+    fp2_sqr(&t1, &b);
+    fp2_add(s, a, b);
+    fp2_sqr(&s, &s);
+    fp2_sub(s, s, t0);
+    fp2_sub(o1, s, t1);          // 2ab
+    fp2_mul_nr(t1, t1);
+    fp2_add(o0, t0, t1);          // a^2 + xi b^2
+}
+HDN void fp12_cyclotomic_sqr(fp12 *r, const fp12 *a) {
+    fp2 t0, t1, t2, t3, z;
+    fp2 z0 = a->c0.c0, z4 = a->c0.c1, z3 = a->c0.c2, z2 = a->c1.c0, z1 = a->c1.c1, z5 = a->c1.c2;
+    // (t0,t1) = fp4sq(z0,z1);  z0' = 3t0 - 2z0;  z1' = 3t1 + 2z1
+    fp4_sqr(t0, t1, z0, z1);
+    fp2_sub(z, t0, z0); fp2_dbl(z, z); fp2_add(r->c0.c0, z, t0);
+    fp2_add(z, t1, z1); fp2_dbl(z, z); fp2_add(r->c1.c1, z, t1);
+    // (t0,t1) = fp4sq(z2,z3); (t2,t3) = fp4sq(z4,z5)
+    fp4_sqr(t0, t1, z2, z3);
+    fp4_sqr(t2, t3, z4, z5);
+    // z4' = 3t0 - 2z4;  z5' = 3t1 + 2z5
+    fp2_sub(z, t0, z4); fp2_dbl(z, z); fp2_add(r->c0.c1, z, t0);
+    fp2_add(z, t1, z5); fp2_dbl(z, z); fp2_add(r->c1.c2, z, t1);
+    // z2' = 3 xi t3 + 2z2;  z3' = 3t2 - 2z3
+    fp2_mul_nr(t3, t3);
+    fp2_add(z, t3, z2); fp2_dbl(z, z); fp2_add(r->c1.c0, z, t3);
+    fp2_sub(z, t2, z3); fp2_dbl(z, z); fp2_add(r->c0.c2, z, t2);
+}
+
+}  // namespace b381

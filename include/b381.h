@@ -1,0 +1,144 @@
+/* b381.h -- C ABI of the B200 BLS12-381 batch-verification engine (libb381.so).
+ *
+ * This is the drop-in boundary for the hot path of phoreproject/bls: the Go packages g1pubs /
+ * g2pubs keep their exported API and forward the pairing / aggregation work here through cgo
+ * (INTEGRATION.md shows the binding).  Each entry point names the reference function(s) it
+ * replaces (file:line under the reference tree).
+ *
+ * Data layout (identical to the reference's in-memory structs, so Go can pass slices without
+ * conversion):
+ *   b381_fp     6 x u64 limbs, least-significant first, Montgomery form R = 2^384, canonical
+ *               in [0, Q)                                   (FQ / FQRepr, fq.go:12-14, fqrepr.go:13-14)
+ *   b381_fp2    c0 || c1                                    (FQ2, fq2.go:13-16)
+ *   b381_fp12   c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2    (FQ12 -> FQ6 -> FQ2, flattened;
+ *               the Go side flattens the two *FQ6 pointers of fq12.go:9-12 before the call)
+ *   b381_g1_affine / b381_g2_affine   x, y, infinity flag + Go's struct padding (g1.go:10-14,
+ *               g2.go:12-16): 104 / 200 bytes
+ *   b381_g1_jac / b381_g2_jac         x, y, z Jacobian, infinity <=> z == 0 (g1.go:252-256,287-289)
+ *   b381_scalar 4 x u64 limbs, least-significant first, canonical integer < r (FRRepr of
+ *               FR.ToRepr(), fr.go:316-329)
+ *
+ * Conventions: every function returns B381_OK (0) or a negative error code and never aborts;
+ * verification outcomes are written to out-parameters.  A ctx is bound to one CUDA device and
+ * may be used by one host thread at a time.  Functions without the _dev suffix take HOST
+ * pointers and do the host<->device copies themselves; _dev functions take DEVICE pointers,
+ * enqueue on the ctx stream and return without synchronising (call b381_sync).
+ * A pair with P or Q at infinity contributes the factor 1 to a Miller product (the reference
+ * panics on such input: pairing.go:17-26, :53-56).
+ */
+#ifndef B381_H
+#define B381_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t l[6]; } b381_fp;
+typedef struct { b381_fp c0, c1; } b381_fp2;
+typedef struct { b381_fp2 c[6]; } b381_fp12;
+typedef struct { b381_fp x, y; uint8_t infinity; uint8_t pad[7]; } b381_g1_affine;
+typedef struct { b381_fp2 x, y; uint8_t infinity; uint8_t pad[7]; } b381_g2_affine;
+typedef struct { b381_fp x, y, z; } b381_g1_jac;
+typedef struct { b381_fp2 x, y, z; } b381_g2_jac;
+typedef struct { uint64_t l[4]; } b381_scalar;
+
+typedef struct b381_ctx b381_ctx;
+
+enum {
+    B381_OK = 0,
+    B381_ERR_ARG = -1,      /* null pointer, bad size, bad group offsets */
+    B381_ERR_CUDA = -2,     /* CUDA runtime error; see b381_last_error */
+    B381_ERR_NOMEM = -3,    /* device or host allocation failed */
+    B381_ERR_NO_DEVICE = -4 /* no usable CUDA device: there is no CPU fallback */
+};
+
+/* ---- context --------------------------------------------------------------------------------- */
+int b381_init(int device, b381_ctx **out);
+void b381_free(b381_ctx *ctx);
+const char *b381_last_error(const b381_ctx *ctx);
+/* run on an existing cudaStream_t (e.g. the caller's framework stream); NULL = the ctx's own stream */
+int b381_set_stream(b381_ctx *ctx, void *cuda_stream);
+int b381_sync(b381_ctx *ctx);
+/* number of kernels this ctx has launched so far */
+uint64_t b381_launch_count(const b381_ctx *ctx);
+
+/* device buffers for callers without their own CUDA runtime (resident public-key tables) */
+int b381_dev_alloc(b381_ctx *ctx, size_t bytes, void **dptr);
+int b381_dev_free(b381_ctx *ctx, void *dptr);
+int b381_h2d(b381_ctx *ctx, void *dptr, const void *host, size_t bytes);
+int b381_d2h(b381_ctx *ctx, void *host, const void *dptr, size_t bytes);
+
+/* ---- pairing --------------------------------------------------------------------------------- */
+/* out[i] = bls.Pairing(p[i], q[i])                                        (pairing.go:132-136) */
+int b381_pairing_batch(b381_ctx *ctx, const b381_g1_affine *p, const b381_g2_affine *q, size_t n,
+                       b381_fp12 *out);
+int b381_pairing_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_affine *d_q,
+                           size_t n, b381_fp12 *d_out);
+/* out[i] = bls.MillerLoop({p[i], G2AffineToPrepared(q[i])})        (pairing.go:16-75, g2.go:650-801) */
+int b381_miller_loop_batch(b381_ctx *ctx, const b381_g1_affine *p, const b381_g2_affine *q, size_t n,
+                           b381_fp12 *out);
+int b381_miller_loop_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_affine *d_q,
+                               size_t n, b381_fp12 *d_out);
+/* out[i] = bls.FinalExponentiation(in[i]); ok[i] = 0 where the reference returns nil (in[i] == 0),
+ * out[i] is then 1                                                         (pairing.go:79-129) */
+int b381_final_exp_batch(b381_ctx *ctx, const b381_fp12 *in, size_t n, b381_fp12 *out, uint8_t *ok);
+int b381_final_exp_batch_dev(b381_ctx *ctx, const b381_fp12 *d_in, size_t n, b381_fp12 *d_out,
+                             uint8_t *d_ok);
+/* Generalised bls.CompareTwoPairings (pairing.go:140-147): for every group g,
+ *   ok[g] = FinalExponentiation(prod_{i in [group_off[g], group_off[g+1])} MillerLoop(p[i], q[i])) == 1.
+ * group_off has ngroups+1 non-decreasing entries, group_off[0] == 0, group_off[ngroups] == npairs.
+ * CompareTwoPairings(P1,Q1,P2,Q2) is the group {(P1,Q1), (-P2,Q2)}; g1pubs.Verify
+ * (g1pubs/bls.go:165-168) is the group {(G1One, sig), (-pub, H(m))}; VerifyAggregate
+ * (g1pubs/bls.go:252-282) is one group of n+1 pairs.                                           */
+int b381_pairing_product_is_one(b381_ctx *ctx, const b381_g1_affine *p, const b381_g2_affine *q,
+                                size_t npairs, const uint32_t *group_off, size_t ngroups, uint8_t *ok);
+int b381_pairing_product_is_one_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_affine *d_q,
+                                    size_t npairs, const uint32_t *d_group_off, size_t ngroups,
+                                    uint8_t *d_ok);
+
+/* ---- aggregation ----------------------------------------------------------------------------- */
+/* out = sum of n affine G1 points == AggregatePublicKeys (g1pubs/bls.go:192-198) /
+ * g2pubs.AggregateSignatures (g2pubs/bls.go:165-177).  The result is returned normalised
+ * (z = 1, or the canonical zero (0,1,0) of g1.go:269): it Equal()s the reference's fold, whose
+ * Jacobian coordinates depend on the order of additions.                                       */
+int b381_g1_sum(b381_ctx *ctx, const b381_g1_affine *p, size_t n, b381_g1_jac *out);
+int b381_g1_sum_dev(b381_ctx *ctx, const b381_g1_affine *d_p, size_t n, b381_g1_jac *d_out);
+/* same over G2 == g1pubs.AggregateSignatures (g1pubs/bls.go:177-183) / g2pubs.AggregatePublicKeys */
+int b381_g2_sum(b381_ctx *ctx, const b381_g2_affine *p, size_t n, b381_g2_jac *out);
+int b381_g2_sum_dev(b381_ctx *ctx, const b381_g2_affine *d_p, size_t n, b381_g2_jac *d_out);
+/* out = sum_i k[i] * p[i]  (Pippenger bucket method).  The reference has no MSM; this equals the
+ * fold of G1Affine.MulFR (g1.go:80-90) results with G1Projective.Add (g1.go:400-482), normalised
+ * as above.                                                                                    */
+int b381_g1_msm(b381_ctx *ctx, const b381_g1_affine *p, const b381_scalar *k, size_t n, b381_g1_jac *out);
+int b381_g1_msm_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_scalar *d_k, size_t n,
+                    b381_g1_jac *d_out);
+/* Bucket-sharded MSM for multi-GPU (one process per GPU): this rank accumulates only the windows
+ * w with w % nranks == rank and writes its partial sum (Jacobian, already weighted by 2^(c*w)) to
+ * *d_partial.  The caller all-gathers the nranks partials and folds them with b381_g1_fold_dev.  */
+int b381_g1_msm_shard_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_scalar *d_k, size_t n,
+                          int rank, int nranks, b381_g1_jac *d_partial);
+/* out = normalised sum of n Jacobian points (G1Projective.Add fold, g1.go:400-482) */
+int b381_g1_fold_dev(b381_ctx *ctx, const b381_g1_jac *d_parts, size_t n, b381_g1_jac *d_out);
+
+/* ---- signature-scheme glue ------------------------------------------------------------------- */
+/* Batch of g1pubs VerifyAggregateCommon (g1pubs/bls.go:287-290) over a resident key registry:
+ * attestation a uses public keys registry[key_idx[key_off[a] .. key_off[a+1])], the aggregate
+ * signature sig[a] and the pre-hashed message point msg_hash[msg_idx[a]] (= HashG2(m) /
+ * HashG2WithDomain(m, d), computed by the Go host).  ok[a] = e(G1One, sig[a]) == e(sum pk, H(m)). */
+int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_registry,
+                                           const uint32_t *d_key_idx, const uint32_t *d_key_off,
+                                           const b381_g2_affine *d_sig, const b381_g2_affine *d_msg_hash,
+                                           const uint32_t *d_msg_idx, size_t nattest, uint8_t *d_ok);
+
+/* ---- measurement -------------------------------------------------------------------------------- */
+/* Integer-pipe roofline probe: launches blocks x threads threads that each issue iters * 8
+ * independent IMAD.WIDE.U32 (the 32x32->64 multiply-accumulate an Fq multiplication is made of).
+ * d_out needs blocks*threads u32.  Time it with events on the ctx stream.                        */
+int b381_imad_probe_dev(b381_ctx *ctx, uint32_t *d_out, int blocks, int threads, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B381_H */

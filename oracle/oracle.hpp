@@ -25,7 +25,7 @@ typedef uint64_t u64;
 typedef unsigned __int128 u128;
 
 // per-thread count of Fq multiplications + squarings (SURVEY.md section 8d unit of work)
-extern thread_local u64 g_fq_mul_count;
+extern thread_local u64 g_fq_mul_count __attribute__((tls_model("initial-exec")));
 
 // ---------------------------------------------------------------------------
 // L0 limb primitives -- stub_fallback.go:11-155

@@ -6,7 +6,7 @@
 
 namespace orc {
 
-thread_local u64 g_fq_mul_count = 0;
+thread_local u64 g_fq_mul_count __attribute__((tls_model("initial-exec"))) = 0;
 
 // ---------------------------------------------------------------------------
 // Repr helpers

@@ -57,11 +57,12 @@ def cpu_baseline(threads, target_s, P, Q):
     """time the oracle's bls.Pairing on `threads` host threads for about target_s seconds"""
     from oracle import pyoracle as orc
     m = min(P.size, 1024)
-    probe = max(threads, 8)
-    t = orc.time_pairings(P[:m], Q[:m], probe, threads)
-    per = t / probe * threads            # seconds per pairing per thread
-    n = max(threads, int(target_s / per) // threads * threads)
-    t = orc.time_pairings(P[:m], Q[:m], n, threads)
+    n, t = 0, 0.0
+    chunk = 16 * threads
+    orc.time_pairings(P[:m], Q[:m], threads, threads)      # spin the threads up
+    while t < target_s:
+        t += orc.time_pairings(P[:m], Q[:m], chunk, threads)
+        n += chunk
     return n / t, n, t
 
 

@@ -74,7 +74,11 @@ class Ctx:
 
     # -- plumbing ---------------------------------------------------------------------------
     def set_stream(self, cuda_stream_handle):
+        """launch on this cudaStream_t (0 = the legacy default stream, e.g. torch's default stream)"""
         self.call("b381_set_stream", ctypes.c_void_p(cuda_stream_handle or 0))
+
+    def use_own_stream(self):
+        self.call("b381_use_own_stream")
 
     def sync(self):
         self.call("b381_sync")

@@ -172,7 +172,12 @@ const char *b381_last_error(const b381_ctx *ctx) { return ctx ? ctx->err : "null
 
 int b381_set_stream(b381_ctx *ctx, void *cuda_stream) {
     if (!ctx) return B381_ERR_ARG;
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;   // NULL is the legacy default stream, as everywhere in CUDA
+    return B381_OK;
+}
+int b381_use_own_stream(b381_ctx *ctx) {
+    if (!ctx) return B381_ERR_ARG;
+    ctx->stream = ctx->own_stream;
     return B381_OK;
 }
 int b381_sync(b381_ctx *ctx) {

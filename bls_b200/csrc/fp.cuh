@@ -11,6 +11,7 @@
 // tests of this logic (tests/emu), never by the product library.
 #pragma once
 #include <stdint.h>
+#include <stddef.h>
 
 #if defined(__CUDACC__)
 #define HD __host__ __device__ __forceinline__

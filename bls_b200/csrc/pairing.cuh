@@ -14,19 +14,6 @@
 
 namespace b381 {
 
-// C-ABI PODs (include/b381.h): Go's G1Affine / G2Affine structs incl. padding (g1.go:10-14, g2.go:12-16)
-struct g1_affine_pod { uint64_t x[6], y[6]; uint8_t inf; uint8_t pad[7]; };
-struct g2_affine_pod { uint64_t x[12], y[12]; uint8_t inf; uint8_t pad[7]; };
-
-HD void fp_load_u64(fp &r, const uint64_t *p) {
-#pragma unroll
-    for (int i = 0; i < 6; i++) { uint64_t v = p[i]; r.l[2 * i] = (uint32_t)v; r.l[2 * i + 1] = (uint32_t)(v >> 32); }
-}
-HD void fp_store_u64(uint64_t *p, const fp &a) {
-#pragma unroll
-    for (int i = 0; i < 6; i++) p[i] = (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32);
-}
-
 struct g2_jac { fp2 x, y, z; };
 
 // doubling step of the Miller loop: r <- 2r, line coefficients out   (g2.go:655-708)

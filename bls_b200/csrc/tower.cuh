@@ -17,6 +17,22 @@ struct fp2 { fp c0, c1; };
 struct fp6 { fp2 c0, c1, c2; };
 struct fp12 { fp6 c0, c1; };
 
+// C-ABI PODs (include/b381.h): Go's G1Affine / G2Affine structs incl. padding (g1.go:10-14, g2.go:12-16)
+struct g1_affine_pod { uint64_t x[6], y[6]; uint8_t inf; uint8_t pad[7]; };
+struct g2_affine_pod { uint64_t x[12], y[12]; uint8_t inf; uint8_t pad[7]; };
+
+HD void fp_load_u64(fp &r, const uint64_t *p) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) { uint64_t v = p[i]; r.l[2 * i] = (uint32_t)v; r.l[2 * i + 1] = (uint32_t)(v >> 32); }
+}
+HD void fp_store_u64(uint64_t *p, const fp &a) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) p[i] = (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32);
+}
+
+struct g1_jac_pod { uint64_t x[6], y[6], z[6]; };
+struct g2_jac_pod { uint64_t x[12], y[12], z[12]; };
+
 // ---- constant tables -------------------------------------------------------------------------
 #if defined(__CUDACC__)
 __device__ __constant__ uint32_t d_frob6_c1[6 * 24] = B381_FROB6_C1_INIT;

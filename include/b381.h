@@ -58,8 +58,10 @@ enum {
 int b381_init(int device, b381_ctx **out);
 void b381_free(b381_ctx *ctx);
 const char *b381_last_error(const b381_ctx *ctx);
-/* run on an existing cudaStream_t (e.g. the caller's framework stream); NULL = the ctx's own stream */
+/* run on an existing cudaStream_t (e.g. the caller's framework stream; NULL = CUDA's legacy default
+ * stream); b381_use_own_stream returns to the non-blocking stream the ctx created in b381_init */
 int b381_set_stream(b381_ctx *ctx, void *cuda_stream);
+int b381_use_own_stream(b381_ctx *ctx);
 int b381_sync(b381_ctx *ctx);
 /* number of kernels this ctx has launched so far */
 uint64_t b381_launch_count(const b381_ctx *ctx);

@@ -11,7 +11,7 @@ import numpy as np
 from . import layout as L
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb381.so")
+LIB_PATH = os.environ.get("B381_LIB") or os.path.join(_HERE, "libb381.so")   # B381_LIB: A/B builds of the same ABI
 
 B381_OK = 0
 ERRORS = {-1: "B381_ERR_ARG", -2: "B381_ERR_CUDA", -3: "B381_ERR_NOMEM", -4: "B381_ERR_NO_DEVICE"}

@@ -217,8 +217,8 @@ HD void fp_neg(fp &r, const fp &a) {
     fp_sub(r, z, a);   // 0 - a borrows iff a != 0, and then adds Q
 }
 
-// r = a * b * 2^-384 mod Q   (fq.go:76-79)
-HD void fp_mul(fp &r, const fp &a, const fp &b) {
+// r = a * b * 2^-384 mod Q   (fq.go:76-79) -- fully inlined body (~300 IMAD.WIDE.U32[.X])
+HD void fp_mul_inl(fp &r, const fp &a, const fp &b) {
 #if defined(__CUDA_ARCH__)
     asm(FP_MUL_PTX
         : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]),
@@ -233,6 +233,12 @@ HD void fp_mul(fp &r, const fp &a, const fp &b) {
     for (int i = 0; i < 12; i++) r.l[i] = t[i];
 #endif
 }
-HD void fp_sqr(fp &r, const fp &a) { fp_mul(r, a, a); }   // fq.go:151-198
+// Out-of-line multiply with BY-VALUE operands: nvcc's device ABI passes the 2 x 12 limbs and the
+// result in registers (no local-memory traffic), so every caller shares one 5 KB copy of the
+// multiplication -- the instruction footprint of the tower stays inside the 32 KB L1.5 I-cache
+// (profiles/r01_v1_ncu_summary.md: `no_instruction` was the top stall with the body inlined).
+HDN fp fp_mul_v(fp a, fp b) { fp r; fp_mul_inl(r, a, b); return r; }
+HD void fp_mul(fp &r, const fp &a, const fp &b) { r = fp_mul_v(a, b); }
+HD void fp_sqr(fp &r, const fp &a) { r = fp_mul_v(a, a); }   // fq.go:151-198
 
 }  // namespace b381

@@ -57,9 +57,28 @@ HD void fp_load_tab(fp &r, const uint32_t *t) {
     for (int i = 0; i < 12; i++) r.l[i] = t[i];
 }
 
-// ---- Fq out-of-line multiplies (call granularity for Fq-only callers) --------------------------
-HDN void fp_mul_n(fp *r, const fp *a, const fp *b) { fp x = *a, y = *b, z; fp_mul(z, x, y); *r = z; }
-HDN void fp_sqr_n(fp *r, const fp *a) { fp x = *a, z; fp_sqr(z, x); *r = z; }
+// ---- pointer forms (kept for callers that hold operands in memory) -------------------------------
+HD void fp_mul_n(fp *r, const fp *a, const fp *b) { *r = fp_mul_v(*a, *b); }
+HD void fp_sqr_n(fp *r, const fp *a) { fp x = *a; *r = fp_mul_v(x, x); }
+
+// ---- vector forms of the cheap operations: one out-of-line loop serves Fq2 (n=2), Fq6 (n=6) and
+// Fq12 (n=12) callers, so an addition costs a call instead of 37 inlined instructions per Fq ------
+HDN void fpv_add(fp *r, const fp *a, const fp *b, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) { fp x = a[i], y = b[i]; fp_add(x, x, y); r[i] = x; }
+}
+HDN void fpv_sub(fp *r, const fp *a, const fp *b, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) { fp x = a[i], y = b[i]; fp_sub(x, x, y); r[i] = x; }
+}
+HDN void fpv_dbl(fp *r, const fp *a, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) { fp x = a[i]; fp_add(x, x, x); r[i] = x; }
+}
+HDN void fpv_neg(fp *r, const fp *a, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) { fp x = a[i]; fp_neg(x, x); r[i] = x; }
+}
 
 // a^(Q-2): FQ.Inverse (fq.go:224-266) returns the same canonical value; 0 -> 0 here (the
 // reference returns "no inverse").  Fixed exponent => no divergence inside a warp.
@@ -80,22 +99,23 @@ HDN void fp_inv(fp *r, const fp *a) {
 }
 
 // ---- Fq2 (fq2.go) ----------------------------------------------------------------------------
-HD void fp2_add(fp2 &r, const fp2 &a, const fp2 &b) { fp_add(r.c0, a.c0, b.c0); fp_add(r.c1, a.c1, b.c1); }  // fq2.go:104-107
-HD void fp2_sub(fp2 &r, const fp2 &a, const fp2 &b) { fp_sub(r.c0, a.c0, b.c0); fp_sub(r.c1, a.c1, b.c1); }  // fq2.go:110-113
-HD void fp2_dbl(fp2 &r, const fp2 &a) { fp_dbl(r.c0, a.c0); fp_dbl(r.c1, a.c1); }                            // fq2.go:92-95
-HD void fp2_neg(fp2 &r, const fp2 &a) { fp_neg(r.c0, a.c0); fp_neg(r.c1, a.c1); }                            // fq2.go:98-101
+HD void fp2_add(fp2 &r, const fp2 &a, const fp2 &b) { fpv_add(&r.c0, &a.c0, &b.c0, 2); }  // fq2.go:104-107
+HD void fp2_sub(fp2 &r, const fp2 &a, const fp2 &b) { fpv_sub(&r.c0, &a.c0, &b.c0, 2); }  // fq2.go:110-113
+HD void fp2_dbl(fp2 &r, const fp2 &a) { fpv_dbl(&r.c0, &a.c0, 2); }                       // fq2.go:92-95
+HD void fp2_neg(fp2 &r, const fp2 &a) { fpv_neg(&r.c0, &a.c0, 2); }                       // fq2.go:98-101
 HD void fp2_conj(fp2 &r, const fp2 &a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }
 HD bool fp2_is_zero(const fp2 &a) { return fp_is_zero(a.c0) && fp_is_zero(a.c1); }
 HD bool fp2_eq(const fp2 &a, const fp2 &b) { return fp_eq(a.c0, b.c0) && fp_eq(a.c1, b.c1); }
 HD void fp2_set_zero(fp2 &r) { fp_set_zero(r.c0); fp_set_zero(r.c1); }
 HD void fp2_set_one(fp2 &r) { fp_set_one(r.c0); fp_set_zero(r.c1); }
 // r = a * (1 + u)   (fq2.go:41-45)
-HD void fp2_mul_nr(fp2 &r, const fp2 &a) {
-    fp t0, t1;
-    fp_sub(t0, a.c0, a.c1);
-    fp_add(t1, a.c0, a.c1);
-    r.c0 = t0; r.c1 = t1;
+HDN void fp2_mul_nr_p(fp2 *r, const fp2 *a) {
+    fp a0 = a->c0, a1 = a->c1, t0, t1;
+    fp_sub(t0, a0, a1);
+    fp_add(t1, a0, a1);
+    r->c0 = t0; r->c1 = t1;
 }
+HD void fp2_mul_nr(fp2 &r, const fp2 &a) { fp2_mul_nr_p(&r, &a); }
 
 // r = a * b   (fq2.go:116-130; Karatsuba, 3 Fq mul)
 HDN void fp2_mul(fp2 *r, const fp2 *a, const fp2 *b) {
@@ -141,21 +161,9 @@ HDN void fp2_inv(fp2 *r, const fp2 *a) {
 }
 
 // ---- Fq6 (fq6.go) ------------------------------------------------------------------------------
-HDN void fp6_add(fp6 *r, const fp6 *a, const fp6 *b) {   // fq6.go:123-127
-    const fp *pa = &a->c0.c0, *pb = &b->c0.c0; fp *pr = &r->c0.c0;
-#pragma unroll 1
-    for (int i = 0; i < 6; i++) { fp x = pa[i], y = pb[i]; fp_add(x, x, y); pr[i] = x; }
-}
-HDN void fp6_sub(fp6 *r, const fp6 *a, const fp6 *b) {   // fq6.go:130-134
-    const fp *pa = &a->c0.c0, *pb = &b->c0.c0; fp *pr = &r->c0.c0;
-#pragma unroll 1
-    for (int i = 0; i < 6; i++) { fp x = pa[i], y = pb[i]; fp_sub(x, x, y); pr[i] = x; }
-}
-HDN void fp6_neg(fp6 *r, const fp6 *a) {                  // fq6.go:116-120
-    const fp *pa = &a->c0.c0; fp *pr = &r->c0.c0;
-#pragma unroll 1
-    for (int i = 0; i < 6; i++) { fp x = pa[i]; fp_neg(x, x); pr[i] = x; }
-}
+HD void fp6_add(fp6 *r, const fp6 *a, const fp6 *b) { fpv_add(&r->c0.c0, &a->c0.c0, &b->c0.c0, 6); }   // fq6.go:123-127
+HD void fp6_sub(fp6 *r, const fp6 *a, const fp6 *b) { fpv_sub(&r->c0.c0, &a->c0.c0, &b->c0.c0, 6); }   // fq6.go:130-134
+HD void fp6_neg(fp6 *r, const fp6 *a) { fpv_neg(&r->c0.c0, &a->c0.c0, 6); }                  // fq6.go:116-120
 // r = a * v   (fq6.go:34-37)
 HD void fp6_mul_nr(fp6 *r, const fp6 *a) {
     fp2 t = a->c2, c0 = a->c0, c1 = a->c1;

@@ -133,7 +133,72 @@ class Ctx:
         self.call("b381_g1_msm", _hp(p), _hp(k), ctypes.c_size_t(p.size), _hp(out))
         return out
 
+    def g1_msm_shard(self, p, k, rank, nranks):
+        """this rank's bucket-sharded partial (Jacobian, not normalised) -- b381_g1_msm_shard_dev"""
+        p = np.ascontiguousarray(p, dtype=L.G1_AFFINE); k = np.ascontiguousarray(k, dtype=np.uint64).reshape(-1, 4)
+        dp, dk, do = self.to_device(p), self.to_device(k), self.dev_empty(L.G1_JAC.itemsize)
+        self.call("b381_g1_msm_shard_dev", dp.ptr, dk.ptr, ctypes.c_size_t(p.size), int(rank), int(nranks), do.ptr)
+        return self.from_device(do, L.G1_JAC, 1)
+
+    def g1_fold(self, parts):
+        """normalised sum of Jacobian points -- b381_g1_fold_dev"""
+        parts = np.ascontiguousarray(parts, dtype=L.G1_JAC)
+        dp, do = self.to_device(parts), self.dev_empty(L.G1_JAC.itemsize)
+        self.call("b381_g1_fold_dev", dp.ptr, ctypes.c_size_t(parts.size), do.ptr)
+        return self.from_device(do, L.G1_JAC, 1)
+
+    def verify_aggregate_common_batch(self, registry, key_idx, key_off, sig, msg_hash, msg_idx):
+        """ok[a] for a batch of VerifyAggregateCommon checks -- b381_verify_aggregate_common_batch_dev"""
+        registry = np.ascontiguousarray(registry, dtype=L.G1_AFFINE)
+        key_idx = np.ascontiguousarray(key_idx, dtype=np.uint32); key_off = np.ascontiguousarray(key_off, dtype=np.uint32)
+        sig = np.ascontiguousarray(sig, dtype=L.G2_AFFINE); msg_hash = np.ascontiguousarray(msg_hash, dtype=L.G2_AFFINE)
+        msg_idx = np.ascontiguousarray(msg_idx, dtype=np.uint32)
+        n = sig.size
+        assert key_off.size == n + 1 and msg_idx.size == n
+        bufs = [self.to_device(a) for a in (registry, key_idx, key_off, sig, msg_hash, msg_idx)]
+        dok = self.dev_empty(max(n, 1))
+        self.call("b381_verify_aggregate_common_batch_dev", *[b.ptr for b in bufs], ctypes.c_size_t(n), dok.ptr)
+        return self.from_device(dok, np.uint8, n)
+
+    # -- raw device buffers owned by the engine (b381_dev_alloc / b381_h2d / b381_d2h) ----------
+    def dev_empty(self, nbytes):
+        return DevBuf(self, nbytes)
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        b = DevBuf(self, arr.nbytes)
+        if arr.nbytes:
+            self.call("b381_h2d", b.ptr, _hp(arr), ctypes.c_size_t(arr.nbytes))
+        b.keep = arr          # the copy is asynchronous: keep the source alive with the buffer
+        return b
+
+    def from_device(self, buf, dtype, count):
+        out = np.empty(count, dtype=dtype)
+        if out.nbytes:
+            self.call("b381_d2h", _hp(out), buf.ptr, ctypes.c_size_t(out.nbytes))   # synchronises the stream
+        else:
+            self.sync()
+        return out
+
     # -- device-pointer entry points (ints are raw device addresses, e.g. torch .data_ptr()) --
     def dev(self, name, *args):
         conv = [ctypes.c_void_p(a) if isinstance(a, int) and not isinstance(a, bool) and a > 0xFFFF else a for a in args]
         self.call(name, *conv)
+
+
+class DevBuf:
+    """device allocation made through the C ABI (b381_dev_alloc); freed with the object"""
+
+    def __init__(self, ctx, nbytes):
+        self.ctx = ctx
+        self.nbytes = int(nbytes)
+        self.ptr = ctypes.c_void_p()
+        self.keep = None
+        ctx.call("b381_dev_alloc", ctypes.c_size_t(max(self.nbytes, 1)), ctypes.byref(self.ptr))
+
+    def __del__(self):
+        try:
+            if self.ptr and self.ctx._h:
+                self.ctx.lib.b381_dev_free(self.ctx._h, self.ptr)
+        except Exception:
+            pass

@@ -1,0 +1,286 @@
+// agg.cuh -- aggregation kernels: point sums (AggregatePublicKeys / AggregateSignatures,
+// g1pubs/bls.go:177-204), the Pippenger bucket MSM the north star adds for weighted aggregates,
+// and the per-attestation public-key aggregation of the VerifyAggregateCommon batch
+// (g1pubs/bls.go:287-290).  The reference folds serially with G1Projective.Add (g1.go:400-482);
+// here every stage is a data-parallel pass over HBM-resident arrays:
+//
+//   sum      : grid-stride mixed additions per thread -> shared-memory tree per block -> one block
+//   MSM      : digit histogram -> per-window exclusive scan -> scatter of point indices by bucket
+//              (a counting sort; 4 B per point per window) -> fixed-size CHUNK partial sums (one
+//              thread per chunk, so a bucket holding every point costs the same as a uniform
+//              spread) -> in-bucket chunk tree -> running-sum segments -> window sums -> Horner
+//
+// Only canonical results (normalised points) cross the ABI, so the order of additions -- which
+// differs from the reference's left fold -- is not observable.
+#pragma once
+#include "curve.cuh"
+
+namespace b381 {
+
+#if defined(__CUDACC__)
+
+#define MSM_CHUNK 64u       // points per chunk partial sum
+#define MSM_SEG 16u         // buckets per running-sum segment
+
+// ---- block tree over shared memory: the sum of every thread's acc ends up in thread 0 -------------
+template <class F, int BLOCK> __device__ void block_reduce_xyzz(xyzz<F> &acc, xyzz<F> *sm) {
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+#pragma unroll 1
+    for (int s = BLOCK / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            xyzz<F> a = sm[threadIdx.x];
+            xyzz_add(a, sm[threadIdx.x + s]);
+            sm[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    acc = sm[0];
+}
+
+// partial[b] = sum of the points this block strides over
+template <class F, class APOD, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_sum_partial(const APOD *__restrict__ p, size_t n, xyzz<F> *__restrict__ partial) {
+    __shared__ xyzz<F> sm[BLOCK];
+    xyzz<F> acc;
+    xyzz_set_inf(acc);
+    size_t stride = (size_t)gridDim.x * BLOCK;
+    for (size_t i = (size_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += stride) {
+        typename F::T x, y; bool inf;
+        load_affine(x, y, inf, p + i);
+        if (!inf) xyzz_madd(acc, x, y);
+    }
+    block_reduce_xyzz<F, BLOCK>(acc, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+// out = normalised sum of m partials (one block)
+template <class F, class JPOD, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_sum_final(const xyzz<F> *__restrict__ partial, int m, JPOD *__restrict__ out) {
+    __shared__ xyzz<F> sm[BLOCK];
+    xyzz<F> acc;
+    xyzz_set_inf(acc);
+    for (int i = threadIdx.x; i < m; i += BLOCK) { xyzz<F> q = partial[i]; xyzz_add(acc, q); }
+    block_reduce_xyzz<F, BLOCK>(acc, sm);
+    if (threadIdx.x == 0) {
+        typename F::T ox, oy, oz;
+        xyzz_to_jac_normalised(ox, oy, oz, acc);
+        store_jac(out, ox, oy, oz);
+    }
+}
+
+// out = normalised sum of n Jacobian points (the all-gathered per-rank MSM partials)
+__global__ void __launch_bounds__(128) k_g1_fold(const g1_jac_pod *__restrict__ parts, size_t n, g1_jac_pod *__restrict__ out) {
+    __shared__ xyzz<FpInl> sm[128];
+    xyzz<FpInl> acc;
+    xyzz_set_inf(acc);
+    for (size_t i = threadIdx.x; i < n; i += 128) {
+        fp x, y, z;
+        load_jac(x, y, z, parts + i);
+        xyzz<FpInl> q;
+        xyzz_from_jac(q, x, y, z);
+        xyzz_add(acc, q);
+    }
+    block_reduce_xyzz<FpInl, 128>(acc, sm);
+    if (threadIdx.x == 0) {
+        fp ox, oy, oz;
+        xyzz_to_jac_normalised(ox, oy, oz, acc);
+        store_jac(out, ox, oy, oz);
+    }
+}
+
+// ---- Pippenger MSM over G1 ------------------------------------------------------------------------
+// windows handled by a call: w = w0 + j * wstep, j < nw (wstep = number of ranks when bucket-sharded)
+struct msm_geom { int c, w0, wstep, nw; uint32_t nb; uint32_t maxchunks; size_t n; };
+
+__global__ void k_msm_hist(const uint64_t *__restrict__ k, msm_geom g, uint32_t *__restrict__ count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    uint64_t s[4] = {k[4 * i], k[4 * i + 1], k[4 * i + 2], k[4 * i + 3]};
+    for (int j = 0; j < g.nw; j++) {
+        uint32_t d = msm_digit(s, g.w0 + j * g.wstep, g.c);
+        if (d) atomicAdd(&count[(size_t)j * g.nb + d], 1u);
+    }
+}
+
+// per window (one block): bucket_off = exclusive scan of count, chunk_off = exclusive scan of
+// ceil(count / MSM_CHUNK); both get a closing total at [nb].  maxch = largest chunk count of a bucket.
+__global__ void __launch_bounds__(1024) k_msm_scan(const uint32_t *__restrict__ count, msm_geom g, uint32_t *__restrict__ bucket_off,
+                                                   uint32_t *__restrict__ chunk_off, uint32_t *__restrict__ maxch) {
+    __shared__ uint32_t sa[1024], sb[1024];
+    int j = blockIdx.x, t = threadIdx.x;
+    const uint32_t *cnt = count + (size_t)j * g.nb;
+    uint32_t *bo = bucket_off + (size_t)j * (g.nb + 1), *co = chunk_off + (size_t)j * (g.nb + 1);
+    uint32_t per = (g.nb + 1023u) / 1024u;
+    uint32_t lo = t * per, hi = lo + per < g.nb ? lo + per : g.nb;
+    uint32_t a = 0, b = 0, mx = 0;
+    for (uint32_t d = lo; d < hi; d++) {
+        uint32_t c = cnt[d], ch = (c + MSM_CHUNK - 1) / MSM_CHUNK;
+        a += c; b += ch; mx = ch > mx ? ch : mx;
+    }
+    sa[t] = a; sb[t] = b;
+    __syncthreads();
+    for (int s = 1; s < 1024; s <<= 1) {          // inclusive Hillis-Steele scan
+        uint32_t va = t >= s ? sa[t - s] : 0, vb = t >= s ? sb[t - s] : 0;
+        __syncthreads();
+        sa[t] += va; sb[t] += vb;
+        __syncthreads();
+    }
+    uint32_t ea = sa[t] - a, eb = sb[t] - b;       // exclusive prefix of this thread's range
+    for (uint32_t d = lo; d < hi; d++) {
+        uint32_t c = cnt[d];
+        bo[d] = ea; co[d] = eb;
+        ea += c; eb += (c + MSM_CHUNK - 1) / MSM_CHUNK;
+    }
+    if (t == 1023) { bo[g.nb] = sa[t]; co[g.nb] = sb[t]; }
+    if (mx) atomicMax(maxch, mx);
+}
+
+// idx[j][bucket_off[j][d] ..] = the indices of the points whose digit in window j is d (count is consumed)
+__global__ void k_msm_scatter(const uint64_t *__restrict__ k, msm_geom g, const uint32_t *__restrict__ bucket_off,
+                              uint32_t *__restrict__ count, uint32_t *__restrict__ idx) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    uint64_t s[4] = {k[4 * i], k[4 * i + 1], k[4 * i + 2], k[4 * i + 3]};
+    for (int j = 0; j < g.nw; j++) {
+        uint32_t d = msm_digit(s, g.w0 + j * g.wstep, g.c);
+        if (!d) continue;
+        uint32_t slot = atomicSub(&count[(size_t)j * g.nb + d], 1u) - 1u;
+        idx[(size_t)j * g.n + bucket_off[(size_t)j * (g.nb + 1) + d] + slot] = (uint32_t)i;
+    }
+}
+
+// one thread per chunk: partial sum of <= MSM_CHUNK points of one bucket
+__global__ void __launch_bounds__(128) k_msm_chunk_sum(const g1_affine_pod *__restrict__ pts, const uint32_t *__restrict__ idx, msm_geom g,
+                                                       const uint32_t *__restrict__ bucket_off, const uint32_t *__restrict__ chunk_off,
+                                                       xyzz<FpInl> *__restrict__ chunks, uint32_t *__restrict__ chunk_bucket) {
+    int j = blockIdx.y;
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t *co = chunk_off + (size_t)j * (g.nb + 1), *bo = bucket_off + (size_t)j * (g.nb + 1);
+    if (q >= co[g.nb]) return;
+    uint32_t lo = 0, hi = g.nb;                    // largest b with co[b] <= q (and a non-empty bucket)
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (co[mid] <= q) lo = mid; else hi = mid; }
+    uint32_t b = lo, l = q - co[b];
+    uint32_t first = bo[b] + l * MSM_CHUNK, last = first + MSM_CHUNK < bo[b + 1] ? first + MSM_CHUNK : bo[b + 1];
+    xyzz<FpInl> acc;
+    msm_bucket_sum(acc, pts, idx + (size_t)j * g.n, first, last);
+    chunks[(size_t)j * g.maxchunks + q] = acc;
+    chunk_bucket[(size_t)j * g.maxchunks + q] = b;
+}
+
+// round r of the in-bucket tree: chunk l of a bucket absorbs chunk l + 2^r when l % 2^(r+1) == 0
+__global__ void __launch_bounds__(128) k_msm_chunk_tree(xyzz<FpInl> *__restrict__ chunks, const uint32_t *__restrict__ chunk_bucket,
+                                                        const uint32_t *__restrict__ chunk_off, msm_geom g, int r,
+                                                        const uint32_t *__restrict__ maxch) {
+    if ((1u << r) >= *maxch) return;
+    int j = blockIdx.y;
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t *co = chunk_off + (size_t)j * (g.nb + 1);
+    if (q >= co[g.nb]) return;
+    uint32_t b = chunk_bucket[(size_t)j * g.maxchunks + q];
+    uint32_t l = q - co[b], nch = co[b + 1] - co[b];
+    if ((l & ((2u << r) - 1)) || l + (1u << r) >= nch) return;
+    xyzz<FpInl> *base = chunks + (size_t)j * g.maxchunks;
+    xyzz<FpInl> a = base[q];
+    xyzz_add(a, base[q + (1u << r)]);
+    base[q] = a;
+}
+
+// one thread per (window, segment of MSM_SEG buckets): sum_{d in segment} d * B[d]
+__global__ void __launch_bounds__(128) k_msm_segment_reduce(const xyzz<FpInl> *__restrict__ chunks, const uint32_t *__restrict__ chunk_off,
+                                                            msm_geom g, xyzz<FpInl> *__restrict__ segsum) {
+    int j = blockIdx.y;
+    uint32_t nseg = g.nb / MSM_SEG;
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    const uint32_t *co = chunk_off + (size_t)j * (g.nb + 1);
+    const xyzz<FpInl> *base = chunks + (size_t)j * g.maxchunks;
+    uint32_t lo = s * MSM_SEG, hi = lo + MSM_SEG;
+    if (lo == 0) lo = 1;
+    xyzz<FpInl> running, acc;
+    xyzz_set_inf(running); xyzz_set_inf(acc);
+    for (uint32_t d = hi; d-- > lo;) {
+        if (co[d + 1] > co[d]) { xyzz<FpInl> bsum = base[co[d]]; xyzz_add(running, bsum); }
+        xyzz_add(acc, running);
+    }
+    if (lo > 1 && !xyzz_is_inf(running)) { xyzz_mul_small(running, lo - 1); xyzz_add(acc, running); }
+    segsum[(size_t)j * nseg + s] = acc;
+}
+
+// one block per window: winsum[j] = sum of its segment sums
+__global__ void __launch_bounds__(128) k_msm_window_sum(const xyzz<FpInl> *__restrict__ segsum, uint32_t nseg, xyzz<FpInl> *__restrict__ winsum) {
+    __shared__ xyzz<FpInl> sm[128];
+    int j = blockIdx.x;
+    xyzz<FpInl> acc;
+    xyzz_set_inf(acc);
+    for (uint32_t s = threadIdx.x; s < nseg; s += 128) { xyzz<FpInl> q = segsum[(size_t)j * nseg + s]; xyzz_add(acc, q); }
+    block_reduce_xyzz<FpInl, 128>(acc, sm);
+    if (threadIdx.x == 0) winsum[j] = acc;
+}
+
+// thread j shifts its window sum to its weight 2^(c * w_j); then a tree adds them; thread 0 writes the
+// result -- normalised (z = 1) for a complete MSM, plain Jacobian for a bucket-sharded partial
+__global__ void __launch_bounds__(64) k_msm_combine(const xyzz<FpInl> *__restrict__ winsum, msm_geom g, int normalise,
+                                                    g1_jac_pod *__restrict__ out) {
+    __shared__ xyzz<FpInl> sm[64];
+    xyzz<FpInl> acc;
+    xyzz_set_inf(acc);
+    for (int j = threadIdx.x; j < g.nw; j += 64) {
+        xyzz<FpInl> s = winsum[j];
+        int shifts = g.c * (g.w0 + j * g.wstep);
+        if (!xyzz_is_inf(s))
+            for (int i = 0; i < shifts; i++) xyzz_dbl(s);
+        xyzz_add(acc, s);
+    }
+    block_reduce_xyzz<FpInl, 64>(acc, sm);
+    if (threadIdx.x == 0) {
+        fp ox, oy, oz;
+        if (normalise) xyzz_to_jac_normalised(ox, oy, oz, acc);
+        else if (xyzz_is_inf(acc)) { fp_set_zero(ox); fp_set_one(oy); fp_set_zero(oz); }
+        else {   // XYZZ -> Jacobian with Z = ZZZ/ZZ... avoided: (X*ZZZ^2*.., ) use Z = ZZ: X' = X*ZZ, Y' = Y*ZZZ, Z' = ZZ
+            // (X/ZZ, Y/ZZZ) == (X*ZZ / ZZ^2, Y*ZZZ / ZZ^3) because ZZZ^2 == ZZ^3
+            fp_mul(ox, acc.x, acc.zz);
+            fp_mul(oy, acc.y, acc.zzz);
+            oz = acc.zz;
+        }
+        store_jac(out, ox, oy, oz);
+    }
+}
+
+// ---- VerifyAggregateCommon batch: per-attestation public-key aggregation -----------------------------
+// attestation a: pk = sum registry[key_idx[key_off[a] .. key_off[a+1])]; writes the two Miller pairs of
+// CompareTwoPairings(G1One, sig, pk, H(m)) (g1pubs/bls.go:165-168, pairing.go:140-147):
+//   (P, Q)[2a] = (G1One, sig[a]),  (P, Q)[2a+1] = (-pk, msg_hash[msg_idx[a]])
+__global__ void __launch_bounds__(128) k_attest_pairs(const g1_affine_pod *__restrict__ registry, const uint32_t *__restrict__ key_idx,
+                                                      const uint32_t *__restrict__ key_off, const g2_affine_pod *__restrict__ sig,
+                                                      const g2_affine_pod *__restrict__ msg_hash, const uint32_t *__restrict__ msg_idx,
+                                                      size_t nattest, g1_affine_pod *__restrict__ P, g2_affine_pod *__restrict__ Q,
+                                                      uint32_t *__restrict__ group_off) {
+    size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a == 0) group_off[0] = 0;
+    if (a >= nattest) return;
+    group_off[a + 1] = (uint32_t)(2 * a + 2);
+    xyzz<FpInl> acc;
+    msm_bucket_sum(acc, registry, key_idx, key_off[a], key_off[a + 1]);
+    fp ox, oy, oz;
+    xyzz_to_jac_normalised(ox, oy, oz, acc);
+    g1_affine_pod *neg = P + 2 * a + 1, *one = P + 2 * a;
+    bool inf = fp_is_zero(oz);
+    fp_neg(oy, oy);
+    if (inf) { fp_set_zero(ox); fp_set_one(oy); }     // G1AffineZero = (0, 1, true), g1.go:22
+    fp_store_u64(neg->x, ox); fp_store_u64(neg->y, oy);
+    neg->inf = inf ? 1 : 0;
+    for (int i = 0; i < 7; i++) neg->pad[i] = 0;
+    const uint32_t gx[12] = {B381_G1_GEN_X_LIMBS}, gy[12] = {B381_G1_GEN_Y_LIMBS};
+    fp t;
+    fp_load_tab(t, gx); fp_store_u64(one->x, t);
+    fp_load_tab(t, gy); fp_store_u64(one->y, t);
+    one->inf = 0;
+    for (int i = 0; i < 7; i++) one->pad[i] = 0;
+    Q[2 * a] = sig[a];
+    Q[2 * a + 1] = msg_hash[msg_idx[a]];
+}
+
+#endif  // __CUDACC__
+
+}  // namespace b381

@@ -10,6 +10,7 @@
 #include "../../include/b381.h"
 #include "pairing.cuh"
 #include "curve.cuh"
+#include "agg.cuh"
 
 using namespace b381;
 
@@ -105,13 +106,14 @@ __global__ void k_imad_probe(uint32_t *out, int iters) {
 // ---------------------------------------------------------------------------------------------
 struct b381_ctx {
     int device;
+    int sms;
     cudaStream_t own_stream;
     cudaStream_t stream;
     uint64_t launches;
     char err[256];
     // grow-only device scratch
-    void *scratch[4];
-    size_t scratch_bytes[4];
+    void *scratch[8];
+    size_t scratch_bytes[8];
 };
 
 #define CK(call)                                                                                      \
@@ -151,6 +153,7 @@ int b381_init(int device, b381_ctx **out) {
     if (!ctx) return B381_ERR_NOMEM;
     memset(ctx, 0, sizeof *ctx);
     ctx->device = device;
+    cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B381_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
     // the tower state of a pairing lives in local memory: prefer L1 over shared memory
@@ -166,7 +169,7 @@ void b381_free(b381_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 4; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < 8; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -346,6 +349,165 @@ int b381_pairing_product_is_one(b381_ctx *ctx, const b381_g1_affine *p, const b3
     if (rc == B381_ERR_CUDA) snprintf(ctx->err, sizeof ctx->err, "pairing_product_is_one: %s", cudaGetErrorString(cudaGetLastError()));
     cudaFree(doff); cudaFree(dok);
     return rc;
+}
+
+// ---- aggregation, device-resident ----------------------------------------------------------------
+#define SUM_BLOCK_G1 128
+#define SUM_BLOCK_G2 64
+static int sum_grid(b381_ctx *ctx, size_t n, int block) {
+    int sms = ctx->sms > 0 ? ctx->sms : 148;
+    size_t want = (n + (size_t)block * 8 - 1) / ((size_t)block * 8);      // >= 8 points per thread
+    size_t cap = (size_t)sms * 4;
+    return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+int b381_g1_sum_dev(b381_ctx *ctx, const b381_g1_affine *d_p, size_t n, b381_g1_jac *d_out) {
+    if (!ctx || !d_out || (n && !d_p)) return B381_ERR_ARG;
+    int grid = sum_grid(ctx, n, SUM_BLOCK_G1);
+    void *part;
+    int rc = scratch_get(ctx, 4, (size_t)grid * sizeof(xyzz<FpInl>), &part);
+    if (rc) return rc;
+    k_sum_partial<FpInl, g1_affine_pod, SUM_BLOCK_G1><<<grid, SUM_BLOCK_G1, 0, ctx->stream>>>((const g1_affine_pod *)d_p, n, (xyzz<FpInl> *)part);
+    k_sum_final<FpInl, g1_jac_pod, SUM_BLOCK_G1><<<1, SUM_BLOCK_G1, 0, ctx->stream>>>((const xyzz<FpInl> *)part, grid, (g1_jac_pod *)d_out);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+int b381_g2_sum_dev(b381_ctx *ctx, const b381_g2_affine *d_p, size_t n, b381_g2_jac *d_out) {
+    if (!ctx || !d_out || (n && !d_p)) return B381_ERR_ARG;
+    int grid = sum_grid(ctx, n, SUM_BLOCK_G2);
+    void *part;
+    int rc = scratch_get(ctx, 4, (size_t)grid * sizeof(xyzz<Fp2Out>), &part);
+    if (rc) return rc;
+    k_sum_partial<Fp2Out, g2_affine_pod, SUM_BLOCK_G2><<<grid, SUM_BLOCK_G2, 0, ctx->stream>>>((const g2_affine_pod *)d_p, n, (xyzz<Fp2Out> *)part);
+    k_sum_final<Fp2Out, g2_jac_pod, SUM_BLOCK_G2><<<1, SUM_BLOCK_G2, 0, ctx->stream>>>((const xyzz<Fp2Out> *)part, grid, (g2_jac_pod *)d_out);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+int b381_g1_fold_dev(b381_ctx *ctx, const b381_g1_jac *d_parts, size_t n, b381_g1_jac *d_out) {
+    if (!ctx || !d_out || (n && !d_parts)) return B381_ERR_ARG;
+    k_g1_fold<<<1, 128, 0, ctx->stream>>>((const g1_jac_pod *)d_parts, n, (g1_jac_pod *)d_out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+
+static inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+int b381_g1_msm_shard_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_scalar *d_k, size_t n, int rank, int nranks,
+                          b381_g1_jac *d_partial) {
+    if (!ctx || !d_partial || (n && (!d_p || !d_k)) || nranks < 1 || rank < 0 || rank >= nranks || n > 0xFFFFFFF0u) return B381_ERR_ARG;
+    bool whole = nranks == 1;
+    msm_geom g;
+    g.c = msm_window_bits(n);
+    int W = msm_num_windows(g.c);
+    g.w0 = rank; g.wstep = nranks; g.nw = rank < W ? (W - rank + nranks - 1) / nranks : 0;
+    g.nb = 1u << g.c; g.n = n;
+    g.maxchunks = (uint32_t)(n / MSM_CHUNK) + g.nb + 1;
+    uint32_t nseg = g.nb / MSM_SEG;
+    int nw = g.nw > 0 ? g.nw : 1;
+    // carve one scratch block
+    size_t o_count = 0, o_boff = o_count + up256((size_t)nw * g.nb * 4), o_coff = o_boff + up256((size_t)nw * (g.nb + 1) * 4);
+    size_t o_max = o_coff + up256((size_t)nw * (g.nb + 1) * 4), o_idx = o_max + 256, o_cb = o_idx + up256((size_t)nw * (n ? n : 1) * 4);
+    size_t o_chunks = o_cb + up256((size_t)nw * g.maxchunks * 4), o_seg = o_chunks + up256((size_t)nw * g.maxchunks * sizeof(xyzz<FpInl>));
+    size_t o_win = o_seg + up256((size_t)nw * nseg * sizeof(xyzz<FpInl>)), total = o_win + up256((size_t)nw * sizeof(xyzz<FpInl>));
+    char *base;
+    int rc = scratch_get(ctx, 5, total, (void **)&base);
+    if (rc) return rc;
+    uint32_t *count = (uint32_t *)(base + o_count), *boff = (uint32_t *)(base + o_boff), *coff = (uint32_t *)(base + o_coff);
+    uint32_t *maxch = (uint32_t *)(base + o_max), *idx = (uint32_t *)(base + o_idx), *cb = (uint32_t *)(base + o_cb);
+    xyzz<FpInl> *chunks = (xyzz<FpInl> *)(base + o_chunks), *seg = (xyzz<FpInl> *)(base + o_seg), *win = (xyzz<FpInl> *)(base + o_win);
+    if (g.nw > 0 && n > 0) {
+        CK(cudaMemsetAsync(base, 0, o_idx, ctx->stream));        // count, offsets, maxch
+        unsigned pg = grid_for(n, 256);
+        k_msm_hist<<<pg, 256, 0, ctx->stream>>>((const uint64_t *)d_k, g, count);
+        k_msm_scan<<<g.nw, 1024, 0, ctx->stream>>>(count, g, boff, coff, maxch);
+        k_msm_scatter<<<pg, 256, 0, ctx->stream>>>((const uint64_t *)d_k, g, boff, count, idx);
+        dim3 cg(grid_for(g.maxchunks, 128), g.nw);
+        k_msm_chunk_sum<<<cg, 128, 0, ctx->stream>>>((const g1_affine_pod *)d_p, idx, g, boff, coff, chunks, cb);
+        ctx->launches += 4;
+        for (int r = 0; ((size_t)MSM_CHUNK << r) < n; r++) {
+            k_msm_chunk_tree<<<cg, 128, 0, ctx->stream>>>(chunks, cb, coff, g, r, maxch);
+            ctx->launches++;
+        }
+        dim3 sg(grid_for(nseg, 128), g.nw);
+        k_msm_segment_reduce<<<sg, 128, 0, ctx->stream>>>(chunks, coff, g, seg);
+        k_msm_window_sum<<<g.nw, 128, 0, ctx->stream>>>(seg, nseg, win);
+        ctx->launches += 2;
+    } else {
+        g.nw = 0;
+    }
+    k_msm_combine<<<1, 64, 0, ctx->stream>>>(win, g, whole ? 1 : 0, (g1_jac_pod *)d_partial);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+int b381_g1_msm_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_scalar *d_k, size_t n, b381_g1_jac *d_out) {
+    return b381_g1_msm_shard_dev(ctx, d_p, d_k, n, 0, 1, d_out);
+}
+
+int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_registry, const uint32_t *d_key_idx,
+                                           const uint32_t *d_key_off, const b381_g2_affine *d_sig,
+                                           const b381_g2_affine *d_msg_hash, const uint32_t *d_msg_idx, size_t nattest,
+                                           uint8_t *d_ok) {
+    if (!ctx || nattest > 0x7FFFFFF0u) return B381_ERR_ARG;
+    if (!nattest) return B381_OK;
+    if (!d_registry || !d_key_idx || !d_key_off || !d_sig || !d_msg_hash || !d_msg_idx || !d_ok) return B381_ERR_ARG;
+    void *P, *Q, *off;
+    int rc = scratch_get(ctx, 2, 2 * nattest * sizeof(b381_g1_affine), &P);
+    if (rc) return rc;
+    rc = scratch_get(ctx, 3, 2 * nattest * sizeof(b381_g2_affine), &Q);
+    if (rc) return rc;
+    rc = scratch_get(ctx, 6, (nattest + 1) * sizeof(uint32_t), &off);
+    if (rc) return rc;
+    k_attest_pairs<<<grid_for(nattest, 128), 128, 0, ctx->stream>>>((const g1_affine_pod *)d_registry, d_key_idx, d_key_off,
+                                                                    (const g2_affine_pod *)d_sig, (const g2_affine_pod *)d_msg_hash,
+                                                                    d_msg_idx, nattest, (g1_affine_pod *)P, (g2_affine_pod *)Q,
+                                                                    (uint32_t *)off);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return b381_pairing_product_is_one_dev(ctx, (b381_g1_affine *)P, (b381_g2_affine *)Q, 2 * nattest, (uint32_t *)off, nattest, d_ok);
+}
+
+// ---- aggregation, host buffers -------------------------------------------------------------------
+}  // extern "C"
+template <class AFF, class JAC, class FN>
+static int sum_host(b381_ctx *ctx, const AFF *p, size_t n, JAC *out, FN fn) {
+    if (!ctx || !out || (n && !p)) return B381_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    void *dp, *dout;
+    int rc = scratch_get(ctx, 2, (n ? n : 1) * sizeof(AFF), &dp);
+    if (rc) return rc;
+    rc = scratch_get(ctx, 7, sizeof(b381_g2_jac), &dout);
+    if (rc) return rc;
+    if (n) CK(cudaMemcpyAsync(dp, p, n * sizeof(AFF), cudaMemcpyHostToDevice, ctx->stream));
+    rc = fn(ctx, (const AFF *)dp, n, (JAC *)dout);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, dout, sizeof(JAC), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B381_OK;
+}
+extern "C" {
+int b381_g1_sum(b381_ctx *ctx, const b381_g1_affine *p, size_t n, b381_g1_jac *out) { return sum_host(ctx, p, n, out, b381_g1_sum_dev); }
+int b381_g2_sum(b381_ctx *ctx, const b381_g2_affine *p, size_t n, b381_g2_jac *out) { return sum_host(ctx, p, n, out, b381_g2_sum_dev); }
+int b381_g1_msm(b381_ctx *ctx, const b381_g1_affine *p, const b381_scalar *k, size_t n, b381_g1_jac *out) {
+    if (!ctx || !out || (n && (!p || !k))) return B381_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    void *dp, *dk, *dout;
+    int rc = scratch_get(ctx, 2, (n ? n : 1) * sizeof(b381_g1_affine), &dp);
+    if (rc) return rc;
+    rc = scratch_get(ctx, 3, (n ? n : 1) * sizeof(b381_scalar), &dk);
+    if (rc) return rc;
+    rc = scratch_get(ctx, 7, sizeof(b381_g2_jac), &dout);
+    if (rc) return rc;
+    if (n) {
+        CK(cudaMemcpyAsync(dp, p, n * sizeof(b381_g1_affine), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(dk, k, n * sizeof(b381_scalar), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = b381_g1_msm_dev(ctx, (const b381_g1_affine *)dp, (const b381_scalar *)dk, n, (b381_g1_jac *)dout);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, dout, sizeof(b381_g1_jac), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B381_OK;
 }
 
 }  // extern "C"

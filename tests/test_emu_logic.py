@@ -1,0 +1,110 @@
+"""CPU unit tests of the DEVICE logic: bls_b200/csrc/*.cuh compiled as plain C++ (tests/emu/emu.cc,
+portable limb bodies) and compared with the oracle.  This exercises the exact tower / pairing /
+group-law / MSM code the kernels run -- without a GPU -- so formula errors surface in the CPU suite.
+The product library never contains this host build."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from bls_b200 import hostgen as hg, layout as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+U64 = np.uint64
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import __graft_entry__ as g
+    so = g.build_emu()
+    return ctypes.CDLL(so)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_fp_ops(emu, orc):
+    xs = orc.XorShift(11)
+    a = xs.rand_fq(300); b = xs.rand_fq(300)
+    q1 = np.array(L.int_to_limbs(L.Q - 1), U64)
+    a[0] = 0; b[1] = 0; a[2] = q1; b[2] = q1; a[3] = q1; b[3] = L.fp_from_int(1)
+    for op, name in [(0, "mul"), (1, "add"), (2, "sub"), (3, "square"), (4, "neg"), (5, "double")]:
+        out = np.empty_like(a)
+        emu.emu_fp_op(op, _p(a), _p(b), _p(out), ctypes.c_size_t(300))
+        assert (out == orc.fq(name, a, b)).all(), name
+    a[0] = L.fp_from_int(7)
+    out = np.empty_like(a[:20])
+    emu.emu_fp_op(6, _p(a), _p(b), _p(out), ctypes.c_size_t(20))     # Fermat inverse == binary-Euclid inverse (fq.go:224-266)
+    assert (out == orc.fq("inverse", a[:20])).all()
+
+
+def test_fp12_ops(emu, orc):
+    xs = orc.XorShift(12)
+    n = 6
+    a = xs.rand_fq(12 * n).reshape(n, 2, 3, 2, 6); b = xs.rand_fq(12 * n).reshape(n, 2, 3, 2, 6)
+    out = np.empty_like(a)
+    for op, name, arg in [(0, "mul", 0), (3, "square", 0), (6, "inverse", 0), (7, "frobenius", 1), (7, "frobenius", 2),
+                          (7, "frobenius", 3), (12, "conjugate", 0)]:
+        emu.emu_fp12_op(op, ctypes.c_uint64(arg), _p(a), _p(b), _p(out), ctypes.c_size_t(n))
+        assert (out == orc.fq12(name, a, b, arg)).all(), (name, arg)
+    # sparse multiplication: fq12.go:32-47 with (c0, c1, c4) taken from b
+    emu.emu_fp12_op(13, ctypes.c_uint64(0), _p(a), _p(b), _p(out), ctypes.c_size_t(n))
+    assert (out == orc.fq12("mul_by_014", a, b)).all()
+
+
+def test_cyclotomic_square_and_exp_by_x(emu, orc):
+    """valid only in the cyclotomic subgroup: use final-exponentiation outputs"""
+    P = hg.g1_progression(3, 1, 2); Q = hg.g2_progression(4, 1, 2)
+    f = orc.pairing_batch(P, Q)
+    out = np.empty_like(f)
+    emu.emu_fp12_op(15, ctypes.c_uint64(0), _p(f), _p(f), _p(out), ctypes.c_size_t(2))
+    assert (out == orc.fq12("square", f)).all()
+    emu.emu_fp12_op(16, ctypes.c_uint64(L.BLS_X), _p(f), _p(f), _p(out), ctypes.c_size_t(2))
+    assert (out == orc.fq12("conjugate", orc.fq12("exp", f, None, L.BLS_X))).all()    # ExpByX, pairing.go:92-98
+
+
+def test_miller_loop_and_final_exp(emu, orc, kats):
+    P = np.concatenate([orc.g1_generator(), hg.g1_progression(0x99, 7, 3)])
+    Q = np.concatenate([orc.g2_generator(), hg.g2_progression(0x55, 9, 3)])
+    ml = np.zeros(4, dtype=L.FP12)
+    emu.emu_miller_loop(_p(P), _p(Q), ctypes.c_size_t(4), _p(ml))
+    for i in range(4):
+        assert (ml[i] == orc.miller_loop(P[i:i + 1], Q[i:i + 1])).all()
+    fe = np.zeros(4, dtype=L.FP12); ok = np.zeros(4, np.uint8)
+    emu.emu_final_exp(_p(ml), ctypes.c_size_t(4), _p(fe), _p(ok))
+    assert ok.all() and fe.tobytes() == orc.pairing_batch(P, Q).tobytes()
+    exp = np.stack([L.fp_from_int(int(x, 16)) for x in kats["pairing_g1_g2"]["coeffs"]]).reshape(2, 3, 2, 6)
+    assert (fe[0] == exp).all()                                   # RELIC vector, pairing_test.go:9-58
+
+
+def test_group_sums(emu, orc):
+    P = hg.g1_progression(21, 5, 40)
+    P = np.concatenate([P, P[:3], hg.g1_neg(P[5:7])]); P["inf"][9] = 1
+    out = np.zeros(1, dtype=L.G1_JAC)
+    for fn in ("emu_g1_sum", "emu_g1_sum_tree"):
+        getattr(emu, fn)(_p(P), ctypes.c_size_t(P.size), _p(out))
+        assert orc.g1.to_affine(out).tobytes() == orc.g1.to_affine(orc.g1.sum_affine(P)).tobytes(), fn
+    Q = hg.g2_progression(22, 3, 17); Q = np.concatenate([Q, Q[:2]])
+    o2 = np.zeros(1, dtype=L.G2_JAC)
+    emu.emu_g2_sum(_p(Q), ctypes.c_size_t(Q.size), _p(o2))
+    assert orc.g2.to_affine(o2).tobytes() == orc.g2.to_affine(orc.g2.sum_affine(Q)).tobytes()
+
+
+@pytest.mark.parametrize("rank,nranks", [(0, 1), (0, 2), (1, 2)])
+def test_msm_building_blocks(emu, orc, rank, nranks):
+    n = 200
+    P = hg.g1_progression(31, 2, n)
+    K, _ = hg.splitmix_scalars(5, n)
+    out = np.zeros(1, dtype=L.G1_JAC)
+    emu.emu_g1_msm(_p(P), _p(K), ctypes.c_size_t(n), 6, rank, nranks, 16, _p(out))
+    if nranks == 1:
+        assert orc.g1.to_affine(out).tobytes() == orc.g1.to_affine(orc.g1_msm_naive(P, K, threads=4)).tobytes()
+    else:
+        other = np.zeros(1, dtype=L.G1_JAC)
+        emu.emu_g1_msm(_p(P), _p(K), ctypes.c_size_t(n), 6, 1 - rank, nranks, 16, _p(other))
+        tot = np.zeros(1, dtype=L.G1_JAC)
+        emu.emu_g1_fold(_p(np.concatenate([out, other])), ctypes.c_size_t(2), _p(tot))
+        assert orc.g1.to_affine(tot).tobytes() == orc.g1.to_affine(orc.g1_msm_naive(P, K, threads=4)).tobytes()

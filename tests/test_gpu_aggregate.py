@@ -1,0 +1,159 @@
+"""Parity of the aggregation kernels (point sums, Pippenger MSM, bucket-sharded MSM + fold, the
+VerifyAggregateCommon batch) against the CPU oracle, through the C ABI.  Results are compared on
+canonical observables: affine coordinates (Montgomery limbs) and booleans, bit-exact."""
+import numpy as np
+import pytest
+
+from bls_b200 import hostgen as hg, layout as L
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from bls_b200 import capi
+    c = capi.Ctx(0)
+    yield c
+    c.close()
+
+
+def _same_point(orc, grp, got_jac, exp_jac):
+    a = grp.to_affine(got_jac); b = grp.to_affine(exp_jac)
+    return a.tobytes() == b.tobytes()
+
+
+def _normalised(orc, jac, fp2=False):
+    """engine sums come back with z == 1 (or the canonical zero)"""
+    one = L.fp_from_int(1)
+    z = jac["z"][0]
+    if fp2:
+        return (z[0] == one).all() and not z[1].any() or not z.any()
+    return (z == one).all() or not z.any()
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 127, 128, 1000, 5000])
+def test_g1_sum_vs_reference_fold(ctx, orc, n):
+    """AggregatePublicKeys (g1pubs/bls.go:192-198): left fold of G1Projective.Add"""
+    P = hg.g1_progression(0xA11CE + n, 0x1D, n) if n else np.zeros(0, dtype=L.G1_AFFINE)
+    got = ctx.g1_sum(P)
+    assert _normalised(orc, got)
+    assert _same_point(orc, orc.g1, got, orc.g1.sum_affine(P))
+
+
+def test_g1_sum_special_cases(ctx, orc):
+    """equal points (doubling branch, g1.go:419-421), P + (-P), infinity inputs (g1.go:401-406)"""
+    P = hg.g1_progression(5, 3, 6)
+    dup = np.concatenate([P[:1], P[:1]])                       # P + P
+    assert _same_point(orc, orc.g1, ctx.g1_sum(dup), orc.g1.sum_affine(dup))
+    canc = np.concatenate([P[:3], hg.g1_neg(P[:3])])           # sums to zero
+    got = ctx.g1_sum(canc)
+    assert not got["z"].any() and _same_point(orc, orc.g1, got, orc.g1.sum_affine(canc))
+    withinf = P.copy(); withinf["inf"][2] = 1; withinf["inf"][5] = 1
+    assert _same_point(orc, orc.g1, ctx.g1_sum(withinf), orc.g1.sum_affine(withinf))
+    many = np.resize(P[:1], 300)                               # 300 * P: every tree level doubles
+    assert _same_point(orc, orc.g1, ctx.g1_sum(many), orc.g1.sum_affine(many))
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 64, 65, 700])
+def test_g2_sum_vs_reference_fold(ctx, orc, n):
+    """g1pubs.AggregateSignatures (g1pubs/bls.go:177-183): fold of G2Projective.Add"""
+    Q = hg.g2_progression(0xB0B + n, 0x11, n) if n else np.zeros(0, dtype=L.G2_AFFINE)
+    got = ctx.g2_sum(Q)
+    assert _normalised(orc, got, fp2=True)
+    assert _same_point(orc, orc.g2, got, orc.g2.sum_affine(Q))
+    if n >= 3:
+        dup = np.concatenate([Q[:2], Q[:2], Q[2:3]])
+        assert _same_point(orc, orc.g2, ctx.g2_sum(dup), orc.g2.sum_affine(dup))
+
+
+@pytest.mark.parametrize("n", [1, 2, 33, 500, 3000])
+def test_g1_msm_vs_double_and_add(ctx, orc, n):
+    """sum k_i P_i == fold of G1Affine.MulFR (g1.go:80-90) with G1Projective.Add"""
+    P = hg.g1_progression(0x5EED + n, 0x77, n)
+    K, _ = hg.splitmix_scalars(n, n)
+    got = ctx.g1_msm(P, K)
+    assert _normalised(orc, got)
+    assert _same_point(orc, orc.g1, got, orc.g1_msm_naive(P, K, threads=8))
+
+
+def test_g1_msm_degenerate_scalars(ctx, orc):
+    """all-ones scalars (== AggregatePublicKeys: every point in one bucket), zeros, r-1, repeated points"""
+    n = 2000
+    P = hg.g1_progression(9, 4, n)
+    ones = np.zeros((n, 4), np.uint64); ones[:, 0] = 1
+    assert _same_point(orc, orc.g1, ctx.g1_msm(P, ones), orc.g1.sum_affine(P))
+    zeros = np.zeros((n, 4), np.uint64)
+    assert not ctx.g1_msm(P, zeros)["z"].any()
+    K, vals = hg.splitmix_scalars(7, 40)
+    K[0] = L.scalar_from_int(L.R_ORDER - 1); K[1] = L.scalar_from_int(0); K[2] = L.scalar_from_int((1 << 255) - 1 - 3)
+    Pm = np.resize(P[:3], 40)                                  # the same 3 points over and over
+    Pm["inf"][5] = 1
+    assert _same_point(orc, orc.g1, ctx.g1_msm(Pm, K), orc.g1_msm_naive(Pm, K, threads=8))
+    assert not ctx.g1_msm(np.zeros(0, dtype=L.G1_AFFINE), np.zeros((0, 4), np.uint64))["z"].any()
+
+
+def test_g1_msm_closed_form_large(ctx, orc):
+    """2^17 points with known discrete logs: sum k_i (s + i d) G1 == (sum k_i (s + i d) mod r) G1"""
+    n = 1 << 17
+    s, d = 0xB2000003, 0x9E3779B97F4A7C15
+    P = hg.g1_progression(s, d, n)
+    K, vals = hg.splitmix_scalars(42, n)
+    S = sum(k * (s + i * d) for i, k in enumerate(vals)) % L.R_ORDER
+    got = orc.g1.to_affine(ctx.g1_msm(P, K))
+    assert got.tobytes() == hg.g1_mul(S).tobytes()
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 8])
+def test_g1_msm_bucket_sharded(ctx, orc, nranks):
+    """BASELINE config 4 semantics on one GPU: every rank's window shard, then the fold of the partials"""
+    n = 1500
+    P = hg.g1_progression(0xC0FFEE, 0x31, n)
+    K, _ = hg.splitmix_scalars(nranks, n)
+    parts = np.concatenate([ctx.g1_msm_shard(P, K, r, nranks) for r in range(nranks)])
+    got = ctx.g1_fold(parts)
+    assert _normalised(orc, got)
+    assert _same_point(orc, orc.g1, got, orc.g1_msm_naive(P, K, threads=8))
+    assert got.tobytes() == ctx.g1_msm(P, K).tobytes()
+
+
+def _attestations(orc, nreg, natt, committee, nmsg, seed):
+    """registry of pk_i = sk_i G1 with sk_i = s + i d; messages as points H_j = h_j G2 (stand-ins for
+    HashG2WithDomain outputs, which the Go host computes); sig_a = (sum of the committee's sk) * H_j"""
+    s, d = 0x1000 + seed, 0x2B
+    reg = hg.g1_progression(s, d, nreg)
+    hs = [0x77 + 5 * j for j in range(nmsg)]
+    H = np.concatenate([hg.g2_mul(h) for h in hs])
+    rng = np.random.RandomState(seed)
+    key_idx, key_off, sigs, msg_idx, expect = [], [0], [], [], []
+    for a in range(natt):
+        m = committee if a % 5 else max(1, committee // 3)       # ragged committees
+        ks = rng.randint(0, nreg, size=m)
+        j = int(rng.randint(0, nmsg))
+        sk = sum(s + int(i) * d for i in ks) % L.R_ORDER
+        bad = a % 4 == 3
+        sigs.append(hg.g2_mul((sk + (1 if bad else 0)) * hs[j]))
+        key_idx += [int(i) for i in ks]; key_off.append(len(key_idx)); msg_idx.append(j); expect.append(0 if bad else 1)
+    return reg, np.array(key_idx, np.uint32), np.array(key_off, np.uint32), np.concatenate(sigs), H, np.array(msg_idx, np.uint32), expect
+
+
+def test_verify_aggregate_common_batch(ctx, orc):
+    """VerifyAggregateCommon (g1pubs/bls.go:287-290) per attestation, incl. corrupted signatures"""
+    reg, kidx, koff, sig, H, midx, expect = _attestations(orc, 64, 21, 9, 3, 1)
+    ok = ctx.verify_aggregate_common_batch(reg, kidx, koff, sig, H, midx)
+    assert ok.tolist() == expect
+    # the oracle's own path: AggregatePublicKeys fold + CompareTwoPairings(G1One, sig, pk, H)
+    g1one = orc.g1.to_proj(orc.g1_generator())
+    for a in range(len(expect)):
+        pk = orc.g1.sum_affine(reg[kidx[koff[a]:koff[a + 1]]])
+        good = orc.compare_two_pairings(g1one, orc.g2.to_proj(sig[a:a + 1]), pk, orc.g2.to_proj(H[midx[a]:midx[a] + 1]))
+        assert int(good) == expect[a] == int(ok[a])
+
+
+def test_verify_aggregate_empty_committee_and_batch(ctx, orc):
+    """an empty committee aggregates to the zero key (the reference panics in MillerLoop; the
+    engine treats the infinity pair as the factor 1, so the check reduces to e(G1, sig) == 1: false)"""
+    reg, kidx, koff, sig, H, midx, expect = _attestations(orc, 16, 3, 4, 2, 2)
+    koff2 = koff.copy(); koff2[1:] = koff2[1]                   # attestations 1, 2 have no keys
+    ok = ctx.verify_aggregate_common_batch(reg, kidx, koff2, sig, H, midx)
+    assert ok.tolist() == [expect[0], 0, 0]
+    assert ctx.verify_aggregate_common_batch(reg, kidx[:0], np.zeros(1, np.uint32), sig[:0], H, midx[:0]).size == 0

@@ -1,0 +1,100 @@
+// +build b200
+
+// batch_b200.go -- additions to package g1pubs (pubkeys in G1, signatures in G2).  The exported
+// API of g1pubs/bls.go is unchanged: Verify / VerifyWithDomain / VerifyAggregateCommon* keep calling
+// bls.CompareTwoPairings, which `-tags b200` routes to the GPU engine (go/bls/pairing_b200.go).
+// Two replacements and two batch entry points live here.
+package g1pubs
+
+import (
+	"github.com/phoreproject/bls"
+)
+
+// AggregatePublicKeys replaces g1pubs/bls.go:192-198 (serial fold of G1Projective.Add) with one
+// device reduction.  Put `// +build !b200` on the original or rename it.
+func AggregatePublicKeysB200(p []*PublicKey) *PublicKey {
+	aff := make([]bls.G1Affine, len(p))
+	for i, pk := range p {
+		aff[i] = *pk.p.ToAffine()
+	}
+	return &PublicKey{p: bls.SumG1(aff)}
+}
+
+// AggregateSignaturesB200 replaces g1pubs/bls.go:177-183.
+func AggregateSignaturesB200(s []*Signature) *Signature {
+	aff := make([]bls.G2Affine, len(s))
+	for i, sig := range s {
+		aff[i] = *sig.s.ToAffine()
+	}
+	return &Signature{s: bls.SumG2(aff)}
+}
+
+// VerifyAggregate replaces g1pubs/bls.go:252-282: same duplicate-message rule (incl. quirk Q7: an
+// empty message is rejected), but ONE product of n+1 Miller loops and one final exponentiation
+// instead of n+1 full pairings.  e(G1, sig) == prod e(pk_i, H(m_i))  <=>
+// FE(ML(-G1, sig) * prod ML(pk_i, H(m_i))) == 1.
+func (s *Signature) VerifyAggregateB200(pubKeys []*PublicKey, msgs [][]byte) bool {
+	if len(pubKeys) != len(msgs) {
+		return false
+	}
+	if hasDuplicates(msgs) { // the sort + dedupe of bls.go:257-273, unchanged
+		return false
+	}
+	n := len(pubKeys)
+	p := make([]bls.G1Affine, n+1)
+	q := make([]bls.G2Affine, n+1)
+	g := bls.G1AffineOne.Copy()
+	g.NegAssign()
+	p[0], q[0] = *g, *s.s.ToAffine()
+	for i := range pubKeys {
+		p[i+1], q[i+1] = *pubKeys[i].p.ToAffine(), *bls.HashG2(msgs[i]) // hashing stays on the host (SURVEY N1)
+	}
+	return bls.PairingProductsAreOne(p, q, []uint32{0, uint32(n + 1)})[0]
+}
+
+// VerifyBatchCommonWithDomain verifies many (aggregate signature, committee, message) triples in one
+// launch: the Ethereum-beacon shape of BASELINE config 5.  ok[i] ==
+// sigs[i].VerifyAggregateCommonWithDomain(committees[i], msgs[i], domain)  (g1pubs/bls.go:294-297).
+func VerifyBatchCommonWithDomain(sigs []*Signature, committees [][]*PublicKey, msgs [][32]byte, domain [8]byte) []bool {
+	n := len(sigs)
+	p := make([]bls.G1Affine, 0, 2*n)
+	q := make([]bls.G2Affine, 0, 2*n)
+	off := make([]uint32, 1, n+1)
+	for i := range sigs {
+		agg := AggregatePublicKeysB200(committees[i]).p.ToAffine()
+		agg.NegAssign()
+		h := bls.HashG2WithDomain(msgs[i], domain).ToAffine()
+		p = append(p, *bls.G1AffineOne, *agg)
+		q = append(q, *sigs[i].s.ToAffine(), *h)
+		off = append(off, uint32(len(p)))
+	}
+	return bls.PairingProductsAreOne(p, q, off)
+}
+
+func hasDuplicates(msgs [][]byte) bool {
+	cp := make([][]byte, len(msgs))
+	for i, m := range msgs {
+		cp[i] = append([]byte(nil), m...)
+	}
+	sorted := sortByteArrays(cp)
+	last := []byte(nil)
+	for _, m := range sorted {
+		if bytesEqual(m, last) {
+			return true
+		}
+		last = m
+	}
+	return false
+}
+
+func bytesEqual(a, b []byte) bool {
+	if len(a) != len(b) {
+		return false
+	}
+	for i := range a {
+		if a[i] != b[i] {
+			return false
+		}
+	}
+	return true
+}

@@ -1,0 +1,46 @@
+// +build b200
+
+// batch_b200.go -- additions to package g2pubs (pubkeys in G2, signatures in G1).  Verify
+// (g2pubs/bls.go:159-162) keeps calling bls.CompareTwoPairings(sig, G2One, HashG1(m), pub), which
+// `-tags b200` routes to the GPU engine; the aggregation folds get device reductions.
+package g2pubs
+
+import (
+	"github.com/phoreproject/bls"
+)
+
+// AggregateSignaturesB200 replaces g2pubs/bls.go:165-171 (signatures are G1 points here).
+func AggregateSignaturesB200(s []*Signature) *Signature {
+	aff := make([]bls.G1Affine, len(s))
+	for i, sig := range s {
+		aff[i] = *sig.s.ToAffine()
+	}
+	return &Signature{s: bls.SumG1(aff)}
+}
+
+// AggregatePublicKeysB200 replaces g2pubs/bls.go:180-186 (public keys are G2 points here).
+func AggregatePublicKeysB200(p []*PublicKey) *PublicKey {
+	aff := make([]bls.G2Affine, len(p))
+	for i, pk := range p {
+		aff[i] = *pk.p.ToAffine()
+	}
+	return &PublicKey{p: bls.SumG2(aff)}
+}
+
+// VerifyBatch verifies many independent (message, public key, signature) triples in one launch:
+// ok[i] == Verify(msgs[i], pubs[i], sigs[i])  (g2pubs/bls.go:159-162), i.e.
+// e(sig, G2One) == e(HashG1(m), pub)  <=>  FE(ML(sig, G2One) * ML(-HashG1(m), pub)) == 1.
+func VerifyBatch(msgs [][]byte, pubs []*PublicKey, sigs []*Signature) []bool {
+	n := len(msgs)
+	p := make([]bls.G1Affine, 0, 2*n)
+	q := make([]bls.G2Affine, 0, 2*n)
+	off := make([]uint32, 1, n+1)
+	for i := range msgs {
+		h := bls.HashG1(msgs[i]).Copy() // *G1Affine (hash.go:326); hashing stays on the host (SURVEY N1)
+		h.NegAssign()
+		p = append(p, *sigs[i].s.ToAffine(), *h)
+		q = append(q, *bls.G2AffineOne, *pubs[i].p.ToAffine())
+		off = append(off, uint32(len(p)))
+	}
+	return bls.PairingProductsAreOne(p, q, off)
+}

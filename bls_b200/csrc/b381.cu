@@ -11,6 +11,9 @@
 #include "pairing.cuh"
 #include "curve.cuh"
 #include "agg.cuh"
+#include "vm.cuh"
+#include "vm_programs.inc"
+#include <stdlib.h>
 
 using namespace b381;
 
@@ -112,9 +115,13 @@ struct b381_ctx {
     uint64_t launches;
     char err[256];
     // grow-only device scratch
-    void *scratch[8];
-    size_t scratch_bytes[8];
+    void *scratch[12];
+    size_t scratch_bytes[12];
+    // warp-cooperative VM programs resident on the device (csrc/vm.cuh)
+    struct { uint4 *code, *consts; int lanes, nsteps, nslots, spill_fq; } vm[3];
+    int use_vm;
 };
+enum { VM_ML1 = 0, VM_FE_A = 1, VM_FE_C = 2 };
 
 #define CK(call)                                                                                      \
     do {                                                                                              \
@@ -140,6 +147,23 @@ static int scratch_get(b381_ctx *ctx, int slot, size_t bytes, void **out) {
 }
 
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+static inline size_t vm_smem_bytes(int lanes, int nslots) { return 448 + (size_t)VM_WARPS * (32 / lanes) * nslots * 48; }
+
+// run VM program `which` over n units; seg[i] = (base, stride) of the per-unit global areas
+static int vm_run(b381_ctx *ctx, int which, const vm_seg seg[4], size_t n, const unsigned char *flag_a, size_t fsa,
+                  const unsigned char *flag_b, size_t fsb, unsigned char *ok) {
+    vm_args A;
+    for (int i = 0; i < 4; i++) A.seg[i] = seg[i];
+    A.seg[4].base = (unsigned char *)ctx->vm[which].consts; A.seg[4].stride = 0;
+    A.code = ctx->vm[which].code;
+    A.nsteps = ctx->vm[which].nsteps; A.nslots = ctx->vm[which].nslots; A.n = n;
+    A.flag_a = flag_a; A.flag_b = flag_b; A.flag_stride_a = fsa; A.flag_stride_b = fsb; A.ok = ok;
+    int lanes = ctx->vm[which].lanes, upb = VM_WARPS * (32 / lanes);
+    k_vm<8><<<grid_for(n, upb), VM_WARPS * 32, vm_smem_bytes(lanes, A.nslots), ctx->stream>>>(A);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
 
 extern "C" {
 
@@ -161,6 +185,22 @@ int b381_init(int device, b381_ctx **out) {
     cudaFuncSetAttribute(k_final_exp, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(k_final_exp_is_one, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     cudaFuncSetAttribute(k_group_product, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    // upload the VM programs and opt in to the shared memory they need
+    static_assert(sizeof(vm_program_images) / sizeof(vm_program_images[0]) == 3, "ml1, fe_a, fe_c");
+    size_t max_smem = 0;
+    for (int i = 0; i < 3; i++) {
+        const vm_program_image &im = vm_program_images[i];
+        size_t cb = (size_t)im.nsteps * im.lanes * 32, kb = (size_t)im.nconsts * 48;
+        if (cudaMalloc(&ctx->vm[i].code, cb) != cudaSuccess || cudaMalloc(&ctx->vm[i].consts, kb) != cudaSuccess ||
+            cudaMemcpy(ctx->vm[i].code, im.code, cb, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(ctx->vm[i].consts, im.consts, kb, cudaMemcpyHostToDevice) != cudaSuccess) { b381_free(ctx); return B381_ERR_CUDA; }
+        ctx->vm[i].lanes = im.lanes; ctx->vm[i].nsteps = im.nsteps; ctx->vm[i].nslots = im.nslots; ctx->vm[i].spill_fq = im.spill_fq;
+        size_t sm = vm_smem_bytes(im.lanes, im.nslots);
+        if (sm > max_smem) max_smem = sm;
+    }
+    if (cudaFuncSetAttribute(k_vm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess) { b381_free(ctx); return B381_ERR_CUDA; }
+    const char *ev = getenv("B381_VM");           // measurement knob: B381_VM=0 runs the thread-per-pairing kernels instead
+    ctx->use_vm = !(ev && ev[0] == '0');
     *out = ctx;
     return B381_OK;
 }
@@ -169,7 +209,8 @@ void b381_free(b381_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 8; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < 12; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < 3; i++) { if (ctx->vm[i].code) cudaFree(ctx->vm[i].code); if (ctx->vm[i].consts) cudaFree(ctx->vm[i].consts); }
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -231,6 +272,12 @@ int b381_miller_loop_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b
                                b381_fp12 *d_out) {
     if (!ctx || (n && (!d_p || !d_q || !d_out))) return B381_ERR_ARG;
     if (!n) return B381_OK;
+    if (ctx->use_vm) {
+        vm_seg seg[4] = {{(unsigned char *)d_p, sizeof(b381_g1_affine)}, {(unsigned char *)d_q, sizeof(b381_g2_affine)},
+                         {(unsigned char *)d_out, sizeof(b381_fp12)}, {nullptr, 0}};
+        return vm_run(ctx, VM_ML1, seg, n, (const unsigned char *)d_p + 96, sizeof(b381_g1_affine),
+                      (const unsigned char *)d_q + 192, sizeof(b381_g2_affine), nullptr);
+    }
     k_miller_loop<<<grid_for(n, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>(
         (const g1_affine_pod *)d_p, (const g2_affine_pod *)d_q, n, (uint64_t *)d_out);
     ctx->launches++;
@@ -240,6 +287,31 @@ int b381_miller_loop_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b
 int b381_final_exp_batch_dev(b381_ctx *ctx, const b381_fp12 *d_in, size_t n, b381_fp12 *d_out, uint8_t *d_ok) {
     if (!ctx || (n && (!d_in || !d_out))) return B381_ERR_ARG;
     if (!n) return B381_OK;
+    if (ctx->use_vm) {
+        // fe_a: f -> the Fq norm the inversion needs; one thread per element inverts it; fe_c: the rest
+        void *nrm, *spill, *fcopy, *dok = d_ok;
+        int rc = scratch_get(ctx, 8, n * 2 * sizeof(b381_fp), &nrm);
+        if (rc) return rc;
+        rc = scratch_get(ctx, 9, n * (size_t)ctx->vm[VM_FE_C].spill_fq * sizeof(b381_fp), &spill);
+        if (rc) return rc;
+        const b381_fp12 *src = d_in;
+        if (d_in == d_out) {                      // in place: the zero test and fe_c read the input after outputs exist
+            rc = scratch_get(ctx, 10, n * sizeof(b381_fp12), &fcopy);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(fcopy, d_in, n * sizeof(b381_fp12), cudaMemcpyDeviceToDevice, ctx->stream));
+            src = (const b381_fp12 *)fcopy;
+        }
+        if (!dok) { rc = scratch_get(ctx, 11, n, &dok); if (rc) return rc; }
+        b381_fp *nbuf = (b381_fp *)nrm, *ninv = nbuf + n;
+        vm_seg sa[4] = {{(unsigned char *)src, sizeof(b381_fp12)}, {nullptr, 0}, {(unsigned char *)nbuf, sizeof(b381_fp)}, {nullptr, 0}};
+        rc = vm_run(ctx, VM_FE_A, sa, n, nullptr, 0, nullptr, 0, nullptr);
+        if (rc) return rc;
+        k_fp_inv_batch<<<grid_for(n, 128), 128, 0, ctx->stream>>>((const uint64_t *)nbuf, n, (uint64_t *)ninv);
+        ctx->launches++;
+        vm_seg sc[4] = {{(unsigned char *)src, sizeof(b381_fp12)}, {(unsigned char *)ninv, sizeof(b381_fp)},
+                        {(unsigned char *)d_out, sizeof(b381_fp12)}, {(unsigned char *)spill, (size_t)ctx->vm[VM_FE_C].spill_fq * sizeof(b381_fp)}};
+        return vm_run(ctx, VM_FE_C, sc, n, nullptr, 0, nullptr, 0, (unsigned char *)dok);
+    }
     k_final_exp<<<grid_for(n, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>((const uint64_t *)d_in, n,
                                                                               (uint64_t *)d_out, d_ok);
     ctx->launches++;
@@ -248,6 +320,14 @@ int b381_final_exp_batch_dev(b381_ctx *ctx, const b381_fp12 *d_in, size_t n, b38
 }
 int b381_pairing_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_affine *d_q, size_t n,
                            b381_fp12 *d_out) {
+    if (ctx && ctx->use_vm && n) {
+        void *ml;
+        int rc = scratch_get(ctx, 10, n * sizeof(b381_fp12), &ml);
+        if (rc) return rc;
+        rc = b381_miller_loop_batch_dev(ctx, d_p, d_q, n, (b381_fp12 *)ml);
+        if (rc) return rc;
+        return b381_final_exp_batch_dev(ctx, (const b381_fp12 *)ml, n, d_out, nullptr);
+    }
     int rc = b381_miller_loop_batch_dev(ctx, d_p, d_q, n, d_out);
     if (rc) return rc;
     return b381_final_exp_batch_dev(ctx, d_out, n, d_out, nullptr);

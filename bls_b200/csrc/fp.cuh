@@ -233,6 +233,22 @@ HD void fp_mul_inl(fp &r, const fp &a, const fp &b) {
     for (int i = 0; i < 12; i++) r.l[i] = t[i];
 #endif
 }
+// r = (a*b + c*d) * 2^-384 mod Q, canonical; operands may be as large as 2Q (device only: the VM's MUL2 step)
+#if defined(__CUDACC__)
+__device__ __forceinline__ void fp_dot2_inl(fp &r, const fp &a, const fp &b, const fp &c, const fp &d) {
+    asm(FP_DOT2_PTX
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]),
+          "=r"(r.l[7]), "=r"(r.l[8]), "=r"(r.l[9]), "=r"(r.l[10]), "=r"(r.l[11])
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(a.l[8]), "r"(a.l[9]), "r"(a.l[10]), "r"(a.l[11]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]),
+          "r"(b.l[8]), "r"(b.l[9]), "r"(b.l[10]), "r"(b.l[11]),
+          "r"(c.l[0]), "r"(c.l[1]), "r"(c.l[2]), "r"(c.l[3]), "r"(c.l[4]), "r"(c.l[5]), "r"(c.l[6]), "r"(c.l[7]),
+          "r"(c.l[8]), "r"(c.l[9]), "r"(c.l[10]), "r"(c.l[11]),
+          "r"(d.l[0]), "r"(d.l[1]), "r"(d.l[2]), "r"(d.l[3]), "r"(d.l[4]), "r"(d.l[5]), "r"(d.l[6]), "r"(d.l[7]),
+          "r"(d.l[8]), "r"(d.l[9]), "r"(d.l[10]), "r"(d.l[11]));
+}
+#endif
 // Out-of-line multiply with BY-VALUE operands: nvcc's device ABI passes the 2 x 12 limbs and the
 // result in registers (no local-memory traffic), so every caller shares one 5 KB copy of the
 // multiplication -- the instruction footprint of the tower stays inside the 32 KB L1.5 I-cache

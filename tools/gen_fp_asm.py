@@ -104,6 +104,48 @@ def gen_mul():
     return p
 
 
+def mad2_redc(p, even, odd, a, bi, c, di, first):
+    """one word of the two-product accumulation: acc += a*bi + c*di, then one reduction word"""
+    if first:
+        mul_row(p, odd, a, 1, bi)
+        mul_row(p, even, a, 0, bi)
+    else:
+        p.emit("add.cc", even[0], even[0], odd[1])
+        madc_row_rshift(p, odd, a, 1, bi)
+        cmad_row(p, even, a, 0, bi)
+        p.emit("addc", odd[N - 1], odd[N - 1], 0)
+    cmad_row(p, odd, c, 1, di)
+    cmad_row(p, even, c, 0, di)
+    p.emit("addc", odd[N - 1], odd[N - 1], 0)
+    mi = p.tmp()
+    p.emit("mul.lo", mi, even[0], M0)
+    cmad_row(p, odd, MODL, 1, mi)
+    cmad_row(p, even, MODL, 0, mi)
+    p.emit("addc", odd[N - 1], odd[N - 1], 0)
+
+
+def gen_dot2():
+    """r = (a*b + c*d) * 2^-384 mod Q with ONE interleaved reduction (2*144 + 156 wide MACs):
+    the lazily reduced Fq2 product rows c0 = a0*b0 + a1*(Q - b1), c1 = a0*b1 + a1*b0.
+    Operands may be as large as 2Q (sums formed on the fly): a*b + c*d < 8Q^2 < Q*2^384."""
+    p = Prog()
+    a = ["a%d" % i for i in range(N)] + [0]
+    b = ["b%d" % i for i in range(N)]
+    c = ["c%d" % i for i in range(N)] + [0]
+    d = ["d%d" % i for i in range(N)]
+    even = [p.tmp() for _ in range(N)]
+    odd = [p.tmp() for _ in range(N)]
+    for i in range(0, N, 2):
+        mad2_redc(p, even, odd, a, b[i], c, d[i], i == 0)
+        mad2_redc(p, odd, even, a, b[i + 1], c, d[i + 1], False)
+    p.emit("add.cc", even[0], even[0], odd[1])
+    for i in range(1, N - 1):
+        p.emit("addc.cc", even[i], even[i], odd[i + 1])
+    p.emit("addc", even[N - 1], even[N - 1], 0)
+    final_sub(p, ["r%d" % i for i in range(N)], even)
+    return p
+
+
 def redc_only(p, even, odd, first):
     """one reduction word on the even/odd pair without adding a product row"""
     if not first:
@@ -291,6 +333,23 @@ def selftest():
         out = run(ps, {"a%d" % i: v for i, v in enumerate(limbs(x))})
         got = sum(out["r%d" % i] << (32 * i) for i in range(N))
         assert got == x * x * Rinv % Q, hex(x)
+    # two-product form with operands up to 2Q (and the plain multiplication on the same range)
+    pd = gen_dot2()
+    big = [0, 1, Q - 1, Q, 2 * Q - 1, 2 * Q - 2, Q + 1]
+    cases2 = [(w, x, y, z) for w in big for x in big for y in big[:4] for z in big[3:]]
+    cases2 += [tuple(rng.randrange(2 * Q) for _ in range(4)) for _ in range(3000)]
+    for w, x, y, z in cases2:
+        regs = {}
+        for nm_, v in (("a", w), ("b", x), ("c", y), ("d", z)):
+            regs.update({"%s%d" % (nm_, i): lv for i, lv in enumerate(limbs(v))})
+        out = run(pd, regs)
+        got = sum(out["r%d" % i] << (32 * i) for i in range(N))
+        assert got == (w * x + y * z) * Rinv % Q, (hex(w), hex(x), hex(y), hex(z))
+        out = run(pm, {k: v for k, v in regs.items() if k[0] in "ab"})
+        got = sum(out["r%d" % i] << (32 * i) for i in range(N))
+        assert got == w * x * Rinv % Q
+    nd = sum(1 for i in pd.ins if i[0].startswith(("mul", "mad")))
+    print("dot2 ok: %d cases, %d ins (%d mul/mad)" % (len(cases2), len(pd.ins), nd))
     nm = sum(1 for i in pm.ins if i[0].startswith(("mul", "mad")))
     ns = sum(1 for i in ps.ins if i[0].startswith(("mul", "mad")))
     print("selftest ok: %d cases; mul: %d ins (%d mul/mad), sqr: %d ins (%d mul/mad)" %
@@ -308,9 +367,13 @@ def to_ptx(p, name, nin):
         opn["r%d" % i] = "%%%d" % k; k += 1
     for i in range(N):
         opn["a%d" % i] = "%%%d" % k; k += 1
-    if nin == 2:
+    if nin >= 2:
         for i in range(N):
             opn["b%d" % i] = "%%%d" % k; k += 1
+    if nin == 4:
+        for nm_ in "cd":
+            for i in range(N):
+                opn["%s%d" % (nm_, i)] = "%%%d" % k; k += 1
 
     def o(x):
         if isinstance(x, int):
@@ -342,6 +405,8 @@ def main():
     txt = "// GENERATED by tools/gen_fp_asm.py -- do not edit.\n"
     txt += "// FP_MUL_PTX: operands %0..%11 = r (out), %12..%23 = a, %24..%35 = b\n"
     txt += to_ptx(gen_mul(), "FP_MUL_PTX", 2)
+    txt += "// FP_DOT2_PTX: %0..%11 = r (out), %12..%23 = a, %24..%35 = b, %36..%47 = c, %48..%59 = d;  r = (a*b + c*d) * 2^-384 mod Q\n"
+    txt += to_ptx(gen_dot2(), "FP_DOT2_PTX", 4)
     out.write_text(txt)
     print("wrote", out)
 

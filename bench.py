@@ -96,6 +96,112 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def traffic_from_profiles(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full
+    summary (profiles/traffic.json, written by tools/ncu_summary.py --traffic); None if not captured"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except (OSError, ValueError):
+        return None
+
+
+def aggregate_extras(ctx, stream, dev, rank, world, torch, np):
+    """aggregate-verification side of the metric (BASELINE.json configs 3-5), device-resident inputs, CUDA events:
+    (a) one g1pubs VerifyAggregateCommon over 2^20 public keys (sum kernel + one 2-pair check),
+    (b) a batch of 2^14 attestations x 128-key committees (Ethereum-beacon shape),
+    (c) a 2^20-point G1 MSM with 255-bit scalars; under torchrun also bucket-sharded over the ranks with one
+        all-gather of 144-byte partials (bls_b200/dist.py)."""
+    import torch.distributed as dist
+    from bls_b200 import hostgen as hg, layout as L, dist as bd
+    out = {}
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).to(dev)
+
+    def timed(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        best = None
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); fn(); e1.record(stream); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        return best
+    m = 1 << 14
+    s0, d0 = 0xA66, 0x51              # same registry on every rank (replicated, as in SURVEY.md 8e)
+    keys = hg.g1_progression(s0, d0, m)                                   # sk_i = s0 + i d0
+    sk_sum = sum(s0 + i * d0 for i in range(m)) % L.R_ORDER
+    # (a) 2^20 keys = the 2^14 distinct keys tiled 64x (throughput of the reduction does not depend on the values)
+    n_a = 1 << 20
+    dK = up(np.resize(keys, n_a))
+    dPk = torch.empty(144, dtype=torch.uint8, device=dev)
+    h = 0x1234567
+    Hm = hg.g2_mul(h)                                                     # stand-in for HashG2(m): the Go host hashes
+    sig = hg.g2_mul(64 * sk_sum * h)
+    g1one = hg.g1_mul(1)
+    dOk = torch.empty(1, dtype=torch.uint8, device=dev)
+    dOff = up(np.array([0, 2], np.uint32))
+    dPP = torch.empty(2 * 104, dtype=torch.uint8, device=dev); dQQ = up(np.concatenate([sig, Hm]))
+    hostPk = np.zeros(1, dtype=L.G1_JAC)
+
+    def one_verify():
+        ctx.dev("b381_g1_sum_dev", dK.data_ptr(), ctypes.c_size_t(n_a), dPk.data_ptr())
+    t_sum = timed(one_verify)
+    ctx.call("b381_d2h", ctypes.c_void_p(hostPk.ctypes.data), ctypes.c_void_p(dPk.data_ptr()), ctypes.c_size_t(144))
+    agg = np.zeros(1, dtype=L.G1_AFFINE); agg["x"] = hostPk["x"]; agg["y"] = hostPk["y"]
+    assert agg.tobytes() == hg.g1_mul(64 * sk_sum).tobytes(), "aggregate public key differs from the closed form"
+    PP = np.concatenate([g1one, hg.g1_neg(agg)])
+    dPP.copy_(up(PP))
+    t_chk = timed(lambda: ctx.dev("b381_pairing_product_is_one_dev", dPP.data_ptr(), dQQ.data_ptr(), ctypes.c_size_t(2),
+                                  dOff.data_ptr(), ctypes.c_size_t(1), dOk.data_ptr()))
+    assert int(dOk.cpu()[0]) == 1, "aggregate verification failed on a valid signature"
+    out["verify_aggregate_common_2^20_keys"] = {"sum_ms": t_sum, "pairing_check_ms": t_chk,
+                                                 "verifies_per_s": 1e3 / (t_sum + t_chk)}
+    # (b) attestation batch: 64 distinct (committee, message) templates tiled to 2^14 attestations, 1 in 64 corrupted
+    natt, comm, ntmpl = 1 << 14, 128, 64
+    rng = np.random.RandomState(1 + rank)
+    tk = rng.randint(0, m, size=(ntmpl, comm))
+    hs = [0x77 + 5 * j for j in range(8)]
+    Hs = np.concatenate([hg.g2_mul(x) for x in hs])
+    sigs, expect = [], []
+    for t in range(ntmpl):
+        sk = sum(s0 + int(i) * d0 for i in tk[t]) % L.R_ORDER
+        bad = t == 7
+        sigs.append(hg.g2_mul((sk + (1 if bad else 0)) * hs[t % 8])); expect.append(0 if bad else 1)
+    kidx = np.tile(tk.reshape(-1), natt // ntmpl).astype(np.uint32)
+    koff = (np.arange(natt + 1) * comm).astype(np.uint32)
+    dA = [up(x) for x in (keys, kidx, koff, np.tile(np.concatenate(sigs), natt // ntmpl), Hs,
+                          np.tile(np.arange(ntmpl) % 8, natt // ntmpl).astype(np.uint32))]
+    dOkA = torch.empty(natt, dtype=torch.uint8, device=dev)
+    t_att = timed(lambda: ctx.dev("b381_verify_aggregate_common_batch_dev", *[x.data_ptr() for x in dA], ctypes.c_size_t(natt),
+                                  dOkA.data_ptr()), reps=2)
+    assert dOkA.cpu().numpy()[:ntmpl].tolist() == expect, "attestation batch verdicts differ from construction"
+    ta = torch.tensor([t_att], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+    out["attestation_batch_2^14_x_128_keys"] = {"ms": float(ta.item()), "aggregate_verifies_per_s": world * natt / (float(ta.item()) * 1e-3)}
+    # (c) MSM 2^20, closed-form check on the tiled points: sum k_i P_(i mod m)
+    n_c = 1 << 20
+    K, kvals = hg.splitmix_scalars(99, 1 << 12)
+    dKs = up(np.resize(K, (n_c, 4)))
+    dOut = torch.empty(144, dtype=torch.uint8, device=dev)
+    t_msm = timed(lambda: ctx.dev("b381_g1_msm_dev", dK.data_ptr(), dKs.data_ptr(), ctypes.c_size_t(n_c), dOut.data_ptr()))
+    ctx.call("b381_d2h", ctypes.c_void_p(hostPk.ctypes.data), ctypes.c_void_p(dOut.data_ptr()), ctypes.c_size_t(144))
+    S = sum(kvals[i % 4096] * (s0 + (i % m) * d0) for i in range(n_c)) % L.R_ORDER
+    agg["x"] = hostPk["x"]; agg["y"] = hostPk["y"]
+    assert agg.tobytes() == hg.g1_mul(S).tobytes(), "MSM result differs from the closed form"
+    out["g1_msm_2^20_255bit"] = {"ms": t_msm, "points_per_s": n_c / (t_msm * 1e-3)}
+    if world > 1:
+        dParts = torch.empty(world * 144, dtype=torch.uint8, device=dev)
+        t_sh = timed(lambda: bd.msm_bucket_sharded_dev(ctx, dK, dKs, n_c, dParts, dOut))
+        ts = torch.tensor([t_sh], dtype=torch.float64, device=dev)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        ctx.call("b381_d2h", ctypes.c_void_p(hostPk.ctypes.data), ctypes.c_void_p(dOut.data_ptr()), ctypes.c_size_t(144))
+        agg["x"] = hostPk["x"]; agg["y"] = hostPk["y"]
+        assert agg.tobytes() == hg.g1_mul(S).tobytes(), "bucket-sharded MSM differs from the closed form"
+        out["g1_msm_2^20_bucket_sharded"] = {"ms": float(ts.item()), "ranks": world, "exchange": "all_gather of %d x 144 B + fold" % world}
+    return out
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -232,7 +338,21 @@ def run_engine(args):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         best = ms if best is None else min(best, ms)
-    imad_peak = pb * pt * pi * 8 / (best * 1e-3)          # wide MACs per second
+    imad_peak_plain = pb * pt * pi * 8 / (best * 1e-3)    # wide MACs per second, independent 64-bit accumulates
+    # the engine's own multiplier in a register-only dependent chain (carry-chained IMAD.WIDE.U32.X): the practical peak
+    fb, ft, fi = 148 * 4, 256, 2048
+    probe2 = torch.empty(fb * ft, dtype=torch.int32, device=dev)
+    best2 = None
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.dev("b381_fpmul_probe_dev", probe2.data_ptr(), fb, ft, fi)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best2 = ms if best2 is None else min(best2, ms)
+    imad_peak_chain = fb * ft * fi * MACS_PER_FQ_MUL / (best2 * 1e-3)
+    imad_peak = max(imad_peak_plain, imad_peak_chain)
 
     # ---- e2e: public host-buffer call, H2D + kernels + D2H inside the timed region ----------------
     pP = ctypes.c_void_p(hP.data_ptr()); pQ = ctypes.c_void_p(hQ.data_ptr()); pO = ctypes.c_void_p(hOut.data_ptr())
@@ -253,6 +373,7 @@ def run_engine(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / float(te.item())
 
+    extras = aggregate_extras(ctx, stream, dev, rank, world, torch, np) if not args.no_aggregate else None
     # ---- result check (sample vs the oracle) + CPU baseline on rank 0 ---------------------------
     if rank == 0:
         from oracle import pyoracle as orc
@@ -285,14 +406,17 @@ def run_engine(args):
                 "bound": "int32-imad (no HBM or tensor bound: ~4.4M wide MACs per 880 B of I/O)",
                 "kernel": dom, "achieved": achieved / 1e12, "peak": imad_peak / 1e12,
                 "unit": "T wide-MAC/s (IMAD.WIDE.U32)", "frac": achieved / imad_peak,
-                "peak_source": "k_imad_probe measured in this run on this GPU (MEASURED_PEAKS.json has no integer peak)",
-                "traffic": None,
+                "peak_source": "measured in this run on this GPU: max of k_fpmul_probe (dependent Fq-multiplication chain, "
+                               "%.2f T/s) and k_imad_probe (independent mad.wide chains, %.2f T/s); MEASURED_PEAKS.json has no "
+                               "integer peak" % (imad_peak_chain / 1e12, imad_peak_plain / 1e12),
+                "traffic": traffic_from_profiles(dom),
                 "kernels_ms": kt,
                 "fq_mul_per_pairing": {"impl_miller": W_IMPL_MILLER, "impl_final_exp": W_IMPL_FINAL_EXP, "reference": W_REF},
                 "ref_equivalent_frac": (n * W_REF * MACS_PER_FQ_MUL / ((kt["k_miller_loop"] + kt["k_final_exp"]) * 1e-3)) / imad_peak,
                 "hbm_gbs_sanity": n * (104 + 200 + 576 * 3) / ((kt["k_miller_loop"] + kt["k_final_exp"]) * 1e-3) / 1e9,
             },
         }
+        line["aggregate"] = extras
         threads = host_threads()
         cv, cn, ct = cpu_baseline(threads, args.cpu_seconds, P, Q)
         line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
@@ -311,6 +435,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the cpu_baseline sample")
+    ap.add_argument("--no-aggregate", action="store_true", help="skip the aggregate-verification extras (configs 3-5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
     if args.impl == "reference":

@@ -82,6 +82,18 @@ __global__ void __launch_bounds__(PAIRING_BLOCK, PAIRING_MIN_BLOCKS) k_final_exp
     ok[i] = (good && fp12_is_one(&r)) ? 1 : 0;
 }
 
+// ok[i] &= (fe[i] == 1)   (the Equals(FQ12One) of pairing.go:146 after a separate final-exponentiation pass)
+__global__ void k_fp12_is_one(const uint64_t *__restrict__ fe, size_t n, uint8_t *__restrict__ ok) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t one[12] = {B381_ONE_LIMBS};
+    const uint64_t *p = fe + 72 * i;
+    uint64_t d = 0;
+    for (int k = 0; k < 6; k++) d |= p[k] ^ ((uint64_t)one[2 * k] | ((uint64_t)one[2 * k + 1] << 32));
+    for (int k = 6; k < 72; k++) d |= p[k];
+    ok[i] = (ok[i] && d == 0) ? 1 : 0;
+}
+
 // Roofline denominator: sustained issue rate of IMAD.WIDE.U32 (the 32x32->64 multiply-accumulate
 // every Fq multiplication is made of).  8 independent chains per thread; each thread executes
 // iters * 8 wide MACs.
@@ -102,6 +114,21 @@ __global__ void k_imad_probe(uint32_t *out, int iters) {
 #pragma unroll
     for (int j = 0; j < 8; j++) r ^= acc[j];
     out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)r ^ (uint32_t)(r >> 32);
+}
+
+// The same roofline measured through the engine's own multiplier: a register-only dependent chain of
+// fp_mul (300 IMAD.WIDE.U32[.X] each).  This is the number the pairing kernels are compared with:
+// the carry-chained form reaches 32 lanes/clk/SM, the plain 64-bit accumulate of k_imad_probe less.
+__global__ void __launch_bounds__(256) k_fpmul_probe(uint32_t *out, int iters) {
+    fp x, y;
+#pragma unroll
+    for (int j = 0; j < 12; j++) { x.l[j] = (blockIdx.x * 977u + threadIdx.x * 131u + j) & 0x0fffffffu; y.l[j] = (threadIdx.x * 7919u + j * 13u) & 0x0fffffffu; }
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) fp_mul_inl(x, x, y);
+    uint32_t r = 0;
+#pragma unroll
+    for (int j = 0; j < 12; j++) r ^= x.l[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -147,6 +174,8 @@ static int scratch_get(b381_ctx *ctx, int slot, size_t bytes, void **out) {
 }
 
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+#define VM_MAX_UNITS 20480      // measured crossover on B200 (tools/small_bench.py): 16384 pairings 21.0 ms (VM) vs 24.2 ms; 32768: 39.5 vs 33.6
+static inline bool vm_for(const b381_ctx *ctx, size_t n) { return ctx->use_vm < 0 ? n <= VM_MAX_UNITS : ctx->use_vm != 0; }
 static inline size_t vm_smem_bytes(int lanes, int nslots) { return 448 + (size_t)VM_WARPS * (32 / lanes) * nslots * 48; }
 
 // run VM program `which` over n units; seg[i] = (base, stride) of the per-unit global areas
@@ -199,8 +228,11 @@ int b381_init(int device, b381_ctx **out) {
         if (sm > max_smem) max_smem = sm;
     }
     if (cudaFuncSetAttribute(k_vm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess) { b381_free(ctx); return B381_ERR_CUDA; }
-    const char *ev = getenv("B381_VM");           // measurement knob: B381_VM=0 runs the thread-per-pairing kernels instead
-    ctx->use_vm = !(ev && ev[0] == '0');
+    // Two schedules of the same arithmetic: the warp-cooperative VM (4 pairings per warp, state in shared memory:
+    // 3x lower latency, fills the GPU from ~8 k pairings) and one pairing per thread (higher throughput once
+    // ~75 k threads are resident).  Default: by batch size; B381_VM=0/1 forces one of them for A/B measurements.
+    const char *ev = getenv("B381_VM");
+    ctx->use_vm = ev ? (ev[0] == '0' ? 0 : 1) : -1;
     *out = ctx;
     return B381_OK;
 }
@@ -267,12 +299,20 @@ int b381_imad_probe_dev(b381_ctx *ctx, uint32_t *d_out, int blocks, int threads,
     return B381_OK;
 }
 
+int b381_fpmul_probe_dev(b381_ctx *ctx, uint32_t *d_out, int blocks, int threads, int iters) {
+    if (!ctx || !d_out || blocks <= 0 || threads <= 0 || threads > 256 || iters <= 0) return B381_ERR_ARG;
+    k_fpmul_probe<<<blocks, threads, 0, ctx->stream>>>(d_out, iters);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+
 // ---- pairing, device-resident ------------------------------------------------------------------
 int b381_miller_loop_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_affine *d_q, size_t n,
                                b381_fp12 *d_out) {
     if (!ctx || (n && (!d_p || !d_q || !d_out))) return B381_ERR_ARG;
     if (!n) return B381_OK;
-    if (ctx->use_vm) {
+    if (vm_for(ctx, n)) {
         vm_seg seg[4] = {{(unsigned char *)d_p, sizeof(b381_g1_affine)}, {(unsigned char *)d_q, sizeof(b381_g2_affine)},
                          {(unsigned char *)d_out, sizeof(b381_fp12)}, {nullptr, 0}};
         return vm_run(ctx, VM_ML1, seg, n, (const unsigned char *)d_p + 96, sizeof(b381_g1_affine),
@@ -287,7 +327,7 @@ int b381_miller_loop_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b
 int b381_final_exp_batch_dev(b381_ctx *ctx, const b381_fp12 *d_in, size_t n, b381_fp12 *d_out, uint8_t *d_ok) {
     if (!ctx || (n && (!d_in || !d_out))) return B381_ERR_ARG;
     if (!n) return B381_OK;
-    if (ctx->use_vm) {
+    if (vm_for(ctx, n)) {
         // fe_a: f -> the Fq norm the inversion needs; one thread per element inverts it; fe_c: the rest
         void *nrm, *spill, *fcopy, *dok = d_ok;
         int rc = scratch_get(ctx, 8, n * 2 * sizeof(b381_fp), &nrm);
@@ -320,7 +360,7 @@ int b381_final_exp_batch_dev(b381_ctx *ctx, const b381_fp12 *d_in, size_t n, b38
 }
 int b381_pairing_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_affine *d_q, size_t n,
                            b381_fp12 *d_out) {
-    if (ctx && ctx->use_vm && n) {
+    if (ctx && n && vm_for(ctx, n)) {
         void *ml;
         int rc = scratch_get(ctx, 10, n * sizeof(b381_fp12), &ml);
         if (rc) return rc;
@@ -346,6 +386,14 @@ int b381_pairing_product_is_one_dev(b381_ctx *ctx, const b381_g1_affine *d_p, co
     k_group_product<<<grid_for(ngroups, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>(
         (const uint64_t *)ml, d_group_off, ngroups, (uint64_t *)prod);
     ctx->launches++;
+    if (vm_for(ctx, ngroups)) {          // few groups: the warp-cooperative final exponentiation has 3x lower latency
+        rc = b381_final_exp_batch_dev(ctx, (const b381_fp12 *)prod, ngroups, (b381_fp12 *)prod, d_ok);
+        if (rc) return rc;
+        k_fp12_is_one<<<grid_for(ngroups, 128), 128, 0, ctx->stream>>>((const uint64_t *)prod, ngroups, d_ok);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return B381_OK;
+    }
     k_final_exp_is_one<<<grid_for(ngroups, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>((const uint64_t *)prod,
                                                                                           ngroups, d_ok);
     ctx->launches++;

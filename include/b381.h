@@ -139,6 +139,10 @@ int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *
  * independent IMAD.WIDE.U32 (the 32x32->64 multiply-accumulate an Fq multiplication is made of).
  * d_out needs blocks*threads u32.  Time it with events on the ctx stream.                        */
 int b381_imad_probe_dev(b381_ctx *ctx, uint32_t *d_out, int blocks, int threads, int iters);
+/* The same roofline through the engine's own Fq multiplier: every thread runs a dependent chain of
+ * iters Montgomery multiplications held in registers (300 carry-chained IMAD.WIDE.U32 each); threads <= 256.
+ * The faster of the two probes is the denominator bench.py reports against.                         */
+int b381_fpmul_probe_dev(b381_ctx *ctx, uint32_t *d_out, int blocks, int threads, int iters);
 
 #ifdef __cplusplus
 }

@@ -87,7 +87,15 @@ def final_sub(p, r, x):
         p.emit("selb", r[i], x[i], d[i], bw)   # r = bw ? x : d
 
 
-def gen_mul():
+def finish(p, even, reduce):
+    if reduce:
+        final_sub(p, ["r%d" % i for i in range(N)], even)
+    else:                                   # lazily reduced result in [0, 2Q): the caller reduces after adding its addends
+        for i in range(N):
+            p.emit("mov", "r%d" % i, even[i])
+
+
+def gen_mul(reduce=True):
     p = Prog()
     a = ["a%d" % i for i in range(N)] + [0]
     b = ["b%d" % i for i in range(N)]
@@ -100,7 +108,7 @@ def gen_mul():
     for i in range(1, N - 1):
         p.emit("addc.cc", even[i], even[i], odd[i + 1])
     p.emit("addc", even[N - 1], even[N - 1], 0)
-    final_sub(p, ["r%d" % i for i in range(N)], even)
+    finish(p, even, reduce)
     return p
 
 
@@ -124,7 +132,7 @@ def mad2_redc(p, even, odd, a, bi, c, di, first):
     p.emit("addc", odd[N - 1], odd[N - 1], 0)
 
 
-def gen_dot2():
+def gen_dot2(reduce=True):
     """r = (a*b + c*d) * 2^-384 mod Q with ONE interleaved reduction (2*144 + 156 wide MACs):
     the lazily reduced Fq2 product rows c0 = a0*b0 + a1*(Q - b1), c1 = a0*b1 + a1*b0.
     Operands may be as large as 2Q (sums formed on the fly): a*b + c*d < 8Q^2 < Q*2^384."""
@@ -142,7 +150,7 @@ def gen_dot2():
     for i in range(1, N - 1):
         p.emit("addc.cc", even[i], even[i], odd[i + 1])
     p.emit("addc", even[N - 1], even[N - 1], 0)
-    final_sub(p, ["r%d" % i for i in range(N)], even)
+    finish(p, even, reduce)
     return p
 
 
@@ -348,6 +356,16 @@ def selftest():
         out = run(pm, {k: v for k, v in regs.items() if k[0] in "ab"})
         got = sum(out["r%d" % i] << (32 * i) for i in range(N))
         assert got == w * x * Rinv % Q
+    # lazily reduced variants: same residue, value below 2Q
+    pmn, pdn = gen_mul(False), gen_dot2(False)
+    for w, x, y, z in cases2[::3]:
+        regs = {}
+        for nm_, v in (("a", w), ("b", x), ("c", y), ("d", z)):
+            regs.update({"%s%d" % (nm_, i): lv for i, lv in enumerate(limbs(v))})
+        got = sum(run(pdn, regs)["r%d" % i] << (32 * i) for i in range(N))
+        assert got < 2 * Q and got % Q == (w * x + y * z) * Rinv % Q
+        got = sum(run(pmn, {k: v for k, v in regs.items() if k[0] in "ab"})["r%d" % i] << (32 * i) for i in range(N))
+        assert got < 2 * Q and got % Q == w * x * Rinv % Q
     nd = sum(1 for i in pd.ins if i[0].startswith(("mul", "mad")))
     print("dot2 ok: %d cases, %d ins (%d mul/mad)" % (len(cases2), len(pd.ins), nd))
     nm = sum(1 for i in pm.ins if i[0].startswith(("mul", "mad")))
@@ -407,6 +425,9 @@ def main():
     txt += to_ptx(gen_mul(), "FP_MUL_PTX", 2)
     txt += "// FP_DOT2_PTX: %0..%11 = r (out), %12..%23 = a, %24..%35 = b, %36..%47 = c, %48..%59 = d;  r = (a*b + c*d) * 2^-384 mod Q\n"
     txt += to_ptx(gen_dot2(), "FP_DOT2_PTX", 4)
+    txt += "// FP_MUL_NR_PTX / FP_DOT2_NR_PTX: the same without the final conditional subtraction: result in [0, 2Q)\n"
+    txt += to_ptx(gen_mul(False), "FP_MUL_NR_PTX", 2)
+    txt += to_ptx(gen_dot2(False), "FP_DOT2_NR_PTX", 4)
     out.write_text(txt)
     print("wrote", out)
 

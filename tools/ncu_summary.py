@@ -26,6 +26,28 @@ def summary(path):
                     pass
                 out.append("| %s | %s | %s |" % (h, u, v))
     return "\n".join(out)
+def traffic(path):
+    """kernel name -> dram bytes (read + write) of the first captured launch of each kernel"""
+    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    h, u = rows[0], rows[1]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    out = {}
+    for r in rows[2:]:
+        name = r[h.index("Kernel Name")].split("(")[0].split("<")[0].replace("void ", "").replace("b381::", "")
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = h.index(key)
+            tot += float(r[i]) * scale.get(u[i], 1)
+        out.setdefault(name, tot)
+    return out
 if __name__ == "__main__":
+    if sys.argv[1] == "--traffic":
+        import json
+        t = {}
+        for p in sys.argv[2:]:
+            t.update(traffic(p))
+        print(json.dumps(t))
+        sys.exit(0)
     for p in sys.argv[1:]:
         print("## " + p); print(summary(p))

@@ -93,7 +93,7 @@ def run_reference(args):
                                    "Go toolchain unavailable)" % (args.steps, per_step)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def traffic_from_profiles(kernel):
@@ -422,13 +422,30 @@ def run_engine(args):
         line["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "%d pairings in %.1f s on %d host threads (C++ restatement of "
                                           "phoreproject/bls pure-Go path; Go toolchain unavailable)" % (cn, ct, threads)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line of the contract goes to the real stdout; everything else a library prints on fd 1
+    (e.g. NCCL's version banner) was redirected to stderr in main()"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

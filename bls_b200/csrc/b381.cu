@@ -11,7 +11,7 @@
 #include "pairing.cuh"
 #include "curve.cuh"
 #include "agg.cuh"
-#include "vm.cuh"
+#include "vm2.cuh"
 #include "vm_programs.inc"
 #include <stdlib.h>
 
@@ -176,19 +176,19 @@ static int scratch_get(b381_ctx *ctx, int slot, size_t bytes, void **out) {
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 #define VM_MAX_UNITS 20480      // measured crossover on B200 (tools/small_bench.py): 16384 pairings 21.0 ms (VM) vs 24.2 ms; 32768: 39.5 vs 33.6
 static inline bool vm_for(const b381_ctx *ctx, size_t n) { return ctx->use_vm < 0 ? n <= VM_MAX_UNITS : ctx->use_vm != 0; }
-static inline size_t vm_smem_bytes(int lanes, int nslots) { return 448 + (size_t)VM_WARPS * (32 / lanes) * nslots * 48; }
+static inline size_t vm_smem_bytes(int lanes, int nslots) { return (size_t)VM2_WARPS * (32 / lanes) * nslots * 96; }
 
 // run VM program `which` over n units; seg[i] = (base, stride) of the per-unit global areas
 static int vm_run(b381_ctx *ctx, int which, const vm_seg seg[4], size_t n, const unsigned char *flag_a, size_t fsa,
                   const unsigned char *flag_b, size_t fsb, unsigned char *ok) {
-    vm_args A;
+    vm2_args A;
     for (int i = 0; i < 4; i++) A.seg[i] = seg[i];
     A.seg[4].base = (unsigned char *)ctx->vm[which].consts; A.seg[4].stride = 0;
     A.code = ctx->vm[which].code;
     A.nsteps = ctx->vm[which].nsteps; A.nslots = ctx->vm[which].nslots; A.n = n;
     A.flag_a = flag_a; A.flag_b = flag_b; A.flag_stride_a = fsa; A.flag_stride_b = fsb; A.ok = ok;
-    int lanes = ctx->vm[which].lanes, upb = VM_WARPS * (32 / lanes);
-    k_vm<8><<<grid_for(n, upb), VM_WARPS * 32, vm_smem_bytes(lanes, A.nslots), ctx->stream>>>(A);
+    int lanes = ctx->vm[which].lanes, upb = VM2_WARPS * (32 / lanes);
+    k_vm2<4><<<grid_for(n, upb), VM2_WARPS * 32, vm_smem_bytes(lanes, A.nslots), ctx->stream>>>(A);
     ctx->launches++;
     CK(cudaGetLastError());
     return B381_OK;
@@ -219,7 +219,7 @@ int b381_init(int device, b381_ctx **out) {
     size_t max_smem = 0;
     for (int i = 0; i < 3; i++) {
         const vm_program_image &im = vm_program_images[i];
-        size_t cb = (size_t)im.nsteps * im.lanes * 32, kb = (size_t)im.nconsts * 48;
+        size_t cb = (size_t)im.nsteps * im.lanes * 64, kb = (size_t)im.nconsts * 96;
         if (cudaMalloc(&ctx->vm[i].code, cb) != cudaSuccess || cudaMalloc(&ctx->vm[i].consts, kb) != cudaSuccess ||
             cudaMemcpy(ctx->vm[i].code, im.code, cb, cudaMemcpyHostToDevice) != cudaSuccess ||
             cudaMemcpy(ctx->vm[i].consts, im.consts, kb, cudaMemcpyHostToDevice) != cudaSuccess) { b381_free(ctx); return B381_ERR_CUDA; }
@@ -227,7 +227,8 @@ int b381_init(int device, b381_ctx **out) {
         size_t sm = vm_smem_bytes(im.lanes, im.nslots);
         if (sm > max_smem) max_smem = sm;
     }
-    if (cudaFuncSetAttribute(k_vm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess) { b381_free(ctx); return B381_ERR_CUDA; }
+    if (max_smem < 200 * 1024) max_smem = 200 * 1024;
+    if (cudaFuncSetAttribute(k_vm2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess) { b381_free(ctx); return B381_ERR_CUDA; }
     // Two schedules of the same arithmetic: the warp-cooperative VM (4 pairings per warp, state in shared memory:
     // 3x lower latency, fills the GPU from ~8 k pairings) and one pairing per thread (higher throughput once
     // ~75 k threads are resident).  Default: by batch size; B381_VM=0/1 forces one of them for A/B measurements.
@@ -304,6 +305,32 @@ int b381_fpmul_probe_dev(b381_ctx *ctx, uint32_t *d_out, int blocks, int threads
     k_fpmul_probe<<<blocks, threads, 0, ctx->stream>>>(d_out, iters);
     ctx->launches++;
     CK(cudaGetLastError());
+    return B381_OK;
+}
+
+// test hook: run an arbitrary VM program (host-side encoded image) over n units
+int b381_vm_exec_dev(b381_ctx *ctx, const void *code, int lanes, int nsteps, int nslots, const void *consts, int nconsts,
+                     void *const d_seg[4], const size_t stride[4], size_t n) {
+    if (!ctx || !code || lanes != 4 || nsteps <= 0 || nslots <= 0 || !d_seg || !stride) return B381_ERR_ARG;
+    uint4 *dcode = nullptr, *dconst = nullptr;
+    size_t cb = (size_t)nsteps * lanes * 64, kb = (size_t)(nconsts > 0 ? nconsts : 1) * 96;
+    CK(cudaMalloc(&dcode, cb));
+    CK(cudaMalloc(&dconst, kb));
+    CK(cudaMemcpy(dcode, code, cb, cudaMemcpyHostToDevice));
+    if (nconsts > 0) CK(cudaMemcpy(dconst, consts, kb, cudaMemcpyHostToDevice));
+    vm2_args A;
+    for (int i = 0; i < 4; i++) { A.seg[i].base = (unsigned char *)d_seg[i]; A.seg[i].stride = stride[i]; }
+    A.seg[4].base = (unsigned char *)dconst; A.seg[4].stride = 0;
+    A.code = dcode; A.nsteps = nsteps; A.nslots = nslots; A.n = n;
+    A.flag_a = A.flag_b = nullptr; A.flag_stride_a = A.flag_stride_b = 0; A.ok = nullptr;
+    size_t sm = vm_smem_bytes(lanes, nslots);
+    if (sm > 200 * 1024) { cudaFree(dcode); cudaFree(dconst); return B381_ERR_ARG; }
+    CK(cudaFuncSetAttribute(k_vm2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_vm2<4><<<grid_for(n, VM2_WARPS * (32 / lanes)), VM2_WARPS * 32, sm, ctx->stream>>>(A);
+    ctx->launches++;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dcode); cudaFree(dconst);
+    if (e != cudaSuccess) { snprintf(ctx->err, sizeof ctx->err, "vm_exec: %s", cudaGetErrorString(e)); return B381_ERR_CUDA; }
     return B381_OK;
 }
 

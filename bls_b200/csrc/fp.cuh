@@ -249,11 +249,62 @@ __device__ __forceinline__ void fp_dot2_inl(fp &r, const fp &a, const fp &b, con
           "r"(d.l[8]), "r"(d.l[9]), "r"(d.l[10]), "r"(d.l[11]));
 }
 #endif
+// r = a + b without reduction (operands of a multiplication may be as large as 2Q)
+HD void fp_add_nr(fp &r, const fp &a, const fp &b) {
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32 %0, %12, %24;\n\taddc.cc.u32 %1, %13, %25;\n\taddc.cc.u32 %2, %14, %26;\n\taddc.cc.u32 %3, %15, %27;\n\t"
+        "addc.cc.u32 %4, %16, %28;\n\taddc.cc.u32 %5, %17, %29;\n\taddc.cc.u32 %6, %18, %30;\n\taddc.cc.u32 %7, %19, %31;\n\t"
+        "addc.cc.u32 %8, %20, %32;\n\taddc.cc.u32 %9, %21, %33;\n\taddc.cc.u32 %10, %22, %34;\n\taddc.u32 %11, %23, %35;"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]),
+          "=r"(r.l[8]), "=r"(r.l[9]), "=r"(r.l[10]), "=r"(r.l[11])
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(a.l[8]), "r"(a.l[9]), "r"(a.l[10]), "r"(a.l[11]),
+          "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]),
+          "r"(b.l[8]), "r"(b.l[9]), "r"(b.l[10]), "r"(b.l[11]));
+#else
+    uint64_t c = 0;
+    for (int i = 0; i < 12; i++) { uint64_t v = (uint64_t)a.l[i] + b.l[i] + c; r.l[i] = (uint32_t)v; c = v >> 32; }
+#endif
+}
+// r = Q - a   (in (0, Q]; used as a negated multiplication operand)
+HD void fp_qminus(fp &r, const fp &a) {
+    const uint32_t q[12] = {B381_Q_LIMBS};
+#if defined(__CUDA_ARCH__)
+    asm("sub.cc.u32 %0, %12, %24;\n\tsubc.cc.u32 %1, %13, %25;\n\tsubc.cc.u32 %2, %14, %26;\n\tsubc.cc.u32 %3, %15, %27;\n\t"
+        "subc.cc.u32 %4, %16, %28;\n\tsubc.cc.u32 %5, %17, %29;\n\tsubc.cc.u32 %6, %18, %30;\n\tsubc.cc.u32 %7, %19, %31;\n\t"
+        "subc.cc.u32 %8, %20, %32;\n\tsubc.cc.u32 %9, %21, %33;\n\tsubc.cc.u32 %10, %22, %34;\n\tsubc.u32 %11, %23, %35;"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]),
+          "=r"(r.l[8]), "=r"(r.l[9]), "=r"(r.l[10]), "=r"(r.l[11])
+        : "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]), "r"(q[4]), "r"(q[5]), "r"(q[6]), "r"(q[7]), "r"(q[8]), "r"(q[9]),
+          "r"(q[10]), "r"(q[11]),
+          "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(a.l[8]), "r"(a.l[9]), "r"(a.l[10]), "r"(a.l[11]));
+#else
+    int64_t br = 0;
+    for (int i = 0; i < 12; i++) { int64_t t = (int64_t)q[i] - a.l[i] + br; r.l[i] = (uint32_t)t; br = t >> 32; }
+#endif
+}
 // Out-of-line multiply with BY-VALUE operands: nvcc's device ABI passes the 2 x 12 limbs and the
 // result in registers (no local-memory traffic), so every caller shares one 5 KB copy of the
 // multiplication -- the instruction footprint of the tower stays inside the 32 KB L1.5 I-cache
 // (profiles/r01_v1_ncu_summary.md: `no_instruction` was the top stall with the body inlined).
 HDN fp fp_mul_v(fp a, fp b) { fp r; fp_mul_inl(r, a, b); return r; }
+// r = (a*b + c*d) * 2^-384 mod Q with ONE reduction (444 instead of 600 wide MACs): the rows of an Fq2 product
+// (fq2.go:116-130 computes the same values with Karatsuba: three reduced multiplications and five additions)
+HDN fp fp_dot2_v(fp a, fp b, fp c, fp d) {
+    fp r;
+#if defined(__CUDA_ARCH__)
+    fp_dot2_inl(r, a, b, c, d);
+#else
+    uint32_t t[12], u[12];
+    hostimpl::mul(t, a.l, b.l);
+    hostimpl::mul(u, c.l, d.l);
+    fp x, y;
+    for (int i = 0; i < 12; i++) { x.l[i] = t[i]; y.l[i] = u[i]; }
+    fp_add(r, x, y);
+#endif
+    return r;
+}
 HD void fp_mul(fp &r, const fp &a, const fp &b) { r = fp_mul_v(a, b); }
 HD void fp_sqr(fp &r, const fp &a) { r = fp_mul_v(a, a); }   // fq.go:151-198
 

@@ -11,7 +11,7 @@
 #include "pairing.cuh"
 #include "curve.cuh"
 #include "agg.cuh"
-#include "vm2.cuh"
+#include "vm.cuh"
 #include "vm_programs.inc"
 #include <stdlib.h>
 
@@ -25,9 +25,13 @@ static_assert(sizeof(b381_g1_jac) == 144 && sizeof(b381_g2_jac) == 288, "layout"
 // ---------------------------------------------------------------------------------------------
 // kernels: one thread per independent unit
 // ---------------------------------------------------------------------------------------------
-#define PAIRING_BLOCK 128
+#ifdef PAIRING_BLOCK_OVERRIDE
+#define PAIRING_BLOCK PAIRING_BLOCK_OVERRIDE
+#else
+#define PAIRING_BLOCK 64    // 1024 blocks for 2^16 pairings spread evenly over 148 SMs x 8 resident blocks (measured +2.5 % over 128)
+#endif
 #ifndef PAIRING_MIN_BLOCKS
-#define PAIRING_MIN_BLOCKS 4   // 128 registers -> 16 warps/SM: measured 1.15 M pairings/s vs 0.90 M at 3 blocks (162 regs), 1.10 M at 5
+#define PAIRING_MIN_BLOCKS 8   // 128 registers -> 16 warps/SM: measured 1.18 M pairings/s vs 0.90 M at 12 warps (162 regs), 1.10 M at 20
 #endif
 
 // out[i] = MillerLoop(p[i], q[i])   (pairing.go:16-75 fused with g2.go:650-801)
@@ -174,7 +178,7 @@ static int scratch_get(b381_ctx *ctx, int slot, size_t bytes, void **out) {
 }
 
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
-#define VM_MAX_UNITS 20480      // measured crossover on B200 (tools/small_bench.py): 16384 pairings 21.0 ms (VM) vs 24.2 ms; 32768: 39.5 vs 33.6
+#define VM_MAX_UNITS 12288      // measured crossover on B200 (tools/small_bench.py): 8192 pairings 11.8 ms (VM) vs 24.1 ms; 16384: 23.2 vs 24.2
 static inline bool vm_for(const b381_ctx *ctx, size_t n) { return ctx->use_vm < 0 ? n <= VM_MAX_UNITS : ctx->use_vm != 0; }
 static inline size_t vm_smem_bytes(int lanes, int nslots) { return (size_t)VM2_WARPS * (32 / lanes) * nslots * 96; }
 
@@ -229,9 +233,9 @@ int b381_init(int device, b381_ctx **out) {
     }
     if (max_smem < 200 * 1024) max_smem = 200 * 1024;
     if (cudaFuncSetAttribute(k_vm2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess) { b381_free(ctx); return B381_ERR_CUDA; }
-    // Two schedules of the same arithmetic: the warp-cooperative VM (4 pairings per warp, state in shared memory:
-    // 3x lower latency, fills the GPU from ~8 k pairings) and one pairing per thread (higher throughput once
-    // ~75 k threads are resident).  Default: by batch size; B381_VM=0/1 forces one of them for A/B measurements.
+    // Two schedules of the same arithmetic: the warp-cooperative VM (8 pairings per warp, state in shared memory:
+    // 2-3x lower latency, no DRAM traffic, fills the GPU from ~8 k pairings) and one pairing per thread (higher
+    // throughput once ~65 k threads are resident).  Default: by batch size; B381_VM=0/1 forces one of them for A/B measurements.
     const char *ev = getenv("B381_VM");
     ctx->use_vm = ev ? (ev[0] == '0' ? 0 : 1) : -1;
     *out = ctx;

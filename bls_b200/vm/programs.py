@@ -1,16 +1,15 @@
-"""The VM programs of the pairing path and their (deterministic) code generation.
+"""The Fq2-granular VM programs of the pairing path (see trace.py / sched.py / csrc/vm.cuh).
 
-Segments of the per-unit global area (kernel arguments, see vm.cuh): 0 and 1 inputs, 2 output, 3 spill.
-  ml    : seg0 = G1 affine (x, y), seg1 = G2 affine (x.c0, x.c1, y.c0, y.c1) -> seg2 = Fq12 (12 Fq)
+Segments of the per-unit global area: 0 and 1 inputs, 2 output, 3 spill, 4 constants.  Indices are in Fq.
+  ml    : seg0 = G1 affine (x, y), seg1 = G2 affine (x, y as Fq2) -> seg2 = Fq12 (6 Fq2)
   fe_a  : seg0 = Fq12 f -> seg2 = the Fq norm n whose inverse the Fq12 inversion needs (1 Fq)
-  fe_c  : seg0 = Fq12 f, seg1 = n^-1 (1 Fq) -> seg2 = FinalExponentiation(f) (12 Fq)
+  fe_c  : seg0 = Fq12 f, seg1 = n^-1 (1 Fq) -> seg2 = FinalExponentiation(f)
 """
 from . import trace as T
 from . import sched as S
 
 
 def frobenius_tables(p):
-    """(1+u)^((Q^k - 1)/d) as Fq2 of constants: fq6.go:144-208, fq12.go:122-168 (regenerated)"""
     Qm = T.Q
 
     def f2mul(a, b):
@@ -24,12 +23,11 @@ def frobenius_tables(p):
             a = f2mul(a, a)
             e >>= 1
         return r
-    xi = (1, 1)
     tabs = {"fq6_c1": {}, "fq6_c2": {}, "fq12_c1": {}}
     for k in (1, 2, 3):
         for name, d, mult in (("fq6_c1", 3, 1), ("fq6_c2", 3, 2), ("fq12_c1", 6, 1)):
-            c = f2pow(xi, mult * (Qm ** k - 1) // d)
-            tabs[name][k] = T.Fq2(p.const(c[0]), p.const(c[1]))
+            c = f2pow((1, 1), mult * (Qm ** k - 1) // d)
+            tabs[name][k] = p.const(c[0], c[1])
     return tabs
 
 
@@ -37,49 +35,45 @@ def build_ml(npairs=1):
     p = T.Program("ml%d" % npairs)
     pairs = []
     for i in range(npairs):
-        px, py = p.load(0, 2 * i), p.load(0, 2 * i + 1)
-        q = [p.load(1, 4 * i + j) for j in range(4)]
-        pairs.append((px, py, T.Fq2(q[0], q[1]), T.Fq2(q[2], q[3])))
+        px, py = p.load(0, 2 * i, 1), p.load(0, 2 * i + 1, 1)
+        qx, qy = p.load(1, 4 * i), p.load(1, 4 * i + 2)
+        pairs.append((px, py, qx, qy))
     f = T.miller_loop(p, pairs)
     for i, c in enumerate(f.coeffs()):
-        p.output(c, 2, i)
+        p.store(c, 2, 2 * i)
     return p
 
 
 def _load_f(p):
-    return T.fq12_from([p.load(0, i) for i in range(12)])
+    return T.fq12_from([p.load(0, 2 * i) for i in range(6)])
 
 
 def build_fe_a():
     p = T.Program("fe_a")
     n, _ = T.fq12_inv_norm(_load_f(p))
-    p.output(n, 2, 0)
+    p.store(n, 2, 0, 1)
     return p
 
 
 def build_fe_c(spill=True):
     p = T.Program("fe_c")
     f = _load_f(p)
-    ninv = p.load(1, 0)
+    ninv = p.load(1, 0, 1)
     tabs = frobenius_tables(p)
     _, inter = T.fq12_inv_norm(f)
-    nspill = [0]
 
     def sp(v):
-        cs = []
-        for c in v.coeffs():
-            cs.append(p.store(c, 3, nspill[0])); nspill[0] += 1
-        return T.fq12_from(cs)
+        return T.fq12_from([p.spill(c) for c in v.coeffs()])
     out = T.final_exp(f, ninv, inter, tabs, sp if spill else None)
     for i, c in enumerate(out.coeffs()):
-        p.output(c, 2, i)
-    p.spill_fq = nspill[0]
+        p.store(c, 2, 2 * i)
     return p
 
 
-def compile_program(p, L, window=0):
-    steps = S.schedule(p, L, window)
-    slot, nslots = S.allocate(p, steps)
-    code, padded = S.encode(p, steps, slot, L)
+def compile_program(p, L, window=0, do_fold=True):
+    ops = S.fold(p.ops)
+    steps = S.schedule(ops, L, window)
+    slot, nslots = S.allocate(ops, steps)
+    code = S.encode(ops, steps, slot, L)
     return {"name": p.name, "L": L, "code": code, "nslots": nslots, "consts": list(p.consts), "nsteps": len(steps),
-            "spill_fq": getattr(p, "spill_fq", 0), "stats": S.stats(p, steps, L, padded)}
+            "spill_fq": p.spill_fq, "stats": S.stats(ops, steps, L)}

@@ -144,7 +144,7 @@ int b381_imad_probe_dev(b381_ctx *ctx, uint32_t *d_out, int blocks, int threads,
  * The faster of the two probes is the denominator bench.py reports against.                         */
 int b381_fpmul_probe_dev(b381_ctx *ctx, uint32_t *d_out, int blocks, int threads, int iters);
 
-/* Test hook of the warp-cooperative VM behind the pairing entry points (bls_b200/csrc/vm2.cuh): runs an encoded
+/* Test hook of the warp-cooperative VM behind the pairing entry points (bls_b200/csrc/vm.cuh): runs an encoded
  * program (host image: nsteps * lanes * 64 bytes; constants: nconsts * 96 bytes, Montgomery form) over n units
  * whose per-unit elements live in the device arrays d_seg[0..3] with the given strides, then synchronises.
  * tests/test_gpu_vm.py drives random programs through it against the big-integer emulator.              */

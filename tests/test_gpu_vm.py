@@ -1,4 +1,4 @@
-"""The VM interpreter kernel (bls_b200/csrc/vm2.cuh) against the big-integer emulator on RANDOM programs:
+"""The VM interpreter kernel (bls_b200/csrc/vm.cuh) against the big-integer emulator on RANDOM programs:
 every operation shape (products, squares, sums; xi / conj / negative terms; tripled groups; Fq and Fq2
 loads and stores) on random field elements including the edge values 0, 1, Q-1."""
 import ctypes
@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from bls_b200 import layout as L
-from bls_b200.vm import sched2 as S, trace2 as T
+from bls_b200.vm import sched as S, trace as T
 
 pytestmark = pytest.mark.gpu
 LANES = 4
@@ -34,9 +34,11 @@ def random_program(rng, nin, nops):
     for _ in range(nops):
         mode = rng.choice(("mul", "mul", "sqr", "lin"))
         d = p._new()
-        a = [term() for _ in range(rng.choice((1, 1, 2, 3)))] if mode != "lin" else []
-        b = [term() for _ in range(rng.choice((1, 1, 2, 3)))] if mode == "mul" else []
-        if rng.random() < 0.5 and a:
+        # operand shapes the tracer emits: squares of single values, products with na * nb <= 4
+        na, nb = rng.choice(((1, 1), (1, 2), (2, 1), (2, 2), (1, 3), (3, 1))) if mode == "mul" else (1, 0)
+        a = [term() for _ in range(na)] if mode != "lin" else []
+        b = [term() for _ in range(nb)] if mode == "mul" else []
+        if mode == "sqr" and rng.random() < 0.7:
             a = [(a[0][0], 1, 0, 0)]                    # the plain single-term fast path
         m3 = rng.random() < 0.3
         g1 = [term() for _ in range(rng.randint(0, 4))] if m3 else []

@@ -1,10 +1,10 @@
 #!/usr/bin/env python3
-"""Micro-programs through b381_vm_exec_dev vs the emulator (debugging aid for csrc/vm2.cuh)."""
+"""Micro-programs through b381_vm_exec_dev vs the emulator (debugging aid for csrc/vm.cuh)."""
 import ctypes, os, random, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from bls_b200 import capi, layout as L
-from bls_b200.vm import sched2 as S, trace2 as T
+from bls_b200.vm import sched as S, trace as T
 ctx = capi.Ctx(0)
 rng = random.Random(1)
 nin = 3

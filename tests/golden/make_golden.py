@@ -105,5 +105,21 @@ k["frobenius_mont"] = {
     "fq6_c2": reprs(table(fq6, "frobeniusCoeffFQ6c2")),
     "fq12_c1_from_1": reprs(table(fq12, "frobeniusCoeffFQ12c1")),
 }
+# hash-to-curve, key derivation and serialisation vectors (hash_test.go:12-82, g1pubs/bls_test.go:409-433, g2pubs/bls_test.go:336-347)
+ht = (REF / "hash_test.go").read_text()
+hx = lambda name: hex(int(re.search(r'%s, _ = bls.FQReprFromString\("([0-9a-f]+)", 16\)' % name, ht).group(1), 16))
+g1t = (REF / "g1pubs" / "bls_test.go").read_text()
+g2t = (REF / "g2pubs" / "bls_test.go").read_text()
+k["hash"] = {
+    "cite": "hash_test.go:12-82; g1pubs/bls_test.go:409-433; g2pubs/bls_test.go:336-347",
+    "message": "the message to be signed",
+    "hash_g1": [hx("expectedG1X"), hx("expectedG1Y")],
+    "hash_g2_xc0_xc1_yc0_yc1": [hx("expectedG2c0X"), hx("expectedG2c1X"), hx("expectedG2c0Y"), hx("expectedG2c1Y")],
+    "hash_g2_with_domain_zero_compressed": re.search(r'expectedSerializedG2, _ = hex.DecodeString\("([0-9a-f]+)"\)', ht).group(1),
+    "derive_secret_key_in": re.search(r'copy\(secKeyIn\[:\], \[\]byte\("(\d+)"\)\)', g1t).group(1),
+    "derive_secret_key_out": hex(int(re.search(r'FRReprFromString\("([0-9a-f]+)", 16\)', g1t).group(1), 16)),
+    "invalid_g1_pubkey": re.search(r'func TestPubkeyDeserializeInvalid.*?unexpectedPub := "([0-9a-f]+)"', g1t, re.S).group(1),
+    "invalid_g2_pubkey": re.search(r'func TestPubkeyDeserializeInvalid.*?unexpectedPub := "([0-9a-f]+)"', g2t, re.S).group(1),
+}
 OUT.write_text(json.dumps(k, indent=1) + "\n")
 print("wrote", OUT, {a: (len(b) if hasattr(b, "__len__") else b) for a, b in k.items()})

@@ -63,18 +63,22 @@ HD void fp_sqr_n(fp *r, const fp *a) { fp x = *a; *r = fp_mul_v(x, x); }
 
 // ---- vector forms of the cheap operations: one out-of-line loop serves Fq2 (n=2), Fq6 (n=6) and
 // Fq12 (n=12) callers, so an addition costs a call instead of 37 inlined instructions per Fq ------
-HDN void fpv_add(fp *r, const fp *a, const fp *b, int n) {
+// n is even everywhere (Fq2 = 2, Fq6 = 6, Fq12 = 12): two elements per iteration, so that the four loads are in
+// flight together and the two carry chains interleave (the one-element loop was latency-bound on one load pair
+// and one chain).  One body for add / sub / double keeps the code small: the hot set of a kernel has to stay inside
+// the 32 KB L1.5 instruction cache (profiles/r01_v4_experiments.md).
+HDN void fpv_addsub(fp *r, const fp *a, const fp *b, int n, int sub) {
 #pragma unroll 1
-    for (int i = 0; i < n; i++) { fp x = a[i], y = b[i]; fp_add(x, x, y); r[i] = x; }
+    for (int i = 0; i < n; i += 2) {
+        fp x0 = a[i], y0 = b[i], x1 = a[i + 1], y1 = b[i + 1];
+        if (sub) { fp_sub(x0, x0, y0); fp_sub(x1, x1, y1); }
+        else { fp_add(x0, x0, y0); fp_add(x1, x1, y1); }
+        r[i] = x0; r[i + 1] = x1;
+    }
 }
-HDN void fpv_sub(fp *r, const fp *a, const fp *b, int n) {
-#pragma unroll 1
-    for (int i = 0; i < n; i++) { fp x = a[i], y = b[i]; fp_sub(x, x, y); r[i] = x; }
-}
-HDN void fpv_dbl(fp *r, const fp *a, int n) {
-#pragma unroll 1
-    for (int i = 0; i < n; i++) { fp x = a[i]; fp_add(x, x, x); r[i] = x; }
-}
+HD void fpv_add(fp *r, const fp *a, const fp *b, int n) { fpv_addsub(r, a, b, n, 0); }
+HD void fpv_sub(fp *r, const fp *a, const fp *b, int n) { fpv_addsub(r, a, b, n, 1); }
+HD void fpv_dbl(fp *r, const fp *a, int n) { fpv_addsub(r, a, a, n, 0); }
 HDN void fpv_neg(fp *r, const fp *a, int n) {
 #pragma unroll 1
     for (int i = 0; i < n; i++) { fp x = a[i]; fp_neg(x, x); r[i] = x; }

@@ -160,6 +160,49 @@ class Ctx:
         self.call("b381_verify_aggregate_common_batch_dev", *[b.ptr for b in bufs], ctypes.c_size_t(n), dok.ptr)
         return self.from_device(dok, np.uint8, n)
 
+    # -- wire formats and scalar multiplication (csrc/codec.cuh) --------------------------------------------------
+    def _decompress(self, name, data, nbytes, dtype, check_subgroup):
+        raw = np.frombuffer(bytes(data), np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, np.uint8).reshape(-1)
+        assert raw.size % nbytes == 0
+        n = raw.size // nbytes
+        out = np.zeros(n, dtype=dtype); status = np.zeros(n, np.uint8)
+        self.call(name, _hp(raw), ctypes.c_size_t(n), int(bool(check_subgroup)), _hp(out), _hp(status))
+        return out, status
+
+    def g1_decompress_batch(self, data, check_subgroup=True):
+        """n x 48 bytes -> (affine points, status codes): DecompressG1 / DecompressG1Unchecked"""
+        return self._decompress("b381_g1_decompress_batch", data, 48, L.G1_AFFINE, check_subgroup)
+
+    def g2_decompress_batch(self, data, check_subgroup=True):
+        """n x 96 bytes -> (affine points, status codes): DecompressG2 / DecompressG2Unchecked"""
+        return self._decompress("b381_g2_decompress_batch", data, 96, L.G2_AFFINE, check_subgroup)
+
+    def g1_compress_batch(self, p):
+        p = np.ascontiguousarray(p, dtype=L.G1_AFFINE); out = np.zeros((p.size, 48), np.uint8)
+        self.call("b381_g1_compress_batch", _hp(p), ctypes.c_size_t(p.size), _hp(out))
+        return out
+
+    def g2_compress_batch(self, p):
+        p = np.ascontiguousarray(p, dtype=L.G2_AFFINE); out = np.zeros((p.size, 96), np.uint8)
+        self.call("b381_g2_compress_batch", _hp(p), ctypes.c_size_t(p.size), _hp(out))
+        return out
+
+    def _mul(self, name, dtype, p, k):
+        p = np.ascontiguousarray(p, dtype=dtype).reshape(-1); k = np.ascontiguousarray(k, dtype=np.uint64).reshape(-1, 4)
+        n = max(p.size, k.shape[0])
+        assert p.size in (1, n) and k.shape[0] in (1, n)
+        out = np.zeros(n, dtype=dtype)
+        self.call(name, _hp(p), ctypes.c_size_t(0 if p.size == 1 and n > 1 else 1), _hp(k),
+                  ctypes.c_size_t(0 if k.shape[0] == 1 and n > 1 else 1), ctypes.c_size_t(n), _hp(out))
+        return out
+
+    def g1_mul_batch(self, p, k):
+        """out[i] = k[i] * p[i] (affine); a single point or a single scalar is broadcast -- MulFR + ToAffine"""
+        return self._mul("b381_g1_mul_batch", L.G1_AFFINE, p, k)
+
+    def g2_mul_batch(self, p, k):
+        return self._mul("b381_g2_mul_batch", L.G2_AFFINE, p, k)
+
     # -- raw device buffers owned by the engine (b381_dev_alloc / b381_h2d / b381_d2h) ----------
     def dev_empty(self, nbytes):
         return DevBuf(self, nbytes)

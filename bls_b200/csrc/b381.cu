@@ -11,6 +11,7 @@
 #include "pairing.cuh"
 #include "curve.cuh"
 #include "agg.cuh"
+#include "codec.cuh"
 #include "vm.cuh"
 #include "vm_programs.inc"
 #include <stdlib.h>
@@ -146,8 +147,8 @@ struct b381_ctx {
     uint64_t launches;
     char err[256];
     // grow-only device scratch
-    void *scratch[12];
-    size_t scratch_bytes[12];
+    void *scratch[16];
+    size_t scratch_bytes[16];
     // warp-cooperative VM programs resident on the device (csrc/vm.cuh)
     struct { uint4 *code, *consts; int lanes, nsteps, nslots, spill_fq; } vm[3];
     int use_vm;
@@ -246,7 +247,7 @@ void b381_free(b381_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 12; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < 16; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     for (int i = 0; i < 3; i++) { if (ctx->vm[i].code) cudaFree(ctx->vm[i].code); if (ctx->vm[i].consts) cudaFree(ctx->vm[i].consts); }
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -336,6 +337,113 @@ int b381_vm_exec_dev(b381_ctx *ctx, const void *code, int lanes, int nsteps, int
     cudaFree(dcode); cudaFree(dconst);
     if (e != cudaSuccess) { snprintf(ctx->err, sizeof ctx->err, "vm_exec: %s", cudaGetErrorString(e)); return B381_ERR_CUDA; }
     return B381_OK;
+}
+
+}   // extern "C" (templates below)
+// ---- wire formats and scalar multiplication (csrc/codec.cuh) -------------------------
+template <class C, class APOD>
+static int decompress_dev(b381_ctx *ctx, const uint8_t *d_in, size_t n, int check, APOD *d_out, uint8_t *d_status) {
+    if (!ctx || (n && (!d_in || !d_out || !d_status))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    k_decompress<C><<<grid_for(n, 64), 64, 0, ctx->stream>>>(d_in, n, check, (typename C::APOD *)d_out, d_status);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+template <class C, class APOD>
+static int decompress_host(b381_ctx *ctx, const uint8_t *in, size_t n, int check, APOD *out, uint8_t *status) {
+    if (!ctx || (n && (!in || !out || !status))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    CK(cudaSetDevice(ctx->device));
+    void *di, *dout, *ds;
+    int rc = scratch_get(ctx, 12, n * C::BYTES, &di); if (rc) return rc;
+    rc = scratch_get(ctx, 13, n * sizeof(APOD), &dout); if (rc) return rc;
+    rc = scratch_get(ctx, 14, n, &ds); if (rc) return rc;
+    CK(cudaMemcpyAsync(di, in, n * C::BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    rc = decompress_dev<C, APOD>(ctx, (const uint8_t *)di, n, check, (APOD *)dout, (uint8_t *)ds); if (rc) return rc;
+    CK(cudaMemcpyAsync(out, dout, n * sizeof(APOD), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(status, ds, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B381_OK;
+}
+template <class C, class APOD>
+static int compress_dev(b381_ctx *ctx, const APOD *d_in, size_t n, uint8_t *d_out) {
+    if (!ctx || (n && (!d_in || !d_out))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    k_compress<C><<<grid_for(n, 64), 64, 0, ctx->stream>>>((const typename C::APOD *)d_in, n, d_out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+template <class C, class APOD>
+static int compress_host(b381_ctx *ctx, const APOD *in, size_t n, uint8_t *out) {
+    if (!ctx || (n && (!in || !out))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    CK(cudaSetDevice(ctx->device));
+    void *di, *dout;
+    int rc = scratch_get(ctx, 12, n * C::BYTES, &dout); if (rc) return rc;
+    rc = scratch_get(ctx, 13, n * sizeof(APOD), &di); if (rc) return rc;
+    CK(cudaMemcpyAsync(di, in, n * sizeof(APOD), cudaMemcpyHostToDevice, ctx->stream));
+    rc = compress_dev<C, APOD>(ctx, (const APOD *)di, n, (uint8_t *)dout); if (rc) return rc;
+    CK(cudaMemcpyAsync(out, dout, n * C::BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B381_OK;
+}
+template <class C, class APOD>
+static int mul_dev(b381_ctx *ctx, const APOD *d_p, size_t p_stride, const b381_scalar *d_k, size_t k_stride, size_t n, APOD *d_out) {
+    if (!ctx || p_stride > 1 || k_stride > 1 || (n && (!d_p || !d_k || !d_out))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    k_point_mul<C><<<grid_for(n, 64), 64, 0, ctx->stream>>>((const typename C::APOD *)d_p, p_stride, (const uint64_t *)d_k, k_stride, n,
+                                                             (typename C::APOD *)d_out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+template <class C, class APOD>
+static int mul_host(b381_ctx *ctx, const APOD *p, size_t p_stride, const b381_scalar *k, size_t k_stride, size_t n, APOD *out) {
+    if (!ctx || p_stride > 1 || k_stride > 1 || (n && (!p || !k || !out))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    CK(cudaSetDevice(ctx->device));
+    size_t np = p_stride ? n : 1, nk = k_stride ? n : 1;
+    void *dp, *dk, *dout;
+    int rc = scratch_get(ctx, 12, np * sizeof(APOD), &dp); if (rc) return rc;
+    rc = scratch_get(ctx, 13, n * sizeof(APOD), &dout); if (rc) return rc;
+    rc = scratch_get(ctx, 14, nk * sizeof(b381_scalar), &dk); if (rc) return rc;
+    CK(cudaMemcpyAsync(dp, p, np * sizeof(APOD), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dk, k, nk * sizeof(b381_scalar), cudaMemcpyHostToDevice, ctx->stream));
+    rc = mul_dev<C, APOD>(ctx, (const APOD *)dp, p_stride, (const b381_scalar *)dk, k_stride, n, (APOD *)dout); if (rc) return rc;
+    CK(cudaMemcpyAsync(out, dout, n * sizeof(APOD), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B381_OK;
+}
+extern "C" {
+int b381_g1_decompress_batch(b381_ctx *ctx, const uint8_t *in, size_t n, int check_subgroup, b381_g1_affine *out, uint8_t *status) {
+    return decompress_host<G1Codec>(ctx, in, n, check_subgroup, out, status);
+}
+int b381_g1_decompress_batch_dev(b381_ctx *ctx, const uint8_t *d_in, size_t n, int check_subgroup, b381_g1_affine *d_out, uint8_t *d_status) {
+    return decompress_dev<G1Codec>(ctx, d_in, n, check_subgroup, d_out, d_status);
+}
+int b381_g2_decompress_batch(b381_ctx *ctx, const uint8_t *in, size_t n, int check_subgroup, b381_g2_affine *out, uint8_t *status) {
+    return decompress_host<G2Codec>(ctx, in, n, check_subgroup, out, status);
+}
+int b381_g2_decompress_batch_dev(b381_ctx *ctx, const uint8_t *d_in, size_t n, int check_subgroup, b381_g2_affine *d_out, uint8_t *d_status) {
+    return decompress_dev<G2Codec>(ctx, d_in, n, check_subgroup, d_out, d_status);
+}
+int b381_g1_compress_batch(b381_ctx *ctx, const b381_g1_affine *in, size_t n, uint8_t *out) { return compress_host<G1Codec>(ctx, in, n, out); }
+int b381_g1_compress_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_in, size_t n, uint8_t *d_out) { return compress_dev<G1Codec>(ctx, d_in, n, d_out); }
+int b381_g2_compress_batch(b381_ctx *ctx, const b381_g2_affine *in, size_t n, uint8_t *out) { return compress_host<G2Codec>(ctx, in, n, out); }
+int b381_g2_compress_batch_dev(b381_ctx *ctx, const b381_g2_affine *d_in, size_t n, uint8_t *d_out) { return compress_dev<G2Codec>(ctx, d_in, n, d_out); }
+int b381_g1_mul_batch(b381_ctx *ctx, const b381_g1_affine *p, size_t p_stride, const b381_scalar *k, size_t k_stride, size_t n, b381_g1_affine *out) {
+    return mul_host<G1Codec>(ctx, p, p_stride, k, k_stride, n, out);
+}
+int b381_g1_mul_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, size_t p_stride, const b381_scalar *d_k, size_t k_stride, size_t n, b381_g1_affine *d_out) {
+    return mul_dev<G1Codec>(ctx, d_p, p_stride, d_k, k_stride, n, d_out);
+}
+int b381_g2_mul_batch(b381_ctx *ctx, const b381_g2_affine *p, size_t p_stride, const b381_scalar *k, size_t k_stride, size_t n, b381_g2_affine *out) {
+    return mul_host<G2Codec>(ctx, p, p_stride, k, k_stride, n, out);
+}
+int b381_g2_mul_batch_dev(b381_ctx *ctx, const b381_g2_affine *d_p, size_t p_stride, const b381_scalar *d_k, size_t k_stride, size_t n, b381_g2_affine *d_out) {
+    return mul_dev<G2Codec>(ctx, d_p, p_stride, d_k, k_stride, n, d_out);
 }
 
 // ---- pairing, device-resident ------------------------------------------------------------------

@@ -1,0 +1,305 @@
+// codec.cuh -- wire formats and scalar multiplication on the device: what the callers of
+// the verification path do on either side of it.
+//   DecompressG1 / DecompressG1Unchecked / GetG1PointFromX / IsInCorrectSubgroupAssumingOnCurve   g1.go:111-141,185-227
+//   DecompressG2 / DecompressG2Unchecked / GetG2PointFromX                                        g2.go:149-169,219-265,293-295
+//   CompressG1 / CompressG2                                                                       g1.go:230-249, g2.go:268-289
+//   FQ.Sqrt (fq.go:203-217), FQ2.Sqrt (fq2.go:198-232), FQ.Cmp / FQ2.Cmp (fq.go:134-137, fq2.go:31-37)
+//   G1Affine.MulFR / G2Affine.MulFR + ToAffine (g1.go:80-90,322-340; g2.go:92-102,365-386): PrivToPub and Sign
+// One thread per point.  Results are canonical field elements / bytes / status codes, so they are the reference's
+// bits whatever formulas run underneath (here: XYZZ double-and-add from curve.cuh and Fermat inversion).
+#pragma once
+#include "curve.cuh"
+
+namespace b381 {
+
+// status codes of the decompression entry points (0 = ok); the reference returns errors with these messages
+enum {
+    CODEC_OK = 0,
+    CODEC_ERR_MODE = 1,       // "unexpected compression mode"                     g1.go:203-205, g2.go:233-235
+    CODEC_ERR_INFINITY = 2,   // "unexpected information in compressed infinity"  g1.go:211-214, g2.go:241-244
+    CODEC_ERR_NOT_ON_CURVE = 3,   // "point not on curve"                          g1.go:119-121, g2.go:157-159
+    CODEC_ERR_SUBGROUP = 4    // "not in correct subgroup"                         g1.go:191-193, g2.go:225-227
+};
+
+#if defined(__CUDACC__)
+__device__ __constant__ uint32_t d_r2_raw[12] = {B381_R2_RAW_LIMBS};
+__device__ __constant__ uint32_t d_neg_one[12] = {B381_NEG_ONE_LIMBS};
+__device__ __constant__ uint32_t d_b_coeff[12] = {B381_B_COEFF_LIMBS};
+__device__ __constant__ uint32_t d_qm3o4[12] = {B381_Q_MINUS_3_OVER_4_LIMBS};
+__device__ __constant__ uint32_t d_qm1o2[12] = {B381_Q_MINUS_1_OVER_2_LIMBS};
+__device__ __constant__ uint32_t d_r_order[8] = {B381_R_ORDER_LIMBS};
+#endif
+#if !defined(__CUDA_ARCH__)
+static const uint32_t h_r2_raw[12] = {B381_R2_RAW_LIMBS};
+static const uint32_t h_neg_one[12] = {B381_NEG_ONE_LIMBS};
+static const uint32_t h_b_coeff[12] = {B381_B_COEFF_LIMBS};
+static const uint32_t h_qm3o4[12] = {B381_Q_MINUS_3_OVER_4_LIMBS};
+static const uint32_t h_qm1o2[12] = {B381_Q_MINUS_1_OVER_2_LIMBS};
+static const uint32_t h_r_order[8] = {B381_R_ORDER_LIMBS};
+#endif
+
+// ---- integers <-> field elements -----------------------------------------------------------------------------------
+// big-endian 48 bytes -> plain limbs (FQReprFromBytes, fqrepr.go:194-202)
+HD void fp_raw_from_be48(fp &r, const uint8_t *b) {
+#pragma unroll 1
+    for (int i = 0; i < 12; i++) {
+        const uint8_t *p = b + 44 - 4 * i;
+        r.l[i] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+    }
+}
+HD void fp_raw_to_be48(uint8_t *b, const fp &a) {   // FQRepr.Bytes, fqrepr.go:181-191
+#pragma unroll 1
+    for (int i = 0; i < 12; i++) {
+        uint8_t *p = b + 44 - 4 * i;
+        uint32_t v = a.l[i];
+        p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v;
+    }
+}
+// -1, 0, +1 on plain limbs (FQRepr.Cmp, fqrepr.go:125-136)
+HD int fp_raw_cmp(const fp &a, const fp &b) {
+    int c = 0;
+#pragma unroll 1
+    for (int i = 11; i >= 0; i--)
+        if (c == 0 && a.l[i] != b.l[i]) c = a.l[i] < b.l[i] ? -1 : 1;
+    return c;
+}
+// plain integer -> Montgomery element; values >= Q become 0 exactly like FQReprToFQ (fq.go:49-56)
+HD void fp_from_raw(fp &r, const fp &raw) {
+    const uint32_t q[12] = {B381_Q_LIMBS};
+    fp qq, k;
+#pragma unroll
+    for (int i = 0; i < 12; i++) qq.l[i] = q[i];
+    if (fp_raw_cmp(raw, qq) >= 0) { fp_set_zero(r); return; }
+    fp_load_tab(k, B381_TAB(r2_raw));
+    fp_mul(r, raw, k);
+}
+// Montgomery element -> plain integer (FQ.ToRepr, fq.go:334-338)
+HD void fp_to_raw(fp &r, const fp &a) {
+    fp one;
+    fp_set_zero(one); one.l[0] = 1;
+    fp_mul(r, a, one);
+}
+// FQ.Cmp (fq.go:134-137): compares the plain integers
+HD int fp_cmp(const fp &a, const fp &b) {
+    fp x, y;
+    fp_to_raw(x, a); fp_to_raw(y, b);
+    return fp_raw_cmp(x, y);
+}
+// FQ2.Cmp (fq2.go:31-37): c1 first
+HD int fp2_cmp(const fp2 &a, const fp2 &b) {
+    int c = fp_cmp(a.c1, b.c1);
+    return c ? c : fp_cmp(a.c0, b.c0);
+}
+
+// ---- exponentiation by a fixed 384-bit exponent and square roots -----------------------------------------------------
+// a^e, e as 12 plain u32 limbs (FQ.Exp fq.go:268-284 / FQ2.Exp fq2.go:170-187: MSB-first square-and-multiply)
+template <class F> HDN void field_pow(typename F::T *r, const typename F::T *a, const uint32_t *e) {
+    typename F::T acc, x = *a;
+    F::set_one(acc);
+    bool started = false;
+#pragma unroll 1
+    for (int i = 383; i >= 0; i--) {
+        bool bit = (e[i >> 5] >> (i & 31)) & 1;
+        if (started) F::sqr(acc, acc);
+        if (bit) {
+            if (started) F::mul(acc, acc, x);
+            else { acc = x; started = true; }
+        }
+    }
+    *r = acc;
+}
+// FQ.Sqrt (fq.go:203-217): q = 3 mod 4
+HDN bool fp_sqrt(fp *out, const fp *a) {
+    fp a1, a0, m1;
+    field_pow<FpInl>(&a1, a, B381_TAB(qm3o4));
+    fp_sqr(a0, a1);
+    fp_mul(a0, a0, *a);
+    fp_load_tab(m1, B381_TAB(neg_one));
+    if (fp_eq(a0, m1)) return false;
+    fp_mul(*out, a1, *a);
+    return true;
+}
+// FQ2.Sqrt (fq2.go:198-232; Algorithm 9 of eprint 2012/685)
+HDN bool fp2_sqrt(fp2 *out, const fp2 *a) {
+    if (fp2_is_zero(*a)) { fp2_set_zero(*out); return true; }
+    fp2 a1, alpha, a0, neg1;
+    field_pow<Fp2Out>(&a1, a, B381_TAB(qm3o4));
+    fp2_sqr(&alpha, &a1);
+    fp2_mul(&alpha, &alpha, a);
+    fp2_conj(a0, alpha);                       // Frobenius(1)
+    fp2_mul(&a0, &a0, &alpha);
+    fp_load_tab(neg1.c0, B381_TAB(neg_one)); fp_set_zero(neg1.c1);
+    if (fp2_eq(a0, neg1)) return false;
+    fp2_mul(&a1, &a1, a);
+    if (fp2_eq(alpha, neg1)) {                 // multiply by u
+        fp t = a1.c0;
+        fp_neg(a1.c0, a1.c1);
+        a1.c1 = t;
+        *out = a1;
+        return true;
+    }
+    fp2 one;
+    fp2_set_one(one);
+    fp2_add(alpha, alpha, one);
+    field_pow<Fp2Out>(&alpha, &alpha, B381_TAB(qm1o2));
+    fp2_mul(out, &alpha, &a1);
+    return true;
+}
+
+// ---- field-generic helpers for the two curves ----------------------------------------------------------------------
+struct G1Codec {
+    typedef FpOut F;
+    typedef fp T;
+    typedef g1_affine_pod APOD;
+    enum { BYTES = 48 };
+    static HD void b_coeff(T &b) { fp_load_tab(b, B381_TAB(b_coeff)); }
+    static HD bool sqrt(T *o, const T *a) { return fp_sqrt(o, a); }
+    static HD int cmp(const T &a, const T &b) { return fp_cmp(a, b); }
+    static HD void x_from_bytes(T &x, const uint8_t *c) { fp raw; fp_raw_from_be48(raw, c); fp_from_raw(x, raw); }
+    static HD void x_to_bytes(uint8_t *c, const T &x) { fp raw; fp_to_raw(raw, x); fp_raw_to_be48(c, raw); }
+    static HD void load(T &x, T &y, const APOD *p) { fp_load_u64(x, p->x); fp_load_u64(y, p->y); }
+    static HD void store(APOD *p, const T &x, const T &y, bool inf) {
+        fp_store_u64(p->x, x); fp_store_u64(p->y, y); p->inf = inf ? 1 : 0;
+        for (int i = 0; i < 7; i++) p->pad[i] = 0;
+    }
+};
+struct G2Codec {
+    typedef Fp2Out F;
+    typedef fp2 T;
+    typedef g2_affine_pod APOD;
+    enum { BYTES = 96 };
+    static HD void b_coeff(T &b) { fp_load_tab(b.c0, B381_TAB(b_coeff)); b.c1 = b.c0; }   // 4(1 + u), g2.go:32
+    static HD bool sqrt(T *o, const T *a) { return fp2_sqrt(o, a); }
+    static HD int cmp(const T &a, const T &b) { return fp2_cmp(a, b); }
+    // x.c1 comes first on the wire (g2.go:250-257, 275-278)
+    static HD void x_from_bytes(T &x, const uint8_t *c) {
+        fp raw;
+        fp_raw_from_be48(raw, c); fp_from_raw(x.c1, raw);
+        fp_raw_from_be48(raw, c + 48); fp_from_raw(x.c0, raw);
+    }
+    static HD void x_to_bytes(uint8_t *c, const T &x) {
+        fp raw;
+        fp_to_raw(raw, x.c1); fp_raw_to_be48(c, raw);
+        fp_to_raw(raw, x.c0); fp_raw_to_be48(c + 48, raw);
+    }
+    static HD void load(T &x, T &y, const APOD *p) {
+        fp_load_u64(x.c0, p->x); fp_load_u64(x.c1, p->x + 6); fp_load_u64(y.c0, p->y); fp_load_u64(y.c1, p->y + 6);
+    }
+    static HD void store(APOD *p, const T &x, const T &y, bool inf) {
+        fp_store_u64(p->x, x.c0); fp_store_u64(p->x + 6, x.c1); fp_store_u64(p->y, y.c0); fp_store_u64(p->y + 6, y.c1);
+        p->inf = inf ? 1 : 0;
+        for (int i = 0; i < 7; i++) p->pad[i] = 0;
+    }
+};
+
+// acc = k * (x, y) for a finite affine point, k as `nlimbs` plain u32 limbs: MSB-first double-and-add, the loop of
+// G1Affine.Mul (g1.go:59-77) on XYZZ accumulators
+template <class F> HDN void point_mul(xyzz<F> *acc, const typename F::T *x, const typename F::T *y, const uint32_t *k, int nlimbs) {
+    xyzz<F> a;
+    xyzz_set_inf(a);
+#pragma unroll 1
+    for (int i = nlimbs * 32 - 1; i >= 0; i--) {
+        xyzz_dbl(a);
+        if ((k[i >> 5] >> (i & 31)) & 1) xyzz_madd(a, *x, *y);
+    }
+    *acc = a;
+}
+// affine coordinates of a finite XYZZ point (ToAffine, g1.go:322-340: same canonical values)
+template <class F> HD void xyzz_to_affine(typename F::T &x, typename F::T &y, const xyzz<F> &p) {
+    typename F::T zi, t;
+    F::inv(zi, p.zzz);                 // 1/ZZZ
+    F::mul(y, p.y, zi);                // y = Y/ZZZ
+    F::mul(t, zi, p.zz);               // 1/Z = ZZ/ZZZ
+    F::sqr(t, t);                      // 1/ZZ
+    F::mul(x, p.x, t);
+}
+
+// ---- decompression ---------------------------------------------------------------------------------------------------
+// DecompressG1[Unchecked] / DecompressG2[Unchecked]; the affine point is written for status 0 and 4 (the reference
+// returns no point with an error; callers must look at the status)
+template <class C> HD int decompress_one(typename C::APOD *out, const uint8_t *in, bool check_subgroup) {
+    typedef typename C::T T;
+    uint8_t c[C::BYTES];
+    for (int i = 0; i < C::BYTES; i++) c[i] = in[i];
+    T x, y, ny, t;
+    C::F::set_zero(x); C::F::set_one(y);
+    if ((c[0] & 0x80) == 0) { C::store(out, x, y, true); return CODEC_ERR_MODE; }
+    if (c[0] & 0x40) {
+        c[0] &= 0x3f;
+        uint8_t o = 0;
+        for (int i = 0; i < C::BYTES; i++) o |= c[i];
+        C::store(out, x, y, true);             // G1AffineZero = (0, 1, infinity), g1.go:269
+        return o ? CODEC_ERR_INFINITY : CODEC_OK;
+    }
+    bool greatest = (c[0] & 0x20) != 0;
+    c[0] &= 0x1f;
+    C::x_from_bytes(x, c);
+    // y^2 = x^3 + b
+    C::F::sqr(t, x);
+    C::F::mul(t, t, x);
+    C::b_coeff(ny);
+    C::F::add(t, t, ny);
+    if (!C::sqrt(&y, &t)) { C::F::set_zero(x); C::F::set_one(y); C::store(out, x, y, true); return CODEC_ERR_NOT_ON_CURVE; }
+    C::F::neg(ny, y);
+    if (!((C::cmp(y, ny) < 0) != greatest)) y = ny;     // g1.go:126-129
+    C::store(out, x, y, false);
+    if (check_subgroup) {
+        xyzz<typename C::F> acc;
+        point_mul<typename C::F>(&acc, &x, &y, B381_TAB(r_order), 8);
+        if (!xyzz_is_inf(acc)) return CODEC_ERR_SUBGROUP;
+    }
+    return CODEC_OK;
+}
+// CompressG1 / CompressG2
+template <class C> HD void compress_one(uint8_t *out, const typename C::APOD *in) {
+    typedef typename C::T T;
+    for (int i = 0; i < C::BYTES; i++) out[i] = 0;
+    if (in->inf) { out[0] = 0xc0; return; }
+    T x, y, ny;
+    C::load(x, y, in);
+    C::x_to_bytes(out, x);
+    C::F::neg(ny, y);
+    if (C::cmp(y, ny) > 0) out[0] |= 0x20;
+    out[0] |= 0x80;
+}
+// out = k * p as an affine point (MulFR + ToAffine); p at infinity or k = 0 give the canonical zero (0, 1, inf)
+template <class C> HD void mul_one(typename C::APOD *out, const typename C::APOD *p, const uint64_t *k) {
+    typedef typename C::T T;
+    T x, y;
+    uint32_t kk[8];
+    for (int i = 0; i < 4; i++) { kk[2 * i] = (uint32_t)k[i]; kk[2 * i + 1] = (uint32_t)(k[i] >> 32); }
+    xyzz<typename C::F> acc;
+    xyzz_set_inf(acc);
+    if (!p->inf) {
+        C::load(x, y, p);
+        point_mul<typename C::F>(&acc, &x, &y, kk, 8);
+    }
+    if (xyzz_is_inf(acc)) { C::F::set_zero(x); C::F::set_one(y); C::store(out, x, y, true); return; }
+    xyzz_to_affine<typename C::F>(x, y, acc);
+    C::store(out, x, y, false);
+}
+
+#if defined(__CUDACC__)
+template <class C> __global__ void __launch_bounds__(64) k_decompress(const uint8_t *__restrict__ in, size_t n, int check_subgroup,
+                                                                      typename C::APOD *__restrict__ out, uint8_t *__restrict__ status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    status[i] = (uint8_t)decompress_one<C>(out + i, in + (size_t)C::BYTES * i, check_subgroup != 0);
+}
+template <class C> __global__ void __launch_bounds__(64) k_compress(const typename C::APOD *__restrict__ in, size_t n,
+                                                                    uint8_t *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    compress_one<C>(out + (size_t)C::BYTES * i, in + i);
+}
+// out[i] = k[i] * p[i * p_stride]: p_stride 0 multiplies one base by every scalar (PrivToPub: the generator)
+template <class C> __global__ void __launch_bounds__(64) k_point_mul(const typename C::APOD *__restrict__ p, size_t p_stride,
+                                                                     const uint64_t *__restrict__ k, size_t k_stride, size_t n,
+                                                                     typename C::APOD *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    mul_one<C>(out + i, p + i * p_stride, k + 4 * i * k_stride);
+}
+#endif
+
+}  // namespace b381

@@ -134,6 +134,43 @@ int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *
                                            const b381_g2_affine *d_sig, const b381_g2_affine *d_msg_hash,
                                            const uint32_t *d_msg_idx, size_t nattest, uint8_t *d_ok);
 
+/* ---- wire formats and scalar multiplication (the callers on either side of the verification path) ------------ */
+/* DecompressG1 (check_subgroup != 0, g1.go:185-195) / DecompressG1Unchecked (g1.go:199-227) over n x 48 bytes;
+ * DecompressG2 (g2.go:219-229) / DecompressG2Unchecked (g2.go:232-265) over n x 96 bytes (x.c1 first).
+ * status[i]: 0 ok; 1 "unexpected compression mode"; 2 "unexpected information in compressed infinity";
+ * 3 "point not on curve"; 4 "not in correct subgroup" (the reference's error strings).  out[i] is the point for
+ * status 0 and 4 and the canonical zero (0, 1, infinity) otherwise.  A coordinate >= Q decodes as 0 exactly as
+ * FQReprToFQ does (fq.go:49-56).  This is what g1pubs.DeserializePublicKey / DeserializeSignature and their g2pubs
+ * mirrors run per key (g1pubs/bls.go:38-58,91-111). */
+enum { B381_POINT_OK = 0, B381_POINT_ERR_MODE = 1, B381_POINT_ERR_INFINITY = 2, B381_POINT_ERR_NOT_ON_CURVE = 3,
+       B381_POINT_ERR_SUBGROUP = 4 };
+int b381_g1_decompress_batch(b381_ctx *ctx, const uint8_t *in, size_t n, int check_subgroup, b381_g1_affine *out,
+                             uint8_t *status);
+int b381_g1_decompress_batch_dev(b381_ctx *ctx, const uint8_t *d_in, size_t n, int check_subgroup,
+                                 b381_g1_affine *d_out, uint8_t *d_status);
+int b381_g2_decompress_batch(b381_ctx *ctx, const uint8_t *in, size_t n, int check_subgroup, b381_g2_affine *out,
+                             uint8_t *status);
+int b381_g2_decompress_batch_dev(b381_ctx *ctx, const uint8_t *d_in, size_t n, int check_subgroup,
+                                 b381_g2_affine *d_out, uint8_t *d_status);
+/* CompressG1 (g1.go:230-249) / CompressG2 (g2.go:268-289): n affine points -> n x 48 / n x 96 bytes
+ * (Serialize of keys and signatures, g1pubs/bls.go:18-24,67-70). */
+int b381_g1_compress_batch(b381_ctx *ctx, const b381_g1_affine *in, size_t n, uint8_t *out);
+int b381_g1_compress_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_in, size_t n, uint8_t *d_out);
+int b381_g2_compress_batch(b381_ctx *ctx, const b381_g2_affine *in, size_t n, uint8_t *out);
+int b381_g2_compress_batch_dev(b381_ctx *ctx, const b381_g2_affine *d_in, size_t n, uint8_t *d_out);
+/* out[i] = k[i * k_stride] * p[i * p_stride] as an affine point: G1Affine.MulFR / G2Affine.MulFR followed by
+ * ToAffine (g1.go:80-90,322-340; g2.go:92-102,365-386).  Strides are 0 or 1: p_stride 0 multiplies ONE base by n
+ * scalars (PrivToPub = sk * G1One, g1pubs/bls.go:144-146), k_stride 0 multiplies n points by ONE scalar (Sign of n
+ * hashed messages with one key, g1pubs/bls.go:132-141).  Scalars are canonical integers < r. */
+int b381_g1_mul_batch(b381_ctx *ctx, const b381_g1_affine *p, size_t p_stride, const b381_scalar *k, size_t k_stride,
+                      size_t n, b381_g1_affine *out);
+int b381_g1_mul_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, size_t p_stride, const b381_scalar *d_k,
+                          size_t k_stride, size_t n, b381_g1_affine *d_out);
+int b381_g2_mul_batch(b381_ctx *ctx, const b381_g2_affine *p, size_t p_stride, const b381_scalar *k, size_t k_stride,
+                      size_t n, b381_g2_affine *out);
+int b381_g2_mul_batch_dev(b381_ctx *ctx, const b381_g2_affine *d_p, size_t p_stride, const b381_scalar *d_k,
+                          size_t k_stride, size_t n, b381_g2_affine *d_out);
+
 /* ---- measurement -------------------------------------------------------------------------------- */
 /* Integer-pipe roofline probe: launches blocks x threads threads that each issue iters * 8
  * independent IMAD.WIDE.U32 (the 32x32->64 multiply-accumulate an Fq multiplication is made of).

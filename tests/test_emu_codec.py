@@ -1,0 +1,81 @@
+"""CPU tests of csrc/codec.cuh (compiled as host C++ in tests/emu) against the oracle: DecompressG1/G2 (checked and
+unchecked, g1.go:185-227, g2.go:219-265), CompressG1/G2 (g1.go:230-249, g2.go:268-289), MulFR + ToAffine."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from bls_b200 import hostgen as hg, layout as L
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import codec_cases as cc
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import __graft_entry__ as g
+    return ctypes.CDLL(g.build_emu())
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _expected_points(pts, st):
+    """the engine writes the canonical zero for statuses 1-3; the oracle leaves its output untouched there"""
+    out = pts.copy()
+    for i in np.nonzero((st != 0) & (st != 4))[0]:
+        out[i] = np.zeros(1, dtype=pts.dtype)[0]
+        out["y"][i] = L.fp_from_int(1) if pts.dtype == L.G1_AFFINE else np.array([L.fp_from_int(1), L.fp_from_int(0)])
+        out["inf"][i] = 1
+    return out
+
+
+@pytest.mark.parametrize("which", ["g1", "g2"])
+def test_decompress_matches_oracle(emu, orc, which):
+    grp, dtype, nb = (orc.g1, L.G1_AFFINE, 48) if which == "g1" else (orc.g2, L.G2_AFFINE, 96)
+    pts = hg.g1_progression(5, 3, 6) if which == "g1" else hg.g2_progression(7, 5, 6)
+    cases = cc.compressed_cases(orc, grp, nb, pts, 1) + [cc.REF_INVALID_G1 if which == "g1" else cc.REF_INVALID_G2]
+    raw = np.frombuffer(b"".join(cases), np.uint8).copy()
+    n = len(cases)
+    for checked in (0, 1):
+        exp_p, exp_s = cc.oracle_decompress(grp, dtype, cases, bool(checked))
+        got = np.zeros(n, dtype=dtype); st = np.zeros(n, np.uint8)
+        getattr(emu, "emu_%s_decompress" % which)(_p(raw), ctypes.c_size_t(n), checked, _p(got), _p(st))
+        assert st.tolist() == exp_s.tolist()
+        assert got.tobytes() == _expected_points(exp_p, exp_s).tobytes()
+    assert exp_s[-1] != 0, "the reference's invalid public key must be rejected (bls_test.go TestPubkeyDeserializeInvalid)"
+    assert set(exp_s.tolist()) >= {0, 1, 2, 3, 4}, "every error path is exercised"
+
+
+@pytest.mark.parametrize("which", ["g1", "g2"])
+def test_compress_roundtrip(emu, orc, which):
+    grp, dtype, nb = (orc.g1, L.G1_AFFINE, 48) if which == "g1" else (orc.g2, L.G2_AFFINE, 96)
+    pts = hg.g1_progression(11, 7, 9) if which == "g1" else hg.g2_progression(13, 9, 9)
+    pts = np.concatenate([pts, hg.g1_neg(pts[:3]) if which == "g1" else pts[:0]])
+    zero = np.zeros(1, dtype=dtype); zero["inf"] = 1; zero["y"] = L.fp_from_int(1) if which == "g1" else np.array([L.fp_from_int(1), L.fp_from_int(0)])
+    pts = np.concatenate([pts, zero])
+    out = np.zeros((pts.size, nb), np.uint8)
+    getattr(emu, "emu_%s_compress" % which)(_p(pts), ctypes.c_size_t(pts.size), _p(out))
+    for i in range(pts.size):
+        assert out[i].tobytes() == grp.compress(pts[i:i + 1])
+
+
+@pytest.mark.parametrize("which", ["g1", "g2"])
+def test_scalar_mul(emu, orc, which):
+    grp, dtype = (orc.g1, L.G1_AFFINE) if which == "g1" else (orc.g2, L.G2_AFFINE)
+    n = 6
+    pts = hg.g1_progression(17, 3, n) if which == "g1" else hg.g2_progression(19, 5, n)
+    xs = orc.XorShift(77)
+    k = xs.rand_fr(n)
+    k[0] = 0; k[1] = [1, 0, 0, 0]; k[2] = L.int_to_limbs(L.R_ORDER - 1, 4)
+    exp = grp.to_affine(grp.mul_fr(pts, k))
+    got = np.zeros(n, dtype=dtype)
+    getattr(emu, "emu_%s_mul" % which)(_p(pts), ctypes.c_size_t(1), _p(k), ctypes.c_size_t(1), ctypes.c_size_t(n), _p(got))
+    assert got.tobytes() == exp.tobytes()
+    # one base, many scalars (PrivToPub) and one scalar, many points (Sign)
+    got1 = np.zeros(n, dtype=dtype)
+    getattr(emu, "emu_%s_mul" % which)(_p(pts), ctypes.c_size_t(0), _p(k), ctypes.c_size_t(1), ctypes.c_size_t(n), _p(got1))
+    assert got1.tobytes() == grp.to_affine(grp.mul_fr(np.repeat(pts[:1], n), k)).tobytes()
+    getattr(emu, "emu_%s_mul" % which)(_p(pts), ctypes.c_size_t(1), _p(k[3:]), ctypes.c_size_t(0), ctypes.c_size_t(n), _p(got1))
+    assert got1.tobytes() == grp.to_affine(grp.mul_fr(pts, np.repeat(k[3:4], n, axis=0))).tobytes()

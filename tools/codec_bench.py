@@ -1,0 +1,58 @@
+#!/usr/bin/env python3
+"""Device-resident timings (CUDA events, best of 3) of the wire-format / scalar-multiplication kernels:
+python tools/codec_bench.py [--n 65536] -> one JSON object on stdout."""
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+from bls_b200 import capi, hostgen as hg, layout as L
+
+n = int(sys.argv[sys.argv.index("--n") + 1]) if "--n" in sys.argv else 65536
+ctx = capi.Ctx(0)
+stream = torch.cuda.current_stream()
+ctx.set_stream(stream.cuda_stream)
+dev = torch.device("cuda", 0)
+up = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).to(dev)
+
+
+def timed(fn, reps=3):
+    fn(); torch.cuda.synchronize()
+    best = None
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); fn(); e1.record(stream); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return best
+
+
+m = min(n, 4096)
+P1 = np.resize(hg.g1_progression(3, 5, m), n); P2 = np.resize(hg.g2_progression(7, 11, m), n)
+K, _ = hg.splitmix_scalars(5, m)
+K = np.resize(K, (n, 4))
+dP1, dP2, dK = up(P1), up(P2), up(K)
+dC1 = torch.empty(n * 48, dtype=torch.uint8, device=dev); dC2 = torch.empty(n * 96, dtype=torch.uint8, device=dev)
+dO1 = torch.empty(n * 104, dtype=torch.uint8, device=dev); dO2 = torch.empty(n * 200, dtype=torch.uint8, device=dev)
+dS = torch.empty(n, dtype=torch.uint8, device=dev)
+N = ctypes.c_size_t(n)
+one = ctypes.c_size_t(1)
+res = {"n": n}
+res["g1_compress_ms"] = timed(lambda: ctx.dev("b381_g1_compress_batch_dev", dP1.data_ptr(), N, dC1.data_ptr()))
+res["g2_compress_ms"] = timed(lambda: ctx.dev("b381_g2_compress_batch_dev", dP2.data_ptr(), N, dC2.data_ptr()))
+for chk in (0, 1):
+    tag = "checked" if chk else "unchecked"
+    res["g1_decompress_%s_ms" % tag] = timed(lambda: ctx.dev("b381_g1_decompress_batch_dev", dC1.data_ptr(), N, chk, dO1.data_ptr(), dS.data_ptr()))
+    assert not dS.any().item() and bytes(dO1.cpu().numpy()) == P1.tobytes()
+    res["g2_decompress_%s_ms" % tag] = timed(lambda: ctx.dev("b381_g2_decompress_batch_dev", dC2.data_ptr(), N, chk, dO2.data_ptr(), dS.data_ptr()))
+    assert not dS.any().item() and bytes(dO2.cpu().numpy()) == P2.tobytes()
+res["g1_mul_ms"] = timed(lambda: ctx.dev("b381_g1_mul_batch_dev", dP1.data_ptr(), one, dK.data_ptr(), one, N, dO1.data_ptr()))
+res["g2_mul_ms"] = timed(lambda: ctx.dev("b381_g2_mul_batch_dev", dP2.data_ptr(), one, dK.data_ptr(), one, N, dO2.data_ptr()))
+for k in list(res):
+    if k.endswith("_ms"):
+        res[k.replace("_ms", "_per_s")] = n / (res[k] * 1e-3)
+print(json.dumps(res))

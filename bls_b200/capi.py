@@ -203,6 +203,19 @@ class Ctx:
     def g2_mul_batch(self, p, k):
         return self._mul("b381_g2_mul_batch", L.G2_AFFINE, p, k)
 
+    def hash_g2_with_domain_batch(self, msgs32, domains8):
+        """HashG2WithDomain over n 32-byte message hashes; domains8 is one 8-byte domain or n of them -> affine points"""
+        m = np.frombuffer(b"".join(bytes(x) for x in msgs32), np.uint8) if not isinstance(msgs32, np.ndarray) else np.ascontiguousarray(msgs32, np.uint8).reshape(-1)
+        d = np.frombuffer(bytes(domains8), np.uint8) if isinstance(domains8, (bytes, bytearray)) else \
+            (np.ascontiguousarray(domains8, np.uint8).reshape(-1) if isinstance(domains8, np.ndarray) else np.frombuffer(b"".join(bytes(x) for x in domains8), np.uint8))
+        assert m.size % 32 == 0 and d.size % 8 == 0
+        n = m.size // 32
+        assert d.size // 8 in (1, n)
+        out = np.zeros(n, dtype=L.G2_AFFINE)
+        self.call("b381_hash_g2_with_domain_batch", _hp(m.copy()), _hp(d.copy()), ctypes.c_size_t(0 if d.size == 8 and n > 1 else 1),
+                  ctypes.c_size_t(n), _hp(out))
+        return out
+
     # -- raw device buffers owned by the engine (b381_dev_alloc / b381_h2d / b381_d2h) ----------
     def dev_empty(self, nbytes):
         return DevBuf(self, nbytes)

@@ -12,6 +12,7 @@
 #include "curve.cuh"
 #include "agg.cuh"
 #include "codec.cuh"
+#include "hash.cuh"
 #include "vm.cuh"
 #include "vm_programs.inc"
 #include <stdlib.h>
@@ -444,6 +445,33 @@ int b381_g2_mul_batch(b381_ctx *ctx, const b381_g2_affine *p, size_t p_stride, c
 }
 int b381_g2_mul_batch_dev(b381_ctx *ctx, const b381_g2_affine *d_p, size_t p_stride, const b381_scalar *d_k, size_t k_stride, size_t n, b381_g2_affine *d_out) {
     return mul_dev<G2Codec>(ctx, d_p, p_stride, d_k, k_stride, n, d_out);
+}
+int b381_hash_g2_with_domain_batch_dev(b381_ctx *ctx, const uint8_t *d_msg32, const uint8_t *d_domain8, size_t domain_stride, size_t n,
+                                       b381_g2_affine *d_out) {
+    if (!ctx || domain_stride > 1 || (n && (!d_msg32 || !d_domain8 || !d_out))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    k_hash_g2_with_domain<<<grid_for(n, 64), 64, 0, ctx->stream>>>(d_msg32, d_domain8, domain_stride, n, (g2_affine_pod *)d_out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+int b381_hash_g2_with_domain_batch(b381_ctx *ctx, const uint8_t *msg32, const uint8_t *domain8, size_t domain_stride, size_t n,
+                                   b381_g2_affine *out) {
+    if (!ctx || domain_stride > 1 || (n && (!msg32 || !domain8 || !out))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    CK(cudaSetDevice(ctx->device));
+    void *dm, *dd, *dout;
+    size_t nd = domain_stride ? n : 1;
+    int rc = scratch_get(ctx, 12, n * 32, &dm); if (rc) return rc;
+    rc = scratch_get(ctx, 13, n * sizeof(b381_g2_affine), &dout); if (rc) return rc;
+    rc = scratch_get(ctx, 14, nd * 8, &dd); if (rc) return rc;
+    CK(cudaMemcpyAsync(dm, msg32, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dd, domain8, nd * 8, cudaMemcpyHostToDevice, ctx->stream));
+    rc = b381_hash_g2_with_domain_batch_dev(ctx, (const uint8_t *)dm, (const uint8_t *)dd, domain_stride, n, (b381_g2_affine *)dout);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, dout, n * sizeof(b381_g2_affine), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B381_OK;
 }
 
 // ---- pairing, device-resident ------------------------------------------------------------------

@@ -171,6 +171,15 @@ int b381_g2_mul_batch(b381_ctx *ctx, const b381_g2_affine *p, size_t p_stride, c
 int b381_g2_mul_batch_dev(b381_ctx *ctx, const b381_g2_affine *d_p, size_t p_stride, const b381_scalar *d_k,
                           size_t k_stride, size_t n, b381_g2_affine *d_out);
 
+/* HashG2WithDomain (g2.go:1041-1085) over a batch: out[i] = the affine form of HashG2WithDomain(msg32[i],
+ * domain8[i * domain_stride]) (the reference returns the same point unnormalised).  domain_stride is 0 (one 8-byte
+ * domain for the batch) or 1.  This is the message point of VerifyWithDomain / SignWithDomain /
+ * VerifyAggregate[Common]WithDomain (g1pubs/bls.go:138-141,171-174,294-311). */
+int b381_hash_g2_with_domain_batch(b381_ctx *ctx, const uint8_t *msg32, const uint8_t *domain8, size_t domain_stride,
+                                   size_t n, b381_g2_affine *out);
+int b381_hash_g2_with_domain_batch_dev(b381_ctx *ctx, const uint8_t *d_msg32, const uint8_t *d_domain8,
+                                       size_t domain_stride, size_t n, b381_g2_affine *d_out);
+
 /* ---- measurement -------------------------------------------------------------------------------- */
 /* Integer-pipe roofline probe: launches blocks x threads threads that each issue iters * 8
  * independent IMAD.WIDE.U32 (the 32x32->64 multiply-accumulate an Fq multiplication is made of).

@@ -52,6 +52,9 @@ for chk in (0, 1):
     assert not dS.any().item() and bytes(dO2.cpu().numpy()) == P2.tobytes()
 res["g1_mul_ms"] = timed(lambda: ctx.dev("b381_g1_mul_batch_dev", dP1.data_ptr(), one, dK.data_ptr(), one, N, dO1.data_ptr()))
 res["g2_mul_ms"] = timed(lambda: ctx.dev("b381_g2_mul_batch_dev", dP2.data_ptr(), one, dK.data_ptr(), one, N, dO2.data_ptr()))
+rng = np.random.RandomState(1)
+dM = up(rng.randint(0, 256, (n, 32), dtype=np.uint8)); dD = up(np.arange(8, dtype=np.uint8))
+res["hash_g2_with_domain_ms"] = timed(lambda: ctx.dev("b381_hash_g2_with_domain_batch_dev", dM.data_ptr(), dD.data_ptr(), ctypes.c_size_t(0), N, dO2.data_ptr()))
 for k in list(res):
     if k.endswith("_ms"):
         res[k.replace("_ms", "_per_s")] = n / (res[k] * 1e-3)

@@ -216,6 +216,19 @@ class Ctx:
                   ctypes.c_size_t(n), _hp(out))
         return out
 
+    def verify_with_domain_batch(self, pubs48, msgs32, domain8, sigs96):
+        """ok[i] for n wire-format (public key, 32-byte message hash, signature) triples -- b381_verify_with_domain_batch"""
+        cat = lambda xs, w: (np.ascontiguousarray(xs, np.uint8).reshape(-1) if isinstance(xs, np.ndarray)
+                             else np.frombuffer(b"".join(bytes(x) for x in xs), np.uint8).copy())
+        p, m, s = cat(pubs48, 48), cat(msgs32, 32), cat(sigs96, 96)
+        d = np.frombuffer(bytes(domain8), np.uint8).copy() if isinstance(domain8, (bytes, bytearray)) else cat(domain8, 8)
+        n = p.size // 48
+        assert p.size == 48 * n and m.size == 32 * n and s.size == 96 * n and d.size in (8, 8 * n)
+        ok = np.zeros(n, np.uint8)
+        self.call("b381_verify_with_domain_batch", _hp(p), _hp(m), _hp(d), ctypes.c_size_t(0 if d.size == 8 and n > 1 else 1), _hp(s),
+                  ctypes.c_size_t(n), _hp(ok))
+        return ok
+
     # -- raw device buffers owned by the engine (b381_dev_alloc / b381_h2d / b381_d2h) ----------
     def dev_empty(self, nbytes):
         return DevBuf(self, nbytes)

@@ -148,8 +148,8 @@ struct b381_ctx {
     uint64_t launches;
     char err[256];
     // grow-only device scratch
-    void *scratch[16];
-    size_t scratch_bytes[16];
+    void *scratch[24];
+    size_t scratch_bytes[24];
     // warp-cooperative VM programs resident on the device (csrc/vm.cuh)
     struct { uint4 *code, *consts; int lanes, nsteps, nslots, spill_fq; } vm[3];
     int use_vm;
@@ -248,7 +248,7 @@ void b381_free(b381_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 16; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < 24; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     for (int i = 0; i < 3; i++) { if (ctx->vm[i].code) cudaFree(ctx->vm[i].code); if (ctx->vm[i].consts) cudaFree(ctx->vm[i].consts); }
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -761,6 +761,55 @@ int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *
     ctx->launches++;
     CK(cudaGetLastError());
     return b381_pairing_product_is_one_dev(ctx, (b381_g1_affine *)P, (b381_g2_affine *)Q, 2 * nattest, (uint32_t *)off, nattest, d_ok);
+}
+
+// ---- VerifyWithDomain from wire bytes: deserialise + hash + 2-pair check per item, all on the device ----------------------
+int b381_verify_with_domain_batch_dev(b381_ctx *ctx, const uint8_t *d_pub48, const uint8_t *d_msg32, const uint8_t *d_domain8,
+                                      size_t domain_stride, const uint8_t *d_sig96, size_t n, uint8_t *d_ok) {
+    if (!ctx || domain_stride > 1 || n > 0x7FFFFFF0u || (n && (!d_pub48 || !d_msg32 || !d_domain8 || !d_sig96 || !d_ok))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    void *pub, *sig, *H, *st, *P, *Q, *off;
+    int rc = scratch_get(ctx, 15, n * sizeof(b381_g1_affine), &pub); if (rc) return rc;
+    rc = scratch_get(ctx, 16, n * sizeof(b381_g2_affine), &sig); if (rc) return rc;
+    rc = scratch_get(ctx, 17, n * sizeof(b381_g2_affine), &H); if (rc) return rc;
+    rc = scratch_get(ctx, 18, 3 * n, &st); if (rc) return rc;
+    rc = scratch_get(ctx, 2, 2 * n * sizeof(b381_g1_affine), &P); if (rc) return rc;
+    rc = scratch_get(ctx, 3, 2 * n * sizeof(b381_g2_affine), &Q); if (rc) return rc;
+    rc = scratch_get(ctx, 6, (n + 1) * sizeof(uint32_t), &off); if (rc) return rc;
+    uint8_t *st_pub = (uint8_t *)st, *st_sig = st_pub + n, *valid = st_pub + 2 * n;
+    rc = b381_g1_decompress_batch_dev(ctx, d_pub48, n, 1, (b381_g1_affine *)pub, st_pub); if (rc) return rc;
+    rc = b381_g2_decompress_batch_dev(ctx, d_sig96, n, 1, (b381_g2_affine *)sig, st_sig); if (rc) return rc;
+    rc = b381_hash_g2_with_domain_batch_dev(ctx, d_msg32, d_domain8, domain_stride, n, (b381_g2_affine *)H); if (rc) return rc;
+    k_verify_pairs<<<grid_for(n, 128), 128, 0, ctx->stream>>>((const g1_affine_pod *)pub, st_pub, (const g2_affine_pod *)sig, st_sig,
+                                                              (const g2_affine_pod *)H, n, (g1_affine_pod *)P, (g2_affine_pod *)Q,
+                                                              (uint32_t *)off, valid);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    rc = b381_pairing_product_is_one_dev(ctx, (b381_g1_affine *)P, (b381_g2_affine *)Q, 2 * n, (uint32_t *)off, n, d_ok);
+    if (rc) return rc;
+    k_and_bytes<<<grid_for(n, 256), 256, 0, ctx->stream>>>(d_ok, valid, n);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+int b381_verify_with_domain_batch(b381_ctx *ctx, const uint8_t *pub48, const uint8_t *msg32, const uint8_t *domain8, size_t domain_stride,
+                                  const uint8_t *sig96, size_t n, uint8_t *ok) {
+    if (!ctx || domain_stride > 1 || (n && (!pub48 || !msg32 || !domain8 || !sig96 || !ok))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    CK(cudaSetDevice(ctx->device));
+    void *in, *dok;
+    size_t nd = domain_stride ? n : 1;
+    int rc = scratch_get(ctx, 19, n * (48 + 32 + 96) + nd * 8, &in); if (rc) return rc;
+    rc = scratch_get(ctx, 20, n, &dok); if (rc) return rc;
+    uint8_t *dp = (uint8_t *)in, *dm = dp + 48 * n, *ds = dm + 32 * n, *dd = ds + 96 * n;
+    CK(cudaMemcpyAsync(dp, pub48, 48 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dm, msg32, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ds, sig96, 96 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dd, domain8, 8 * nd, cudaMemcpyHostToDevice, ctx->stream));
+    rc = b381_verify_with_domain_batch_dev(ctx, dp, dm, dd, domain_stride, ds, n, (uint8_t *)dok); if (rc) return rc;
+    CK(cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B381_OK;
 }
 
 // ---- aggregation, host buffers -------------------------------------------------------------------

@@ -104,6 +104,41 @@ __global__ void __launch_bounds__(64) k_hash_g2_with_domain(const uint8_t *__res
     if (i >= n) return;
     hash_g2_with_domain_one(out + i, msg + 32 * i, domain + 8 * i * domain_stride);
 }
+// The two Miller pairs of g1pubs.VerifyWithDomain (g1pubs/bls.go:171-174 -> CompareTwoPairings(G1One, sig, pub, H),
+// pairing.go:140-147): (P, Q)[2i] = (G1One, sig[i]), (P, Q)[2i+1] = (-pub[i], H[i]).  valid[i] = 0 when the key or the
+// signature failed to deserialise or is the point at infinity (the reference returns an error from Deserialize* in
+// the first case and panics in MillerLoop in the second): such a check is reported false.
+__global__ void __launch_bounds__(128) k_verify_pairs(const g1_affine_pod *__restrict__ pub, const uint8_t *__restrict__ pub_status,
+                                                      const g2_affine_pod *__restrict__ sig, const uint8_t *__restrict__ sig_status,
+                                                      const g2_affine_pod *__restrict__ H, size_t n, g1_affine_pod *__restrict__ P,
+                                                      g2_affine_pod *__restrict__ Q, uint32_t *__restrict__ group_off,
+                                                      uint8_t *__restrict__ valid) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) group_off[0] = 0;
+    if (i >= n) return;
+    group_off[i + 1] = (uint32_t)(2 * i + 2);
+    g1_affine_pod a = pub[i];
+    valid[i] = (pub_status[i] == 0 && sig_status[i] == 0 && !a.inf && !sig[i].inf) ? 1 : 0;
+    fp y;
+    fp_load_u64(y, a.y);
+    fp_neg(y, y);
+    fp_store_u64(a.y, y);
+    P[2 * i + 1] = a;
+    g1_affine_pod one;
+    const uint32_t gx[12] = {B381_G1_GEN_X_LIMBS}, gy[12] = {B381_G1_GEN_Y_LIMBS};
+    fp t;
+    fp_load_tab(t, gx); fp_store_u64(one.x, t);
+    fp_load_tab(t, gy); fp_store_u64(one.y, t);
+    one.inf = 0;
+    for (int k = 0; k < 7; k++) one.pad[k] = 0;
+    P[2 * i] = one;
+    Q[2 * i] = sig[i];
+    Q[2 * i + 1] = H[i];
+}
+__global__ void k_and_bytes(uint8_t *__restrict__ ok, const uint8_t *__restrict__ valid, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ok[i] = (ok[i] && valid[i]) ? 1 : 0;
+}
 #endif
 
 }  // namespace b381

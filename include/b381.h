@@ -180,6 +180,19 @@ int b381_hash_g2_with_domain_batch(b381_ctx *ctx, const uint8_t *msg32, const ui
 int b381_hash_g2_with_domain_batch_dev(b381_ctx *ctx, const uint8_t *d_msg32, const uint8_t *d_domain8,
                                        size_t domain_stride, size_t n, b381_g2_affine *d_out);
 
+/* g1pubs.VerifyWithDomain (g1pubs/bls.go:171-174) for n independent (public key, message hash, signature) triples
+ * given in WIRE format: pub48 = n x 48 bytes (PublicKey.Serialize), sig96 = n x 96 bytes (Signature.Serialize),
+ * msg32 = n x 32 bytes, domain8 = 8 bytes (domain_stride 0) or n x 8 bytes (domain_stride 1).  Per item the device
+ * runs DeserializePublicKey + DeserializeSignature (decompression and subgroup checks, g1pubs/bls.go:38-58,91-111),
+ * HashG2WithDomain, and CompareTwoPairings(G1One, sig, pub, H) (pairing.go:140-147).  ok[i] = 1 iff everything
+ * succeeded and the pairing equation holds; a key or signature that fails to deserialise, or is the point at
+ * infinity (where the reference panics), yields 0. */
+int b381_verify_with_domain_batch(b381_ctx *ctx, const uint8_t *pub48, const uint8_t *msg32, const uint8_t *domain8,
+                                  size_t domain_stride, const uint8_t *sig96, size_t n, uint8_t *ok);
+int b381_verify_with_domain_batch_dev(b381_ctx *ctx, const uint8_t *d_pub48, const uint8_t *d_msg32,
+                                      const uint8_t *d_domain8, size_t domain_stride, const uint8_t *d_sig96, size_t n,
+                                      uint8_t *d_ok);
+
 /* ---- measurement -------------------------------------------------------------------------------- */
 /* Integer-pipe roofline probe: launches blocks x threads threads that each issue iters * 8
  * independent IMAD.WIDE.U32 (the 32x32->64 multiply-accumulate an Fq multiplication is made of).

@@ -55,6 +55,20 @@ res["g2_mul_ms"] = timed(lambda: ctx.dev("b381_g2_mul_batch_dev", dP2.data_ptr()
 rng = np.random.RandomState(1)
 dM = up(rng.randint(0, 256, (n, 32), dtype=np.uint8)); dD = up(np.arange(8, dtype=np.uint8))
 res["hash_g2_with_domain_ms"] = timed(lambda: ctx.dev("b381_hash_g2_with_domain_batch_dev", dM.data_ptr(), dD.data_ptr(), ctypes.c_size_t(0), N, dO2.data_ptr()))
+# wire-level VerifyWithDomain: valid triples made with the engine itself
+sk = dK
+dPub = torch.empty(n * 104, dtype=torch.uint8, device=dev); dPubC = torch.empty(n * 48, dtype=torch.uint8, device=dev)
+G = up(hg.g1_mul(1))
+ctx.dev("b381_g1_mul_batch_dev", G.data_ptr(), ctypes.c_size_t(0), dK.data_ptr(), one, N, dPub.data_ptr())
+ctx.dev("b381_g1_compress_batch_dev", dPub.data_ptr(), N, dPubC.data_ptr())
+dH = torch.empty(n * 200, dtype=torch.uint8, device=dev); dSig = torch.empty(n * 200, dtype=torch.uint8, device=dev)
+dSigC = torch.empty(n * 96, dtype=torch.uint8, device=dev); dOk = torch.empty(n, dtype=torch.uint8, device=dev)
+ctx.dev("b381_hash_g2_with_domain_batch_dev", dM.data_ptr(), dD.data_ptr(), ctypes.c_size_t(0), N, dH.data_ptr())
+ctx.dev("b381_g2_mul_batch_dev", dH.data_ptr(), one, dK.data_ptr(), one, N, dSig.data_ptr())
+ctx.dev("b381_g2_compress_batch_dev", dSig.data_ptr(), N, dSigC.data_ptr())
+res["verify_with_domain_wire_ms"] = timed(lambda: ctx.dev("b381_verify_with_domain_batch_dev", dPubC.data_ptr(), dM.data_ptr(), dD.data_ptr(),
+                                                             ctypes.c_size_t(0), dSigC.data_ptr(), N, dOk.data_ptr()), reps=2)
+assert bool(dOk.all().item()), "valid signatures must verify"
 for k in list(res):
     if k.endswith("_ms"):
         res[k.replace("_ms", "_per_s")] = n / (res[k] * 1e-3)

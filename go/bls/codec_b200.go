@@ -1,0 +1,176 @@
+// +build b200
+
+// codec_b200.go -- additions to package bls: the wire-format, hashing and scalar-multiplication entry points of
+// libb381.so (include/b381.h), i.e. the work the callers of the verification path do on either side of it.
+// Batch functions are additions; the single-item functions of the reference (DecompressG1/G2, CompressG1/G2,
+// HashG2WithDomain, G1Affine.MulFR, G2Affine.MulFR) keep their signatures and can forward here with n = 1.
+// NOT COMPILED in this repository's build image (no Go toolchain); see INTEGRATION.md.
+package bls
+
+/*
+#include "b381.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"unsafe"
+)
+
+// decodeErrors are the reference's own messages (g1.go:120,192,204,213; g2.go:158,226,234,242), indexed by status.
+var decodeErrors = []error{
+	nil,
+	errors.New("unexpected compression mode"),
+	errors.New("unexpected information in compressed infinity"),
+	errors.New("point not on curve"),
+	errors.New("not in correct subgroup"),
+}
+
+// DecompressG1Batch is DecompressG1 (g1.go:185-195) over many 48-byte encodings; errs[i] is nil or the
+// reference's error.  checked = false gives DecompressG1Unchecked (g1.go:199-227).
+func DecompressG1Batch(in [][48]byte, checked bool) ([]G1Affine, []error) {
+	n := len(in)
+	out := make([]G1Affine, n)
+	st := make([]uint8, n)
+	errs := make([]error, n)
+	if n == 0 {
+		return out, errs
+	}
+	chk := C.int(0)
+	if checked {
+		chk = 1
+	}
+	rc := C.b381_g1_decompress_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&in[0])), C.size_t(n), chk,
+		(*C.b381_g1_affine)(unsafe.Pointer(&out[0])), (*C.uint8_t)(unsafe.Pointer(&st[0])))
+	must(rc)
+	for i, s := range st {
+		errs[i] = decodeErrors[s]
+	}
+	return out, errs
+}
+
+// DecompressG2Batch is DecompressG2 (g2.go:219-229) / DecompressG2Unchecked (g2.go:232-265) over 96-byte encodings.
+func DecompressG2Batch(in [][96]byte, checked bool) ([]G2Affine, []error) {
+	n := len(in)
+	out := make([]G2Affine, n)
+	st := make([]uint8, n)
+	errs := make([]error, n)
+	if n == 0 {
+		return out, errs
+	}
+	chk := C.int(0)
+	if checked {
+		chk = 1
+	}
+	rc := C.b381_g2_decompress_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&in[0])), C.size_t(n), chk,
+		(*C.b381_g2_affine)(unsafe.Pointer(&out[0])), (*C.uint8_t)(unsafe.Pointer(&st[0])))
+	must(rc)
+	for i, s := range st {
+		errs[i] = decodeErrors[s]
+	}
+	return out, errs
+}
+
+// CompressG1Batch / CompressG2Batch: CompressG1 (g1.go:230-249) / CompressG2 (g2.go:268-289).
+func CompressG1Batch(p []G1Affine) [][48]byte {
+	out := make([][48]byte, len(p))
+	if len(p) > 0 {
+		must(C.b381_g1_compress_batch(ctx(), (*C.b381_g1_affine)(unsafe.Pointer(&p[0])), C.size_t(len(p)),
+			(*C.uint8_t)(unsafe.Pointer(&out[0]))))
+	}
+	return out
+}
+
+func CompressG2Batch(p []G2Affine) [][96]byte {
+	out := make([][96]byte, len(p))
+	if len(p) > 0 {
+		must(C.b381_g2_compress_batch(ctx(), (*C.b381_g2_affine)(unsafe.Pointer(&p[0])), C.size_t(len(p)),
+			(*C.uint8_t)(unsafe.Pointer(&out[0]))))
+	}
+	return out
+}
+
+// scalars flattens []*FR (a pointer type, fr.go:11-13) into canonical 4 x u64 integers: FR.ToRepr (fr.go:316-329).
+func scalars(k []*FR) []FRRepr {
+	out := make([]FRRepr, len(k))
+	for i, s := range k {
+		out[i] = *s.ToRepr()
+	}
+	return out
+}
+
+// MulG1Batch: out[i] = p[i].MulFR(k[i]).ToAffine() (g1.go:80-90,322-340).  len(p) == 1 broadcasts the base
+// (PrivToPub, g1pubs/bls.go:144-146); len(k) == 1 broadcasts the scalar.
+func MulG1Batch(p []G1Affine, k []*FR) []G1Affine {
+	n := len(p)
+	if len(k) > n {
+		n = len(k)
+	}
+	out := make([]G1Affine, n)
+	ks := scalars(k)
+	ps, kst := C.size_t(1), C.size_t(1)
+	if len(p) == 1 && n > 1 {
+		ps = 0
+	}
+	if len(k) == 1 && n > 1 {
+		kst = 0
+	}
+	must(C.b381_g1_mul_batch(ctx(), (*C.b381_g1_affine)(unsafe.Pointer(&p[0])), ps,
+		(*C.b381_scalar)(unsafe.Pointer(&ks[0])), kst, C.size_t(n), (*C.b381_g1_affine)(unsafe.Pointer(&out[0]))))
+	return out
+}
+
+// MulG2Batch: out[i] = p[i].MulFR(k[i]).ToAffine() (g2.go:92-102,365-386): Sign of many hashed messages.
+func MulG2Batch(p []G2Affine, k []*FR) []G2Affine {
+	n := len(p)
+	if len(k) > n {
+		n = len(k)
+	}
+	out := make([]G2Affine, n)
+	ks := scalars(k)
+	ps, kst := C.size_t(1), C.size_t(1)
+	if len(p) == 1 && n > 1 {
+		ps = 0
+	}
+	if len(k) == 1 && n > 1 {
+		kst = 0
+	}
+	must(C.b381_g2_mul_batch(ctx(), (*C.b381_g2_affine)(unsafe.Pointer(&p[0])), ps,
+		(*C.b381_scalar)(unsafe.Pointer(&ks[0])), kst, C.size_t(n), (*C.b381_g2_affine)(unsafe.Pointer(&out[0]))))
+	return out
+}
+
+// HashG2WithDomainBatch: out[i] = HashG2WithDomain(msgs[i], domain).ToAffine() (g2.go:1041-1085).
+func HashG2WithDomainBatch(msgs [][32]byte, domain [8]byte) []G2Affine {
+	out := make([]G2Affine, len(msgs))
+	if len(msgs) > 0 {
+		must(C.b381_hash_g2_with_domain_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&msgs[0])),
+			(*C.uint8_t)(unsafe.Pointer(&domain[0])), 0, C.size_t(len(msgs)), (*C.b381_g2_affine)(unsafe.Pointer(&out[0]))))
+	}
+	return out
+}
+
+// VerifyWithDomainWire verifies n wire-format triples entirely on the device: ok[i] ==
+// g1pubs.VerifyWithDomain(msgs[i], DeserializePublicKey(pubs[i]), DeserializeSignature(sigs[i]), domain)
+// (g1pubs/bls.go:38-58,91-111,171-174), false when either deserialisation fails.
+func VerifyWithDomainWire(pubs [][48]byte, msgs [][32]byte, domain [8]byte, sigs [][96]byte) []bool {
+	n := len(pubs)
+	ok8 := make([]uint8, n)
+	out := make([]bool, n)
+	if n == 0 {
+		return out
+	}
+	must(C.b381_verify_with_domain_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&pubs[0])), (*C.uint8_t)(unsafe.Pointer(&msgs[0])),
+		(*C.uint8_t)(unsafe.Pointer(&domain[0])), 0, (*C.uint8_t)(unsafe.Pointer(&sigs[0])), C.size_t(n),
+		(*C.uint8_t)(unsafe.Pointer(&ok8[0]))))
+	for i, v := range ok8 {
+		out[i] = v != 0
+	}
+	return out
+}
+
+func must(rc C.int) {
+	if rc != C.B381_OK {
+		panic(C.GoString(C.b381_last_error(ctx())))
+	}
+}

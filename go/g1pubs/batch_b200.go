@@ -71,6 +71,26 @@ func VerifyBatchCommonWithDomain(sigs []*Signature, committees [][]*PublicKey, m
 	return bls.PairingProductsAreOne(p, q, off)
 }
 
+// VerifyWithDomainBatch verifies n independent wire-format (public key, message hash, signature) triples with one
+// call; deserialisation, subgroup checks, hashing to G2 and the pairing checks all run on the device.
+// ok[i] == VerifyWithDomain(msgs[i], DeserializePublicKey(pubs[i]), DeserializeSignature(sigs[i]), domain), false
+// where either Deserialize* would have returned an error (g1pubs/bls.go:38-58,91-111,171-174).
+func VerifyWithDomainBatch(pubs [][48]byte, msgs [][32]byte, domain [8]byte, sigs [][96]byte) []bool {
+	return bls.VerifyWithDomainWire(pubs, msgs, domain, sigs)
+}
+
+// DeserializePublicKeys is DeserializePublicKey (g1pubs/bls.go:91-98) over a batch.
+func DeserializePublicKeys(b [][48]byte) ([]*PublicKey, []error) {
+	aff, errs := bls.DecompressG1Batch(b, true)
+	out := make([]*PublicKey, len(b))
+	for i := range aff {
+		if errs[i] == nil {
+			out[i] = &PublicKey{p: aff[i].ToProjective()}
+		}
+	}
+	return out, errs
+}
+
 func hasDuplicates(msgs [][]byte) bool {
 	cp := make([][]byte, len(msgs))
 	for i, m := range msgs {

@@ -28,6 +28,11 @@ __device__ __constant__ uint32_t d_b_coeff[12] = {B381_B_COEFF_LIMBS};
 __device__ __constant__ uint32_t d_qm3o4[12] = {B381_Q_MINUS_3_OVER_4_LIMBS};
 __device__ __constant__ uint32_t d_qm1o2[12] = {B381_Q_MINUS_1_OVER_2_LIMBS};
 __device__ __constant__ uint32_t d_r_order[8] = {B381_R_ORDER_LIMBS};
+__device__ __constant__ uint32_t d_beta[12] = {B381_BETA_LIMBS};
+__device__ __constant__ uint32_t d_psi_cx_c1[12] = {B381_PSI_CX_C1_LIMBS};
+__device__ __constant__ uint32_t d_psi_cy[24] = {B381_PSI_CY_LIMBS};
+__device__ __constant__ uint32_t d_bls_x[2] = {B381_BLS_X_LIMBS};
+__device__ __constant__ uint32_t d_bls_x2[4] = {B381_BLS_X2_LIMBS};
 #endif
 #if !defined(__CUDA_ARCH__)
 static const uint32_t h_r2_raw[12] = {B381_R2_RAW_LIMBS};
@@ -36,6 +41,11 @@ static const uint32_t h_b_coeff[12] = {B381_B_COEFF_LIMBS};
 static const uint32_t h_qm3o4[12] = {B381_Q_MINUS_3_OVER_4_LIMBS};
 static const uint32_t h_qm1o2[12] = {B381_Q_MINUS_1_OVER_2_LIMBS};
 static const uint32_t h_r_order[8] = {B381_R_ORDER_LIMBS};
+static const uint32_t h_beta[12] = {B381_BETA_LIMBS};
+static const uint32_t h_psi_cx_c1[12] = {B381_PSI_CX_C1_LIMBS};
+static const uint32_t h_psi_cy[24] = {B381_PSI_CY_LIMBS};
+static const uint32_t h_bls_x[2] = {B381_BLS_X_LIMBS};
+static const uint32_t h_bls_x2[4] = {B381_BLS_X2_LIMBS};
 #endif
 
 // ---- integers <-> field elements -----------------------------------------------------------------------------------
@@ -155,6 +165,7 @@ struct G1Codec {
     static HD void b_coeff(T &b) { fp_load_tab(b, B381_TAB(b_coeff)); }
     static HD bool sqrt(T *o, const T *a) { return fp_sqrt(o, a); }
     static HD int cmp(const T &a, const T &b) { return fp_cmp(a, b); }
+    static HD bool in_subgroup(const T &x, const T &y);
     static HD void x_from_bytes(T &x, const uint8_t *c) { fp raw; fp_raw_from_be48(raw, c); fp_from_raw(x, raw); }
     static HD void x_to_bytes(uint8_t *c, const T &x) { fp raw; fp_to_raw(raw, x); fp_raw_to_be48(c, raw); }
     static HD void load(T &x, T &y, const APOD *p) { fp_load_u64(x, p->x); fp_load_u64(y, p->y); }
@@ -171,6 +182,7 @@ struct G2Codec {
     static HD void b_coeff(T &b) { fp_load_tab(b.c0, B381_TAB(b_coeff)); b.c1 = b.c0; }   // 4(1 + u), g2.go:32
     static HD bool sqrt(T *o, const T *a) { return fp2_sqrt(o, a); }
     static HD int cmp(const T &a, const T &b) { return fp2_cmp(a, b); }
+    static HD bool in_subgroup(const T &x, const T &y);
     // x.c1 comes first on the wire (g2.go:250-257, 275-278)
     static HD void x_from_bytes(T &x, const uint8_t *c) {
         fp raw;
@@ -204,6 +216,21 @@ template <class F> HDN void point_mul(xyzz<F> *acc, const typename F::T *x, cons
     }
     *acc = a;
 }
+// acc = (pos - neg) * (x, y): MSB-first ladder over a non-adjacent form given as two bit masks (constants only)
+template <class F> HDN void point_mul_naf(xyzz<F> *acc, const typename F::T *x, const typename F::T *y, const uint32_t *pos,
+                                          const uint32_t *neg, int nlimbs) {
+    xyzz<F> a;
+    xyzz_set_inf(a);
+    typename F::T ny;
+    F::neg(ny, *y);
+#pragma unroll 1
+    for (int i = nlimbs * 32 - 1; i >= 0; i--) {
+        xyzz_dbl(a);
+        if ((pos[i >> 5] >> (i & 31)) & 1) xyzz_madd(a, *x, *y);
+        else if ((neg[i >> 5] >> (i & 31)) & 1) xyzz_madd(a, *x, ny);
+    }
+    *acc = a;
+}
 // affine coordinates of a finite XYZZ point (ToAffine, g1.go:322-340: same canonical values)
 template <class F> HD void xyzz_to_affine(typename F::T &x, typename F::T &y, const xyzz<F> &p) {
     typename F::T zi, t;
@@ -213,6 +240,70 @@ template <class F> HD void xyzz_to_affine(typename F::T &x, typename F::T &y, co
     F::sqr(t, t);                      // 1/ZZ
     F::mul(x, p.x, t);
 }
+
+// ---- membership in the r-torsion ---------------------------------------------------------------------------------------
+// The reference tests [r]P == O with a 255-bit double-and-add (IsInCorrectSubgroupAssumingOnCurve, g1.go:137-141,
+// g2.go:293-295).  For points ON THE CURVE the endomorphism criteria of M. Scott, "A note on group membership tests
+// for G1, G2 and GT on BLS pairing-friendly curves" (eprint 2021/1130) decide the same predicate with a 128-bit
+// (G1) / 64-bit (G2) ladder:   G1:  (beta x, y) == -[x^2] P        G2:  psi(P) == [x] P      (x = -0xd201000000010000)
+// B381_SUBGROUP_LADDER selects the reference's full ladder instead (tests compare both with the oracle, including
+// points of the cofactor subgroups).
+// is the finite XYZZ point `a` equal to the affine point (x, y)?
+template <class F> HD bool xyzz_eq_affine(const xyzz<F> &a, const typename F::T &x, const typename F::T &y) {
+    if (xyzz_is_inf(a)) return false;
+    typename F::T t;
+    F::mul(t, x, a.zz);
+    F::sub(t, t, a.x);
+    if (!F::is_zero(t)) return false;
+    F::mul(t, y, a.zzz);
+    F::sub(t, t, a.y);
+    return F::is_zero(t);
+}
+HD bool g1_in_subgroup(const fp &x, const fp &y) {
+#ifdef B381_SUBGROUP_LADDER
+    xyzz<FpOut> acc;
+    point_mul<FpOut>(&acc, &x, &y, B381_TAB(r_order), 8);
+    return xyzz_is_inf(acc);
+#else
+    xyzz<FpOut> acc;
+    point_mul<FpOut>(&acc, &x, &y, B381_TAB(bls_x2), 4);        // [x^2] P
+    fp bx, ny, beta;
+    fp_load_tab(beta, B381_TAB(beta));
+    fp_mul(bx, x, beta);
+    fp_neg(ny, y);
+    return xyzz_eq_affine<FpOut>(acc, bx, ny);                    // == -(beta x, y)
+#endif
+}
+// psi(x, y) = (PSI_CX conj(x), PSI_CY conj(y)), PSI_CX = (0, k): the reference's psi (hash.go:341-366)
+HD void g2_psi(fp2 &ox, fp2 &oy, const fp2 &x, const fp2 &y) {
+    fp k;
+    fp_load_tab(k, B381_TAB(psi_cx_c1));
+    fp2 cy, t;
+    // (0 + k u)(x0 - x1 u) = k x1 + k x0 u
+    fp_mul(t.c0, x.c1, k);
+    fp_mul(t.c1, x.c0, k);
+    ox = t;
+    fp_load_tab(cy.c0, B381_TAB(psi_cy)); fp_load_tab(cy.c1, B381_TAB(psi_cy) + 12);
+    fp2_conj(t, y);
+    fp2_mul(&oy, &t, &cy);
+}
+HD bool g2_in_subgroup(const fp2 &x, const fp2 &y) {
+#ifdef B381_SUBGROUP_LADDER
+    xyzz<Fp2Out> acc;
+    point_mul<Fp2Out>(&acc, &x, &y, B381_TAB(r_order), 8);
+    return xyzz_is_inf(acc);
+#else
+    xyzz<Fp2Out> acc;
+    point_mul<Fp2Out>(&acc, &x, &y, B381_TAB(bls_x), 2);         // [|x|] P = -[x] P
+    fp2 px, py;
+    g2_psi(px, py, x, y);
+    fp2_neg(py, py);
+    return xyzz_eq_affine<Fp2Out>(acc, px, py);                   // [|x|] P == -psi(P)
+#endif
+}
+
+HD bool G1Codec::in_subgroup(const fp &x, const fp &y) { return g1_in_subgroup(x, y); }
+HD bool G2Codec::in_subgroup(const fp2 &x, const fp2 &y) { return g2_in_subgroup(x, y); }
 
 // ---- decompression ---------------------------------------------------------------------------------------------------
 // DecompressG1[Unchecked] / DecompressG2[Unchecked]; the affine point is written for status 0 and 4 (the reference
@@ -243,11 +334,7 @@ template <class C> HD int decompress_one(typename C::APOD *out, const uint8_t *i
     C::F::neg(ny, y);
     if (!((C::cmp(y, ny) < 0) != greatest)) y = ny;     // g1.go:126-129
     C::store(out, x, y, false);
-    if (check_subgroup) {
-        xyzz<typename C::F> acc;
-        point_mul<typename C::F>(&acc, &x, &y, B381_TAB(r_order), 8);
-        if (!xyzz_is_inf(acc)) return CODEC_ERR_SUBGROUP;
-    }
+    if (check_subgroup && !C::in_subgroup(x, y)) return CODEC_ERR_SUBGROUP;
     return CODEC_OK;
 }
 // CompressG1 / CompressG2

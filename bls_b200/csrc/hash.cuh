@@ -21,10 +21,14 @@ namespace b381 {
         0xc67178f2
 #if defined(__CUDACC__)
 __device__ __constant__ uint32_t d_g2_cofactor[16] = {B381_G2_COFACTOR_LIMBS};
+__device__ __constant__ uint32_t d_g2_cof_pos[16] = {B381_G2_COFACTOR_NAF_POS_LIMBS};
+__device__ __constant__ uint32_t d_g2_cof_neg[16] = {B381_G2_COFACTOR_NAF_NEG_LIMBS};
 __device__ __constant__ uint32_t d_sha_k[64] = {B381_SHA_K};
 #endif
 #if !defined(__CUDA_ARCH__)
 static const uint32_t h_g2_cofactor[16] = {B381_G2_COFACTOR_LIMBS};
+static const uint32_t h_g2_cof_pos[16] = {B381_G2_COFACTOR_NAF_POS_LIMBS};
+static const uint32_t h_g2_cof_neg[16] = {B381_G2_COFACTOR_NAF_NEG_LIMBS};
 static const uint32_t h_sha_k[64] = {B381_SHA_K};
 #endif
 
@@ -80,17 +84,27 @@ HD void hash_g2_with_domain_one(g2_affine_pod *out, const uint8_t *msg32, const 
     buf[40] = 2; sha256_short(dg, buf, 41); fp_from_digest(x.c1, dg);
     G2Codec::b_coeff(b);
     fp2_set_one(one);
+    // FQ2.Sqrt fails exactly when x^3 + b is a non-square, i.e. when its norm is a non-residue of Fq: one Fq
+    // exponentiation (570 multiplications) per rejected candidate instead of an Fq2 exponentiation (1 330), and the
+    // lanes of a warp leave the divergent search before the expensive root
+    fp m1;
+    fp_load_tab(m1, B381_TAB(neg_one));
     for (;;) {
         fp2_sqr(&t, &x);
         fp2_mul(&t, &t, &x);
         fp2_add(t, t, b);
-        if (fp2_sqrt(&y, &t)) break;
+        fp n0, n1;
+        fp_sqr(n0, t.c0); fp_sqr(n1, t.c1);
+        fp_add(n0, n0, n1);
+        field_pow<FpInl>(&n1, &n0, B381_TAB(qm1o2));       // Euler: -1 for a non-residue (0 and 1 are squares)
+        if (!fp_eq(n1, m1)) break;
         fp2_add(x, x, one);
     }
+    fp2_sqrt(&y, &t);
     fp2_neg(t, y);
     if (!(fp2_cmp(y, t) > 0)) y = t;                   // "favor the lower y value": keep the one with Parity() true
     xyzz<Fp2Out> acc;
-    point_mul<Fp2Out>(&acc, &x, &y, B381_TAB(g2_cofactor), 16);
+    point_mul_naf<Fp2Out>(&acc, &x, &y, B381_TAB(g2_cof_pos), B381_TAB(g2_cof_neg), 16);
     if (xyzz_is_inf(acc)) { fp2_set_zero(x); fp2_set_one(y); G2Codec::store(out, x, y, true); return; }
     xyzz_to_affine<Fp2Out>(x, y, acc);
     G2Codec::store(out, x, y, false);

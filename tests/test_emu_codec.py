@@ -79,3 +79,49 @@ def test_scalar_mul(emu, orc, which):
     assert got1.tobytes() == grp.to_affine(grp.mul_fr(np.repeat(pts[:1], n), k)).tobytes()
     getattr(emu, "emu_%s_mul" % which)(_p(pts), ctypes.c_size_t(1), _p(k[3:]), ctypes.c_size_t(0), ctypes.c_size_t(n), _p(got1))
     assert got1.tobytes() == grp.to_affine(grp.mul_fr(pts, np.repeat(k[3:4], n, axis=0))).tobytes()
+
+
+@pytest.mark.parametrize("which", ["g1", "g2"])
+def test_subgroup_criterion_on_cofactor_points(emu, orc, which):
+    """The endomorphism membership tests (codec.cuh) must agree with the reference's [r]P == O (g1.go:137-141,
+    g2.go:293-295) on every curve point -- in particular on points of the cofactor subgroups, of small order, and on
+    sums of a subgroup point and a cofactor point."""
+    from bls_b200 import hostmath as hm
+    grp, dtype, nb = (orc.g1, L.G1_AFFINE, 48) if which == "g1" else (orc.g2, L.G2_AFFINE, 96)
+    mul, add = (hm.g1_mul, hm.g1_add) if which == "g1" else (hm.g2_mul, hm.g2_add)
+    to_pods = hg.g1_points if which == "g1" else hg.g2_points
+    gen = hm.G1 if which == "g1" else hm.G2
+    cof = 76329603384216526031706109802092473003 if which == "g1" else hm.G2_COFACTOR   # g1.go:144, g2.go:133
+    # random curve points: decompress random x values without the subgroup check
+    rng = np.random.RandomState(11)
+    pts = []
+    while len(pts) < 4:
+        b = bytearray(rng.randint(0, 256, nb, dtype=np.uint8).tobytes())
+        b[0] = (b[0] & 0x1f) | 0x80
+        if nb == 96:
+            b[48] &= 0x1f
+        e, o = grp.decompress(bytes(b), False)
+        if e == 0:
+            x = L.fp_to_int(o["x"][0]) if which == "g1" else (L.fp_to_int(o["x"][0][0]), L.fp_to_int(o["x"][0][1]))
+            y = L.fp_to_int(o["y"][0]) if which == "g1" else (L.fp_to_int(o["y"][0][0]), L.fp_to_int(o["y"][0][1]))
+            pts.append((x, y))
+    small = [3, 11, 10177] if which == "g1" else [13, 23, 2713]
+    cands = []
+    for R in pts:
+        T = mul(R, L.R_ORDER)                          # in the cofactor subgroup
+        S = mul(R, cof)                                # in the r-torsion
+        cands += [R, T, S, add(T, S), add(S, mul(gen, 5))]
+        for p in small:
+            if cof % p == 0:
+                U = mul(T, cof // p)                   # order 1 or p
+                if U is not None:
+                    cands += [U, add(U, S)]
+    cands = [c for c in cands if c is not None]
+    arr = to_pods(cands)
+    comp = b"".join(grp.compress(arr[i:i + 1]) for i in range(arr.size))
+    raw = np.frombuffer(comp, np.uint8).copy()
+    got = np.zeros(arr.size, dtype=dtype); st = np.zeros(arr.size, np.uint8)
+    getattr(emu, "emu_%s_decompress" % which)(_p(raw), ctypes.c_size_t(arr.size), 1, _p(got), _p(st))
+    exp = [0 if grp.in_subgroup(arr[i:i + 1]) else 4 for i in range(arr.size)]
+    assert st.tolist() == exp
+    assert 0 in exp and 4 in exp

@@ -109,7 +109,7 @@ def traffic_from_profiles(kernel):
 def aggregate_extras(ctx, stream, dev, rank, world, torch, np):
     """aggregate-verification side of the metric (BASELINE.json configs 3-5), device-resident inputs, CUDA events:
     (a) one g1pubs VerifyAggregateCommon over 2^20 public keys (sum kernel + one 2-pair check),
-    (b) a batch of 2^14 attestations x 128-key committees (Ethereum-beacon shape),
+    (b) a batch of 2^15 attestations x 128-key committees (Ethereum-beacon shape; 2^18 over 8 GPUs),
     (c) a 2^20-point G1 MSM with 255-bit scalars; under torchrun also bucket-sharded over the ranks with one
         all-gather of 144-byte partials (bls_b200/dist.py)."""
     import torch.distributed as dist
@@ -157,7 +157,7 @@ def aggregate_extras(ctx, stream, dev, rank, world, torch, np):
     out["verify_aggregate_common_2^20_keys"] = {"sum_ms": t_sum, "pairing_check_ms": t_chk,
                                                  "verifies_per_s": 1e3 / (t_sum + t_chk)}
     # (b) attestation batch: 64 distinct (committee, message) templates tiled to 2^14 attestations, 1 in 64 corrupted
-    natt, comm, ntmpl = 1 << 14, 128, 64
+    natt, comm, ntmpl = 1 << 15, 128, 64        # BASELINE config 5: 2^18 attestations over 8 GPUs = 2^15 per GPU
     rng = np.random.RandomState(1 + rank)
     tk = rng.randint(0, m, size=(ntmpl, comm))
     hs = [0x77 + 5 * j for j in range(8)]
@@ -178,7 +178,36 @@ def aggregate_extras(ctx, stream, dev, rank, world, torch, np):
     ta = torch.tensor([t_att], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ta, op=dist.ReduceOp.MAX)
-    out["attestation_batch_2^14_x_128_keys"] = {"ms": float(ta.item()), "aggregate_verifies_per_s": world * natt / (float(ta.item()) * 1e-3)}
+    out["attestation_batch_2^15_x_128_keys"] = {"ms": float(ta.item()), "aggregate_verifies_per_s": world * natt / (float(ta.item()) * 1e-3)}
+    # (b') g1pubs.VerifyWithDomain from wire bytes: 2^16 (public key, message hash, signature) triples per GPU; deserialisation,
+    # subgroup checks, HashG2WithDomain and the 2-pair check all on the device.  Inputs are made with the engine itself
+    # (PrivToPub / SignWithDomain / Serialize batches, each parity-tested against the oracle); one triple in 64 is corrupted.
+    nw = 1 << 16
+    one, zero, NW = ctypes.c_size_t(1), ctypes.c_size_t(0), ctypes.c_size_t(nw)
+    Kw, _ = hg.splitmix_scalars(7 + rank, 1 << 12)
+    dKw = up(np.resize(Kw, (nw, 4)))
+    rngw = np.random.RandomState(100 + rank)
+    msgs_w = rngw.randint(0, 256, (nw, 32), dtype=np.uint8)
+    dM = up(msgs_w); dDom = up(np.arange(8, dtype=np.uint8)); dG = up(hg.g1_mul(1))
+    dPub = torch.empty(nw * 104, dtype=torch.uint8, device=dev); dPubC = torch.empty(nw * 48, dtype=torch.uint8, device=dev)
+    dH = torch.empty(nw * 200, dtype=torch.uint8, device=dev); dSg = torch.empty(nw * 200, dtype=torch.uint8, device=dev)
+    dSgC = torch.empty(nw * 96, dtype=torch.uint8, device=dev); dOkW = torch.empty(nw, dtype=torch.uint8, device=dev)
+    ctx.dev("b381_g1_mul_batch_dev", dG.data_ptr(), zero, dKw.data_ptr(), one, NW, dPub.data_ptr())
+    ctx.dev("b381_g1_compress_batch_dev", dPub.data_ptr(), NW, dPubC.data_ptr())
+    ctx.dev("b381_hash_g2_with_domain_batch_dev", dM.data_ptr(), dDom.data_ptr(), zero, NW, dH.data_ptr())
+    ctx.dev("b381_g2_mul_batch_dev", dH.data_ptr(), one, dKw.data_ptr(), one, NW, dSg.data_ptr())
+    ctx.dev("b381_g2_compress_batch_dev", dSg.data_ptr(), NW, dSgC.data_ptr())
+    dM[63 * 32::64 * 32] ^= 1                                     # flip a bit of every 64th message
+    t_wire = timed(lambda: ctx.dev("b381_verify_with_domain_batch_dev", dPubC.data_ptr(), dM.data_ptr(), dDom.data_ptr(), zero,
+                                   dSgC.data_ptr(), NW, dOkW.data_ptr()), reps=2)
+    okw = dOkW.cpu().numpy()
+    assert okw.reshape(-1, 64)[:, :63].all() and not okw.reshape(-1, 64)[:, 63].any(), "wire-level verdicts differ from construction"
+    tw = torch.tensor([t_wire], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    out["verify_with_domain_wire_2^16"] = {"ms": float(tw.item()), "verifies_per_s": world * nw / (float(tw.item()) * 1e-3),
+                                           "bytes_in_per_verify": 48 + 32 + 96}
+    del dKw, dM, dPub, dPubC, dH, dSg, dSgC, dOkW
     # (c) MSM 2^20, closed-form check on the tiled points: sum k_i P_(i mod m)
     n_c = 1 << 20
     K, kvals = hg.splitmix_scalars(99, 1 << 12)

@@ -112,7 +112,7 @@ HD void hash_g2_with_domain_one(g2_affine_pod *out, const uint8_t *msg32, const 
 
 #if defined(__CUDACC__)
 // out[i] = HashG2WithDomain(msg[i], domain[i * domain_stride]); domain_stride 0 = one domain for the whole batch
-__global__ void __launch_bounds__(64) k_hash_g2_with_domain(const uint8_t *__restrict__ msg, const uint8_t *__restrict__ domain,
+__global__ void __launch_bounds__(64, CODEC_MIN_BLOCKS) k_hash_g2_with_domain(const uint8_t *__restrict__ msg, const uint8_t *__restrict__ domain,
                                                             size_t domain_stride, size_t n, g2_affine_pod *__restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -229,6 +229,42 @@ class Ctx:
                   ctypes.c_size_t(n), _hp(ok))
         return ok
 
+    @staticmethod
+    def _pack(msgs):
+        off = np.zeros(len(msgs) + 1, np.uint64)
+        if len(msgs):
+            off[1:] = np.cumsum([len(m) for m in msgs])
+        raw = np.frombuffer(b"".join(bytes(m) for m in msgs) + b"\0", np.uint8).copy()
+        return raw, off
+
+    def hash_g1_batch(self, msgs):
+        """HashG1 of every message (bytes) -> affine G1 points -- b381_hash_g1_batch"""
+        raw, off = self._pack(msgs); out = np.zeros(len(msgs), dtype=L.G1_AFFINE)
+        self.call("b381_hash_g1_batch", _hp(raw), _hp(off), ctypes.c_size_t(len(msgs)), _hp(out))
+        return out
+
+    def hash_g2_batch(self, msgs):
+        """HashG2 of every message (bytes) -> affine G2 points -- b381_hash_g2_batch"""
+        raw, off = self._pack(msgs); out = np.zeros(len(msgs), dtype=L.G2_AFFINE)
+        self.call("b381_hash_g2_batch", _hp(raw), _hp(off), ctypes.c_size_t(len(msgs)), _hp(out))
+        return out
+
+    def _verify_wire(self, name, pubs, pb, msgs, sigs, sb):
+        p = np.ascontiguousarray(pubs, np.uint8).reshape(-1); s = np.ascontiguousarray(sigs, np.uint8).reshape(-1)
+        n = len(msgs)
+        assert p.size == pb * n and s.size == sb * n
+        raw, off = self._pack(msgs); ok = np.zeros(n, np.uint8)
+        self.call(name, _hp(p), _hp(raw), _hp(off), _hp(s), ctypes.c_size_t(n), _hp(ok))
+        return ok
+
+    def g1pubs_verify_batch(self, pubs48, msgs, sigs96):
+        """ok[i] = g1pubs.Verify(msgs[i], pub_i, sig_i) from wire bytes -- b381_g1pubs_verify_batch"""
+        return self._verify_wire("b381_g1pubs_verify_batch", pubs48, 48, msgs, sigs96, 96)
+
+    def g2pubs_verify_batch(self, pubs96, msgs, sigs48):
+        """ok[i] = g2pubs.Verify(msgs[i], pub_i, sig_i) from wire bytes -- b381_g2pubs_verify_batch"""
+        return self._verify_wire("b381_g2pubs_verify_batch", pubs96, 96, msgs, sigs48, 48)
+
     # -- raw device buffers owned by the engine (b381_dev_alloc / b381_h2d / b381_d2h) ----------
     def dev_empty(self, nbytes):
         return DevBuf(self, nbytes)

@@ -13,6 +13,7 @@
 #include "agg.cuh"
 #include "codec.cuh"
 #include "hash.cuh"
+#include "swu.cuh"
 #include "vm.cuh"
 #include "vm_programs.inc"
 #include <stdlib.h>
@@ -763,26 +764,45 @@ int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *
     return b381_pairing_product_is_one_dev(ctx, (b381_g1_affine *)P, (b381_g2_affine *)Q, 2 * nattest, (uint32_t *)off, nattest, d_ok);
 }
 
-// ---- VerifyWithDomain from wire bytes: deserialise + hash + 2-pair check per item, all on the device ----------------------
-int b381_verify_with_domain_batch_dev(b381_ctx *ctx, const uint8_t *d_pub48, const uint8_t *d_msg32, const uint8_t *d_domain8,
-                                      size_t domain_stride, const uint8_t *d_sig96, size_t n, uint8_t *d_ok) {
-    if (!ctx || domain_stride > 1 || n > 0x7FFFFFF0u || (n && (!d_pub48 || !d_msg32 || !d_domain8 || !d_sig96 || !d_ok))) return B381_ERR_ARG;
+// ---- Verify / VerifyWithDomain from wire bytes: deserialise + hash + 2-pair check per item, all on the device -----------------
+}   // extern "C"
+enum { WIRE_G1PUBS_DOMAIN = 0, WIRE_G1PUBS = 1, WIRE_G2PUBS = 2 };
+// mode WIRE_G1PUBS_DOMAIN: msg = n x 32 bytes, aux = domain (8 bytes x (stride ? n : 1)); otherwise msg = packed messages and
+// aux = n + 1 u64 offsets.  g1pubs: keys 48 B / signatures 96 B; g2pubs: keys 96 B / signatures 48 B.
+static int verify_wire_dev(b381_ctx *ctx, int mode, const uint8_t *d_pub, const uint8_t *d_msg, const void *d_aux, size_t domain_stride,
+                           const uint8_t *d_sig, size_t n, uint8_t *d_ok) {
+    if (!ctx || domain_stride > 1 || n > 0x7FFFFFF0u || (n && (!d_pub || !d_msg || !d_aux || !d_sig || !d_ok))) return B381_ERR_ARG;
     if (!n) return B381_OK;
+    const bool g2p = mode == WIRE_G2PUBS;
+    const size_t pub_pod = g2p ? sizeof(b381_g2_affine) : sizeof(b381_g1_affine), sig_pod = g2p ? sizeof(b381_g1_affine) : sizeof(b381_g2_affine);
     void *pub, *sig, *H, *st, *P, *Q, *off;
-    int rc = scratch_get(ctx, 15, n * sizeof(b381_g1_affine), &pub); if (rc) return rc;
-    rc = scratch_get(ctx, 16, n * sizeof(b381_g2_affine), &sig); if (rc) return rc;
-    rc = scratch_get(ctx, 17, n * sizeof(b381_g2_affine), &H); if (rc) return rc;
+    int rc = scratch_get(ctx, 15, n * pub_pod, &pub); if (rc) return rc;
+    rc = scratch_get(ctx, 16, n * sig_pod, &sig); if (rc) return rc;
+    rc = scratch_get(ctx, 17, n * sig_pod, &H); if (rc) return rc;          // the message point lives in the signature's group
     rc = scratch_get(ctx, 18, 3 * n, &st); if (rc) return rc;
     rc = scratch_get(ctx, 2, 2 * n * sizeof(b381_g1_affine), &P); if (rc) return rc;
     rc = scratch_get(ctx, 3, 2 * n * sizeof(b381_g2_affine), &Q); if (rc) return rc;
     rc = scratch_get(ctx, 6, (n + 1) * sizeof(uint32_t), &off); if (rc) return rc;
     uint8_t *st_pub = (uint8_t *)st, *st_sig = st_pub + n, *valid = st_pub + 2 * n;
-    rc = b381_g1_decompress_batch_dev(ctx, d_pub48, n, 1, (b381_g1_affine *)pub, st_pub); if (rc) return rc;
-    rc = b381_g2_decompress_batch_dev(ctx, d_sig96, n, 1, (b381_g2_affine *)sig, st_sig); if (rc) return rc;
-    rc = b381_hash_g2_with_domain_batch_dev(ctx, d_msg32, d_domain8, domain_stride, n, (b381_g2_affine *)H); if (rc) return rc;
-    k_verify_pairs<<<grid_for(n, 128), 128, 0, ctx->stream>>>((const g1_affine_pod *)pub, st_pub, (const g2_affine_pod *)sig, st_sig,
-                                                              (const g2_affine_pod *)H, n, (g1_affine_pod *)P, (g2_affine_pod *)Q,
-                                                              (uint32_t *)off, valid);
+    if (!g2p) {
+        rc = b381_g1_decompress_batch_dev(ctx, d_pub, n, 1, (b381_g1_affine *)pub, st_pub); if (rc) return rc;
+        rc = b381_g2_decompress_batch_dev(ctx, d_sig, n, 1, (b381_g2_affine *)sig, st_sig); if (rc) return rc;
+        if (mode == WIRE_G1PUBS_DOMAIN)
+            rc = b381_hash_g2_with_domain_batch_dev(ctx, d_msg, (const uint8_t *)d_aux, domain_stride, n, (b381_g2_affine *)H);
+        else
+            rc = b381_hash_g2_batch_dev(ctx, d_msg, (const uint64_t *)d_aux, n, (b381_g2_affine *)H);
+        if (rc) return rc;
+        k_verify_pairs<<<grid_for(n, 128), 128, 0, ctx->stream>>>((const g1_affine_pod *)pub, st_pub, (const g2_affine_pod *)sig, st_sig,
+                                                                  (const g2_affine_pod *)H, n, (g1_affine_pod *)P, (g2_affine_pod *)Q,
+                                                                  (uint32_t *)off, valid);
+    } else {
+        rc = b381_g2_decompress_batch_dev(ctx, d_pub, n, 1, (b381_g2_affine *)pub, st_pub); if (rc) return rc;
+        rc = b381_g1_decompress_batch_dev(ctx, d_sig, n, 1, (b381_g1_affine *)sig, st_sig); if (rc) return rc;
+        rc = b381_hash_g1_batch_dev(ctx, d_msg, (const uint64_t *)d_aux, n, (b381_g1_affine *)H); if (rc) return rc;
+        k_verify_pairs_g2pubs<<<grid_for(n, 128), 128, 0, ctx->stream>>>((const g2_affine_pod *)pub, st_pub, (const g1_affine_pod *)sig, st_sig,
+                                                                         (const g1_affine_pod *)H, n, (g1_affine_pod *)P, (g2_affine_pod *)Q,
+                                                                         (uint32_t *)off, valid);
+    }
     ctx->launches++;
     CK(cudaGetLastError());
     rc = b381_pairing_product_is_one_dev(ctx, (b381_g1_affine *)P, (b381_g2_affine *)Q, 2 * n, (uint32_t *)off, n, d_ok);
@@ -792,24 +812,89 @@ int b381_verify_with_domain_batch_dev(b381_ctx *ctx, const uint8_t *d_pub48, con
     CK(cudaGetLastError());
     return B381_OK;
 }
-int b381_verify_with_domain_batch(b381_ctx *ctx, const uint8_t *pub48, const uint8_t *msg32, const uint8_t *domain8, size_t domain_stride,
-                                  const uint8_t *sig96, size_t n, uint8_t *ok) {
-    if (!ctx || domain_stride > 1 || (n && (!pub48 || !msg32 || !domain8 || !sig96 || !ok))) return B381_ERR_ARG;
+static int verify_wire_host(b381_ctx *ctx, int mode, const uint8_t *pub, const uint8_t *msg, size_t msg_bytes, const void *aux, size_t aux_bytes,
+                            size_t domain_stride, const uint8_t *sig, size_t n, uint8_t *ok) {
+    if (!ctx || domain_stride > 1 || (n && (!pub || !msg || !aux || !sig || !ok))) return B381_ERR_ARG;
     if (!n) return B381_OK;
     CK(cudaSetDevice(ctx->device));
+    const size_t pb = mode == WIRE_G2PUBS ? 96 : 48, sb = mode == WIRE_G2PUBS ? 48 : 96;
     void *in, *dok;
-    size_t nd = domain_stride ? n : 1;
-    int rc = scratch_get(ctx, 19, n * (48 + 32 + 96) + nd * 8, &in); if (rc) return rc;
+    size_t aux_off = (n * (pb + sb) + msg_bytes + 15) & ~(size_t)15;
+    int rc = scratch_get(ctx, 19, aux_off + aux_bytes, &in); if (rc) return rc;
     rc = scratch_get(ctx, 20, n, &dok); if (rc) return rc;
-    uint8_t *dp = (uint8_t *)in, *dm = dp + 48 * n, *ds = dm + 32 * n, *dd = ds + 96 * n;
-    CK(cudaMemcpyAsync(dp, pub48, 48 * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(dm, msg32, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ds, sig96, 96 * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(dd, domain8, 8 * nd, cudaMemcpyHostToDevice, ctx->stream));
-    rc = b381_verify_with_domain_batch_dev(ctx, dp, dm, dd, domain_stride, ds, n, (uint8_t *)dok); if (rc) return rc;
+    uint8_t *dp = (uint8_t *)in, *ds = dp + pb * n, *dm = ds + sb * n, *da = dp + aux_off;
+    CK(cudaMemcpyAsync(dp, pub, pb * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ds, sig, sb * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (msg_bytes) CK(cudaMemcpyAsync(dm, msg, msg_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(da, aux, aux_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = verify_wire_dev(ctx, mode, dp, dm, da, domain_stride, ds, n, (uint8_t *)dok); if (rc) return rc;
     CK(cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return B381_OK;
+}
+template <class S, class APOD>
+static int hash_curve_dev(b381_ctx *ctx, const uint8_t *d_msgs, const uint64_t *d_off, size_t n, APOD *d_out) {
+    if (!ctx || (n && (!d_msgs || !d_off || !d_out))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    k_hash_to_curve<S><<<grid_for(n, 64), 64, 0, ctx->stream>>>(d_msgs, d_off, n, (typename S::APOD *)d_out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+template <class S, class APOD>
+static int hash_curve_host(b381_ctx *ctx, const uint8_t *msgs, const uint64_t *off, size_t n, APOD *out) {
+    if (!ctx || (n && (!msgs || !off || !out))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    if (off[0] != 0) return B381_ERR_ARG;
+    for (size_t i = 0; i < n; i++) if (off[i] > off[i + 1]) return B381_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    void *dm, *doff, *dout;
+    size_t mb = off[n];
+    int rc = scratch_get(ctx, 12, mb + 16, &dm); if (rc) return rc;
+    rc = scratch_get(ctx, 13, n * sizeof(APOD), &dout); if (rc) return rc;
+    rc = scratch_get(ctx, 14, (n + 1) * sizeof(uint64_t), &doff); if (rc) return rc;
+    if (mb) CK(cudaMemcpyAsync(dm, msgs, mb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(doff, off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    rc = hash_curve_dev<S, APOD>(ctx, (const uint8_t *)dm, (const uint64_t *)doff, n, (APOD *)dout); if (rc) return rc;
+    CK(cudaMemcpyAsync(out, dout, n * sizeof(APOD), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B381_OK;
+}
+static int check_offsets(const uint64_t *off, size_t n) {
+    if (!off || off[0] != 0) return B381_ERR_ARG;
+    for (size_t i = 0; i < n; i++) if (off[i] > off[i + 1]) return B381_ERR_ARG;
+    return B381_OK;
+}
+extern "C" {
+int b381_hash_g1_batch(b381_ctx *ctx, const uint8_t *msgs, const uint64_t *msg_off, size_t n, b381_g1_affine *out) { return hash_curve_host<G1Swu>(ctx, msgs, msg_off, n, out); }
+int b381_hash_g1_batch_dev(b381_ctx *ctx, const uint8_t *d_msgs, const uint64_t *d_msg_off, size_t n, b381_g1_affine *d_out) { return hash_curve_dev<G1Swu>(ctx, d_msgs, d_msg_off, n, d_out); }
+int b381_hash_g2_batch(b381_ctx *ctx, const uint8_t *msgs, const uint64_t *msg_off, size_t n, b381_g2_affine *out) { return hash_curve_host<G2Swu>(ctx, msgs, msg_off, n, out); }
+int b381_hash_g2_batch_dev(b381_ctx *ctx, const uint8_t *d_msgs, const uint64_t *d_msg_off, size_t n, b381_g2_affine *d_out) { return hash_curve_dev<G2Swu>(ctx, d_msgs, d_msg_off, n, d_out); }
+int b381_verify_with_domain_batch_dev(b381_ctx *ctx, const uint8_t *d_pub48, const uint8_t *d_msg32, const uint8_t *d_domain8,
+                                      size_t domain_stride, const uint8_t *d_sig96, size_t n, uint8_t *d_ok) {
+    return verify_wire_dev(ctx, WIRE_G1PUBS_DOMAIN, d_pub48, d_msg32, d_domain8, domain_stride, d_sig96, n, d_ok);
+}
+int b381_verify_with_domain_batch(b381_ctx *ctx, const uint8_t *pub48, const uint8_t *msg32, const uint8_t *domain8, size_t domain_stride,
+                                  const uint8_t *sig96, size_t n, uint8_t *ok) {
+    return verify_wire_host(ctx, WIRE_G1PUBS_DOMAIN, pub48, msg32, 32 * n, domain8, 8 * (domain_stride ? n : 1), domain_stride, sig96, n, ok);
+}
+int b381_g1pubs_verify_batch_dev(b381_ctx *ctx, const uint8_t *d_pub48, const uint8_t *d_msgs, const uint64_t *d_msg_off, const uint8_t *d_sig96,
+                                 size_t n, uint8_t *d_ok) {
+    return verify_wire_dev(ctx, WIRE_G1PUBS, d_pub48, d_msgs, d_msg_off, 0, d_sig96, n, d_ok);
+}
+int b381_g1pubs_verify_batch(b381_ctx *ctx, const uint8_t *pub48, const uint8_t *msgs, const uint64_t *msg_off, const uint8_t *sig96, size_t n,
+                             uint8_t *ok) {
+    if (n && check_offsets(msg_off, n)) return B381_ERR_ARG;
+    return verify_wire_host(ctx, WIRE_G1PUBS, pub48, msgs, n ? msg_off[n] : 0, msg_off, (n + 1) * sizeof(uint64_t), 0, sig96, n, ok);
+}
+int b381_g2pubs_verify_batch_dev(b381_ctx *ctx, const uint8_t *d_pub96, const uint8_t *d_msgs, const uint64_t *d_msg_off, const uint8_t *d_sig48,
+                                 size_t n, uint8_t *d_ok) {
+    return verify_wire_dev(ctx, WIRE_G2PUBS, d_pub96, d_msgs, d_msg_off, 0, d_sig48, n, d_ok);
+}
+int b381_g2pubs_verify_batch(b381_ctx *ctx, const uint8_t *pub96, const uint8_t *msgs, const uint64_t *msg_off, const uint8_t *sig48, size_t n,
+                             uint8_t *ok) {
+    if (n && check_offsets(msg_off, n)) return B381_ERR_ARG;
+    return verify_wire_host(ctx, WIRE_G2PUBS, pub96, msgs, n ? msg_off[n] : 0, msg_off, (n + 1) * sizeof(uint64_t), 0, sig48, n, ok);
 }
 
 // ---- aggregation, host buffers -------------------------------------------------------------------

@@ -169,6 +169,65 @@ func VerifyWithDomainWire(pubs [][48]byte, msgs [][32]byte, domain [8]byte, sigs
 	return out
 }
 
+// packMessages lays variable-length messages back to back with an offsets array (n + 1 entries).
+func packMessages(msgs [][]byte) ([]byte, []uint64) {
+	off := make([]uint64, len(msgs)+1)
+	total := 0
+	for i, m := range msgs {
+		total += len(m)
+		off[i+1] = uint64(total)
+	}
+	buf := make([]byte, 0, total+1)
+	for _, m := range msgs {
+		buf = append(buf, m...)
+	}
+	return append(buf, 0), off
+}
+
+// HashG1Batch / HashG2Batch: HashG1 (hash.go:320-331) / HashG2 (hash.go:404-411) of every message.
+func HashG1Batch(msgs [][]byte) []G1Affine {
+	out := make([]G1Affine, len(msgs))
+	if len(msgs) > 0 {
+		buf, off := packMessages(msgs)
+		must(C.b381_hash_g1_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&buf[0])), (*C.uint64_t)(unsafe.Pointer(&off[0])),
+			C.size_t(len(msgs)), (*C.b381_g1_affine)(unsafe.Pointer(&out[0]))))
+	}
+	return out
+}
+
+func HashG2Batch(msgs [][]byte) []G2Affine {
+	out := make([]G2Affine, len(msgs))
+	if len(msgs) > 0 {
+		buf, off := packMessages(msgs)
+		must(C.b381_hash_g2_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&buf[0])), (*C.uint64_t)(unsafe.Pointer(&off[0])),
+			C.size_t(len(msgs)), (*C.b381_g2_affine)(unsafe.Pointer(&out[0]))))
+	}
+	return out
+}
+
+// VerifyWire: g1pubs.Verify (g2pubs = false: 48-byte keys, 96-byte signatures, g1pubs/bls.go:165-168) or g2pubs.Verify
+// (g2pubs = true: 96-byte keys, 48-byte signatures, g2pubs/bls.go:159-162) for n wire-format triples on the device.
+func VerifyWire(g2pubs bool, pubs []byte, msgs [][]byte, sigs []byte) []bool {
+	n := len(msgs)
+	ok8 := make([]uint8, n)
+	out := make([]bool, n)
+	if n == 0 {
+		return out
+	}
+	buf, off := packMessages(msgs)
+	if g2pubs {
+		must(C.b381_g2pubs_verify_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&pubs[0])), (*C.uint8_t)(unsafe.Pointer(&buf[0])),
+			(*C.uint64_t)(unsafe.Pointer(&off[0])), (*C.uint8_t)(unsafe.Pointer(&sigs[0])), C.size_t(n), (*C.uint8_t)(unsafe.Pointer(&ok8[0]))))
+	} else {
+		must(C.b381_g1pubs_verify_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&pubs[0])), (*C.uint8_t)(unsafe.Pointer(&buf[0])),
+			(*C.uint64_t)(unsafe.Pointer(&off[0])), (*C.uint8_t)(unsafe.Pointer(&sigs[0])), C.size_t(n), (*C.uint8_t)(unsafe.Pointer(&ok8[0]))))
+	}
+	for i, v := range ok8 {
+		out[i] = v != 0
+	}
+	return out
+}
+
 func must(rc C.int) {
 	if rc != C.B381_OK {
 		panic(C.GoString(C.b381_last_error(ctx())))

@@ -118,3 +118,15 @@ func bytesEqual(a, b []byte) bool {
 	}
 	return true
 }
+
+// VerifyBatch verifies n independent wire-format (public key, message, signature) triples: ok[i] ==
+// Verify(msgs[i], DeserializePublicKey(pubs[i]), DeserializeSignature(sigs[i])) (g1pubs/bls.go:38-58,91-111,165-168).
+func VerifyBatch(pubs [][48]byte, msgs [][]byte, sigs [][96]byte) []bool {
+	p := make([]byte, 0, 48*len(pubs))
+	s := make([]byte, 0, 96*len(sigs))
+	for i := range pubs {
+		p = append(p, pubs[i][:]...)
+		s = append(s, sigs[i][:]...)
+	}
+	return bls.VerifyWire(false, p, msgs, s)
+}

@@ -44,3 +44,15 @@ func VerifyBatch(msgs [][]byte, pubs []*PublicKey, sigs []*Signature) []bool {
 	}
 	return bls.PairingProductsAreOne(p, q, off)
 }
+
+// VerifyBatch verifies n independent wire-format (public key, message, signature) triples: ok[i] ==
+// Verify(msgs[i], DeserializePublicKey(pubs[i]), DeserializeSignature(sigs[i])) (g2pubs/bls.go:33-53,91-111,159-162).
+func VerifyBatch(pubs [][96]byte, msgs [][]byte, sigs [][48]byte) []bool {
+	p := make([]byte, 0, 96*len(pubs))
+	s := make([]byte, 0, 48*len(sigs))
+	for i := range pubs {
+		p = append(p, pubs[i][:]...)
+		s = append(s, sigs[i][:]...)
+	}
+	return bls.VerifyWire(true, p, msgs, s)
+}

@@ -193,6 +193,27 @@ int b381_verify_with_domain_batch_dev(b381_ctx *ctx, const uint8_t *d_pub48, con
                                       const uint8_t *d_domain8, size_t domain_stride, const uint8_t *d_sig96, size_t n,
                                       uint8_t *d_ok);
 
+/* HashG1 (hash.go:320-331) / HashG2 (hash.go:404-411) over a batch of variable-length messages packed back to back:
+ * message i is msgs[msg_off[i] .. msg_off[i+1]), msg_off has n + 1 entries starting at 0.  hash_to_field (hp / hp2,
+ * hash.go:41-113), the simplified SWU maps (g1.go:628-714, g2.go:933-1031), iso11 / iso3 and ClearH / clearH2
+ * (hash.go:185-203,282-309,341-389) all run on the device.  These are the message points of g2pubs.Verify / Sign
+ * (HashG1) and g1pubs.Verify / Sign / VerifyAggregate (HashG2). */
+int b381_hash_g1_batch(b381_ctx *ctx, const uint8_t *msgs, const uint64_t *msg_off, size_t n, b381_g1_affine *out);
+int b381_hash_g1_batch_dev(b381_ctx *ctx, const uint8_t *d_msgs, const uint64_t *d_msg_off, size_t n, b381_g1_affine *d_out);
+int b381_hash_g2_batch(b381_ctx *ctx, const uint8_t *msgs, const uint64_t *msg_off, size_t n, b381_g2_affine *out);
+int b381_hash_g2_batch_dev(b381_ctx *ctx, const uint8_t *d_msgs, const uint64_t *d_msg_off, size_t n, b381_g2_affine *d_out);
+/* g1pubs.Verify (g1pubs/bls.go:165-168) and g2pubs.Verify (g2pubs/bls.go:159-162) for n independent wire-format
+ * triples: like b381_verify_with_domain_batch, with HashG2(msg) / HashG1(msg) as the message point.  g1pubs: 48-byte
+ * keys, 96-byte signatures; g2pubs: 96-byte keys, 48-byte signatures. */
+int b381_g1pubs_verify_batch(b381_ctx *ctx, const uint8_t *pub48, const uint8_t *msgs, const uint64_t *msg_off,
+                             const uint8_t *sig96, size_t n, uint8_t *ok);
+int b381_g1pubs_verify_batch_dev(b381_ctx *ctx, const uint8_t *d_pub48, const uint8_t *d_msgs, const uint64_t *d_msg_off,
+                                 const uint8_t *d_sig96, size_t n, uint8_t *d_ok);
+int b381_g2pubs_verify_batch(b381_ctx *ctx, const uint8_t *pub96, const uint8_t *msgs, const uint64_t *msg_off,
+                             const uint8_t *sig48, size_t n, uint8_t *ok);
+int b381_g2pubs_verify_batch_dev(b381_ctx *ctx, const uint8_t *d_pub96, const uint8_t *d_msgs, const uint64_t *d_msg_off,
+                                 const uint8_t *d_sig48, size_t n, uint8_t *d_ok);
+
 /* ---- measurement -------------------------------------------------------------------------------- */
 /* Integer-pipe roofline probe: launches blocks x threads threads that each issue iters * 8
  * independent IMAD.WIDE.U32 (the 32x32->64 multiply-accumulate an Fq multiplication is made of).

@@ -55,3 +55,41 @@ def test_hash_g2_with_domain_kat_and_host(emu, orc, kats):
     out1 = np.zeros(len(msgs), dtype=L.G2_AFFINE)
     emu.emu_hash_g2_with_domain(_p(m), _p(d), ctypes.c_size_t(0), ctypes.c_size_t(len(msgs)), _p(out1))
     assert out1.tobytes() == expected_hashes(msgs, [doms[0]] * len(msgs)).tobytes()
+
+
+def swu_messages():
+    rng = np.random.RandomState(8)
+    return [b"the message to be signed", b"", b"a", bytes(range(54)), bytes(range(55)), bytes(range(56)), bytes(range(64)),
+            rng.bytes(119), rng.bytes(200)]
+
+
+def pack(msgs):
+    off = np.zeros(len(msgs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(m) for m in msgs])
+    raw = np.frombuffer(b"".join(msgs) + b"\0", np.uint8).copy()
+    return raw, off
+
+
+def test_sha256_prefixed(emu):
+    for m in swu_messages():
+        raw = np.frombuffer(m + b"\0", np.uint8).copy()
+        dg = np.zeros(8, np.uint32)
+        emu.emu_sha256_prefixed(ctypes.c_uint8(1), _p(raw), ctypes.c_size_t(len(m)), _p(dg))
+        assert b"".join(int(w).to_bytes(4, "big") for w in dg) == hashlib.sha256(b"\x01" + m).digest()
+
+
+def test_hash_g1_g2_kats_and_host(emu, orc, kats):
+    """HashG1 / HashG2 (hash.go:320-331,404-411): the reference's known answers (hash_test.go:12-26,48-62) and the
+    pinned host restatement on messages of every padding class"""
+    msgs = swu_messages()
+    raw, off = pack(msgs)
+    o1 = np.zeros(len(msgs), dtype=L.G1_AFFINE); o2 = np.zeros(len(msgs), dtype=L.G2_AFFINE)
+    emu.emu_hash_g1(_p(raw), _p(off), ctypes.c_size_t(len(msgs)), _p(o1))
+    emu.emu_hash_g2(_p(raw), _p(off), ctypes.c_size_t(len(msgs)), _p(o2))
+    h = kats["hash"]
+    assert msgs[0].decode() == h["message"]
+    assert [hex(L.fp_to_int(o1["x"][0])), hex(L.fp_to_int(o1["y"][0]))] == h["hash_g1"]
+    assert o1.tobytes() == hg.g1_points([hm.hash_g1(m) for m in msgs]).tobytes()
+    assert o2.tobytes() == hg.g2_points([hm.hash_g2(m) for m in msgs]).tobytes()
+    for i in range(len(msgs)):
+        assert orc.g1.in_subgroup(o1[i:i + 1]) and orc.g2.in_subgroup(o2[i:i + 1])

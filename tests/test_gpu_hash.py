@@ -43,3 +43,30 @@ def test_hash_batch_properties(ctx, orc):
     # the decompression kernel agrees that they are valid signatures-to-be: compress -> checked decompress round trip
     back, st = ctx.g2_decompress_batch(ctx.g2_compress_batch(out).tobytes(), check_subgroup=True)
     assert not st.any() and back.tobytes() == out.tobytes()
+
+
+def test_hash_g1_g2_match_reference(ctx, orc, kats):
+    """b381_hash_g1_batch / b381_hash_g2_batch: HashG1 / HashG2 (hash.go:320-331,404-411) against the reference's known
+    answers (hash_test.go:12-26,48-62) and the pinned host restatement, messages of every SHA-256 padding class"""
+    from test_emu_hash import swu_messages
+    from bls_b200 import hostgen as hg, hostmath as hm
+    msgs = swu_messages()
+    o1 = ctx.hash_g1_batch(msgs); o2 = ctx.hash_g2_batch(msgs)
+    h = kats["hash"]
+    assert [hex(L.fp_to_int(o1["x"][0])), hex(L.fp_to_int(o1["y"][0]))] == h["hash_g1"]
+    assert o1.tobytes() == hg.g1_points([hm.hash_g1(m) for m in msgs]).tobytes()
+    assert o2.tobytes() == hg.g2_points([hm.hash_g2(m) for m in msgs]).tobytes()
+
+
+def test_hash_to_curve_batch_properties(ctx, orc):
+    rng = np.random.RandomState(9)
+    n = 2048
+    msgs = [rng.bytes(int(rng.randint(0, 150))) for _ in range(n // 2)]
+    msgs = msgs + msgs
+    o1 = ctx.hash_g1_batch(msgs); o2 = ctx.hash_g2_batch(msgs)
+    assert o1[:n // 2].tobytes() == o1[n // 2:].tobytes() and o2[:n // 2].tobytes() == o2[n // 2:].tobytes()
+    b1, s1 = ctx.g1_decompress_batch(ctx.g1_compress_batch(o1).tobytes(), check_subgroup=True)
+    b2, s2 = ctx.g2_decompress_batch(ctx.g2_compress_batch(o2).tobytes(), check_subgroup=True)
+    assert not s1.any() and not s2.any() and b1.tobytes() == o1.tobytes() and b2.tobytes() == o2.tobytes()
+    for i in range(0, n // 2, 211):
+        assert orc.g1.in_subgroup(o1[i:i + 1]) and orc.g2.in_subgroup(o2[i:i + 1])

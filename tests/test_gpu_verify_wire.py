@@ -82,3 +82,38 @@ def test_batch_scale_by_construction(ctx):
     # per-item domains (stride 1) give the same verdicts when every item carries the same domain
     ok1 = ctx.verify_with_domain_batch(pubs[:512], msgs[:512], np.tile(np.frombuffer(domain, np.uint8), 512), sigs[:512])
     assert ok1.tolist() == expect[:512].tolist()
+
+
+def make_plain_batch(ctx, n, seed, g2pubs=False):
+    rng = np.random.RandomState(seed)
+    sk = np.array([L.int_to_limbs(int.from_bytes(rng.bytes(31), "big") + 1, 4) for _ in range(n)], np.uint64)
+    msgs = [rng.bytes(int(rng.randint(1, 100))) for _ in range(n)]
+    if not g2pubs:      # g1pubs: keys in G1, signatures in G2 = sk * HashG2(m)
+        pubs = ctx.g1_compress_batch(ctx.g1_mul_batch(hg.g1_mul(1), sk))
+        sigs = ctx.g2_compress_batch(ctx.g2_mul_batch(ctx.hash_g2_batch(msgs), sk))
+    else:               # g2pubs: keys in G2, signatures in G1 = sk * HashG1(m)
+        pubs = ctx.g2_compress_batch(ctx.g2_mul_batch(hg.g2_mul(1), sk))
+        sigs = ctx.g1_compress_batch(ctx.g1_mul_batch(ctx.hash_g1_batch(msgs), sk))
+    return msgs, pubs, sigs
+
+
+@pytest.mark.parametrize("pkg", ["g1pubs", "g2pubs"])
+def test_plain_verify_against_host_mirror(ctx, pkg):
+    """b381_g1pubs_verify_batch / b381_g2pubs_verify_batch against the host mirror of g1pubs.Verify (g1pubs/bls.go:165-168)
+    and g2pubs.Verify (g2pubs/bls.go:159-162), plus planted failures at batch scale"""
+    import importlib
+    mod = importlib.import_module("bls_b200." + pkg)
+    from bls_b200 import g1pubs
+    g1pubs.set_engine(ctx)
+    n = 1024
+    msgs, pubs, sigs = make_plain_batch(ctx, n, 21, g2pubs=pkg == "g2pubs")
+    expect = np.ones(n, np.uint8)
+    for i in range(5, n, 37):
+        msgs[i] = msgs[i] + b"!"; expect[i] = 0
+    sigs[2], sigs[3] = sigs[3].copy(), sigs[2].copy(); expect[2] = expect[3] = 0
+    pubs[8] = pubs[9]; expect[8] = 0
+    ok = (ctx.g1pubs_verify_batch if pkg == "g1pubs" else ctx.g2pubs_verify_batch)(pubs, msgs, sigs)
+    assert ok.tolist() == expect.tolist()
+    for i in (0, 2, 5, 8, 11):
+        pk = mod.DeserializePublicKey(pubs[i].tobytes()); sg = mod.DeserializeSignature(sigs[i].tobytes())
+        assert mod.Verify(msgs[i], pk, sg) == bool(expect[i])

@@ -69,6 +69,16 @@ ctx.dev("b381_g2_compress_batch_dev", dSig.data_ptr(), N, dSigC.data_ptr())
 res["verify_with_domain_wire_ms"] = timed(lambda: ctx.dev("b381_verify_with_domain_batch_dev", dPubC.data_ptr(), dM.data_ptr(), dD.data_ptr(),
                                                              ctypes.c_size_t(0), dSigC.data_ptr(), N, dOk.data_ptr()), reps=2)
 assert bool(dOk.all().item()), "valid signatures must verify"
+# SWU hashing and the plain Verify from wire bytes (64-byte messages)
+ml = 64
+dMsg = up(rng.randint(0, 256, (n, ml), dtype=np.uint8)); dOff = up((np.arange(n + 1, dtype=np.uint64) * ml))
+res["hash_g1_ms"] = timed(lambda: ctx.dev("b381_hash_g1_batch_dev", dMsg.data_ptr(), dOff.data_ptr(), N, dO1.data_ptr()))
+res["hash_g2_ms"] = timed(lambda: ctx.dev("b381_hash_g2_batch_dev", dMsg.data_ptr(), dOff.data_ptr(), N, dH.data_ptr()))
+ctx.dev("b381_g2_mul_batch_dev", dH.data_ptr(), one, dK.data_ptr(), one, N, dSig.data_ptr())
+ctx.dev("b381_g2_compress_batch_dev", dSig.data_ptr(), N, dSigC.data_ptr())
+res["g1pubs_verify_wire_ms"] = timed(lambda: ctx.dev("b381_g1pubs_verify_batch_dev", dPubC.data_ptr(), dMsg.data_ptr(), dOff.data_ptr(),
+                                                        dSigC.data_ptr(), N, dOk.data_ptr()), reps=2)
+assert bool(dOk.all().item()), "valid signatures must verify (g1pubs.Verify)"
 for k in list(res):
     if k.endswith("_ms"):
         res[k.replace("_ms", "_per_s")] = n / (res[k] * 1e-3)

@@ -64,18 +64,46 @@ __global__ void __launch_bounds__(PAIRING_BLOCK, PAIRING_MIN_BLOCKS) k_final_exp
 // prod[g] = product of ml[group_off[g] .. group_off[g+1])   (the shared accumulator f of pairing.go:40-69)
 __global__ void __launch_bounds__(PAIRING_BLOCK, PAIRING_MIN_BLOCKS) k_group_product(const uint64_t *__restrict__ ml,
                                                                    const uint32_t *__restrict__ group_off,
-                                                                   size_t ngroups, uint64_t *__restrict__ prod) {
+                                                                   size_t ngroups, uint64_t *__restrict__ prod, int first_only) {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= ngroups) return;
     fp12 acc, t;
     fp12_set_one(&acc);
     uint32_t lo = group_off[g], hi = group_off[g + 1];
+    if (first_only && hi > lo) hi = lo + 1;        // k_group_tree has already folded the group into its first element
     for (uint32_t i = lo; i < hi; i++) {
         fp12_load_u64(&t, ml + 72 * (size_t)i);
         if (i == lo) fp12_copy(&acc, &t);
         else fp12_mul(&acc, &acc, &t);
     }
     fp12_store_u64(prod + 72 * g, &acc);
+}
+
+// Large groups (VerifyAggregate with many messages, g1pubs/bls.go:252-282; random-linear-combination batches): the product
+// of a group is formed as a tree over its Miller values instead of one serial chain.  Level l: element at position pos of
+// its group absorbs the element at pos + 2^l when pos is a multiple of 2^(l+1); after ceil(log2(size)) levels the first
+// element of the group holds the product.  *maxsize (largest group) lets surplus launches exit at once.
+__global__ void k_group_maxsize(const uint32_t *__restrict__ group_off, size_t ngroups, uint32_t *__restrict__ maxsize) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < ngroups) atomicMax(maxsize, group_off[g + 1] - group_off[g]);
+}
+__global__ void __launch_bounds__(PAIRING_BLOCK, PAIRING_MIN_BLOCKS) k_group_tree(uint64_t *__restrict__ ml, const uint32_t *__restrict__ group_off,
+                                                                                  size_t ngroups, size_t npairs, int level,
+                                                                                  const uint32_t *__restrict__ maxsize) {
+    if ((1u << level) >= *maxsize) return;
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= npairs) return;
+    size_t lo = 0, hi = ngroups;                   // largest g with group_off[g] <= e
+    while (hi - lo > 1) { size_t mid = (lo + hi) >> 1; if (group_off[mid] <= e) lo = mid; else hi = mid; }
+    uint32_t start = group_off[lo], end = group_off[lo + 1];
+    if (e >= end) return;                          // e lies in an empty tail
+    uint32_t pos = (uint32_t)e - start, step = 1u << level;
+    if ((pos & (2 * step - 1)) || e + step >= end) return;
+    fp12 a, b;
+    fp12_load_u64(&a, ml + 72 * e);
+    fp12_load_u64(&b, ml + 72 * (e + step));
+    fp12_mul(&a, &a, &b);
+    fp12_store_u64(ml + 72 * e, &a);
 }
 
 // ok[g] = FinalExponentiation(prod[g]) == 1   (pairing.go:143-146)
@@ -551,8 +579,22 @@ int b381_pairing_product_is_one_dev(b381_ctx *ctx, const b381_g1_affine *d_p, co
     if (rc) return rc;
     rc = b381_miller_loop_batch_dev(ctx, d_p, d_q, npairs, (b381_fp12 *)ml);
     if (rc) return rc;
+    int tree = npairs > 2 * ngroups;               // some group has more than two factors: fold groups as trees
+    if (tree) {
+        void *mx;
+        rc = scratch_get(ctx, 21, sizeof(uint32_t), &mx);
+        if (rc) return rc;
+        CK(cudaMemsetAsync(mx, 0, sizeof(uint32_t), ctx->stream));
+        k_group_maxsize<<<grid_for(ngroups, 256), 256, 0, ctx->stream>>>(d_group_off, ngroups, (uint32_t *)mx);
+        ctx->launches++;
+        for (int level = 0; ((size_t)1 << level) < npairs; level++) {
+            k_group_tree<<<grid_for(npairs, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>((uint64_t *)ml, d_group_off, ngroups, npairs,
+                                                                                            level, (const uint32_t *)mx);
+            ctx->launches++;
+        }
+    }
     k_group_product<<<grid_for(ngroups, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>(
-        (const uint64_t *)ml, d_group_off, ngroups, (uint64_t *)prod);
+        (const uint64_t *)ml, d_group_off, ngroups, (uint64_t *)prod, tree);
     ctx->launches++;
     if (vm_for(ctx, ngroups)) {          // few groups: the warp-cooperative final exponentiation has 3x lower latency
         rc = b381_final_exp_batch_dev(ctx, (const b381_fp12 *)prod, ngroups, (b381_fp12 *)prod, d_ok);

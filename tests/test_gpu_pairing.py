@@ -111,6 +111,34 @@ def test_product_ragged_groups(ctx, orc):
     assert orc.pairing_product_is_one(P, Q, off).tolist() == [1, 1, 1, 0]
 
 
+def test_product_large_groups_tree(ctx, orc):
+    """VerifyAggregate-shaped products (g1pubs/bls.go:252-282): groups of hundreds of pairs are folded as trees
+    (k_group_tree).  prod e((s+id)G1, (s'+id')G2) * e(-E G1, G2) == 1 with E = sum (s+id)(s'+id'), sizes 1..301 mixed
+    with empty and two-pair groups; one group is broken on purpose; a small case is compared with the oracle."""
+    s1, d1, s2, d2 = 0x1234567, 0x89, 0xabcdef1, 0x35
+    sizes = [301, 0, 2, 64, 65, 1, 127, 2, 33]
+    ps, qs, off, expect = [], [], [0], []
+    for gi, m in enumerate(sizes):
+        if m == 0:
+            expect.append(1)
+        elif m == 1:
+            ps.append(hg.g1_mul(5)); qs.append(hg.g2_mul(7)); expect.append(0)
+        else:
+            k = m - 1
+            P = hg.g1_progression(s1 + gi, d1, k); Q = hg.g2_progression(s2 + gi, d2, k)
+            E = sum((s1 + gi + i * d1) * (s2 + gi + i * d2) for i in range(k)) % L.R_ORDER
+            bad = gi == 6
+            ps += [P, hg.g1_neg(hg.g1_mul(E + (1 if bad else 0)))]; qs += [Q, hg.g2_mul(1)]
+            expect.append(0 if bad else 1)
+        off.append(off[-1] + m)
+    P = np.concatenate(ps); Q = np.concatenate(qs)
+    assert ctx.pairing_product_is_one(P, Q, off).tolist() == expect
+    lo, hi = off[7], off[9]                       # the last two groups (2 and 33 pairs) through the oracle as well
+    sub = [o - lo for o in off[7:10]]
+    assert orc.pairing_product_is_one(P[lo:hi], Q[lo:hi], sub, threads=8).tolist() == expect[7:9]
+    assert ctx.pairing_product_is_one(P[lo:hi], Q[lo:hi], sub).tolist() == expect[7:9]
+
+
 def test_bad_arguments(ctx):
     import ctypes
     from bls_b200 import capi

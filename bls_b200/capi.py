@@ -265,6 +265,16 @@ class Ctx:
         """ok[i] = g2pubs.Verify(msgs[i], pub_i, sig_i) from wire bytes -- b381_g2pubs_verify_batch"""
         return self._verify_wire("b381_g2pubs_verify_batch", pubs96, 96, msgs, sigs48, 48)
 
+    def verify_with_domain_rlc_batch(self, pubs48, msgs32, domain8, sigs96, weights):
+        """one boolean for the whole batch (random linear combination) -- b381_verify_with_domain_rlc_batch"""
+        p = np.ascontiguousarray(pubs48, np.uint8).reshape(-1); m = np.ascontiguousarray(msgs32, np.uint8).reshape(-1)
+        s = np.ascontiguousarray(sigs96, np.uint8).reshape(-1); d = np.frombuffer(bytes(domain8), np.uint8).copy()
+        n = p.size // 48
+        r = np.zeros((n, 4), np.uint64); r[:, 0] = np.asarray(weights, np.uint64)
+        ok = np.zeros(1, np.uint8)
+        self.call("b381_verify_with_domain_rlc_batch", _hp(p), _hp(m), _hp(d), ctypes.c_size_t(0), _hp(s), _hp(r), ctypes.c_size_t(n), _hp(ok))
+        return bool(ok[0])
+
     # -- raw device buffers owned by the engine (b381_dev_alloc / b381_h2d / b381_d2h) ----------
     def dev_empty(self, nbytes):
         return DevBuf(self, nbytes)

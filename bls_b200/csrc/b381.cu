@@ -811,8 +811,10 @@ int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *
 enum { WIRE_G1PUBS_DOMAIN = 0, WIRE_G1PUBS = 1, WIRE_G2PUBS = 2 };
 // mode WIRE_G1PUBS_DOMAIN: msg = n x 32 bytes, aux = domain (8 bytes x (stride ? n : 1)); otherwise msg = packed messages and
 // aux = n + 1 u64 offsets.  g1pubs: keys 48 B / signatures 96 B; g2pubs: keys 96 B / signatures 48 B.
+static int verify_rlc_core(b381_ctx *ctx, const b381_g1_affine *d_pub, const b381_g2_affine *d_h, const b381_g2_affine *d_sig,
+                           const uint8_t *d_pub_status, const uint8_t *d_sig_status, const b381_scalar *d_r, size_t n, uint8_t *d_ok);
 static int verify_wire_dev(b381_ctx *ctx, int mode, const uint8_t *d_pub, const uint8_t *d_msg, const void *d_aux, size_t domain_stride,
-                           const uint8_t *d_sig, size_t n, uint8_t *d_ok) {
+                           const uint8_t *d_sig, size_t n, uint8_t *d_ok, const b381_scalar *d_rlc = nullptr) {
     if (!ctx || domain_stride > 1 || n > 0x7FFFFFF0u || (n && (!d_pub || !d_msg || !d_aux || !d_sig || !d_ok))) return B381_ERR_ARG;
     if (!n) return B381_OK;
     const bool g2p = mode == WIRE_G2PUBS;
@@ -834,10 +836,13 @@ static int verify_wire_dev(b381_ctx *ctx, int mode, const uint8_t *d_pub, const 
         else
             rc = b381_hash_g2_batch_dev(ctx, d_msg, (const uint64_t *)d_aux, n, (b381_g2_affine *)H);
         if (rc) return rc;
+        if (d_rlc)       // one boolean for the whole batch
+            return verify_rlc_core(ctx, (const b381_g1_affine *)pub, (const b381_g2_affine *)H, (const b381_g2_affine *)sig, st_pub, st_sig, d_rlc, n, d_ok);
         k_verify_pairs<<<grid_for(n, 128), 128, 0, ctx->stream>>>((const g1_affine_pod *)pub, st_pub, (const g2_affine_pod *)sig, st_sig,
                                                                   (const g2_affine_pod *)H, n, (g1_affine_pod *)P, (g2_affine_pod *)Q,
                                                                   (uint32_t *)off, valid);
     } else {
+        if (d_rlc) return B381_ERR_ARG;
         rc = b381_g2_decompress_batch_dev(ctx, d_pub, n, 1, (b381_g2_affine *)pub, st_pub); if (rc) return rc;
         rc = b381_g1_decompress_batch_dev(ctx, d_sig, n, 1, (b381_g1_affine *)sig, st_sig); if (rc) return rc;
         rc = b381_hash_g1_batch_dev(ctx, d_msg, (const uint64_t *)d_aux, n, (b381_g1_affine *)H); if (rc) return rc;
@@ -854,8 +859,41 @@ static int verify_wire_dev(b381_ctx *ctx, int mode, const uint8_t *d_pub, const 
     CK(cudaGetLastError());
     return B381_OK;
 }
+// ---- random-linear-combination batch verification: ONE final exponentiation for n signatures ---------------------------------
+// ok = [ prod_i e(r_i pk_i, H_i) * e(-G1One, sum_i r_i sig_i) == 1 ]: with independent random r_i this accepts iff every
+// e(G1One, sig_i) == e(pk_i, H_i) holds (g1pubs.Verify*, g1pubs/bls.go:165-174), except with probability ~2^-bits(r).
+// n + 1 Miller loops, one tree product, one final exponentiation, n short scalar multiplications in G1 and G2.
+static int verify_rlc_core(b381_ctx *ctx, const b381_g1_affine *d_pub, const b381_g2_affine *d_h, const b381_g2_affine *d_sig,
+                           const uint8_t *d_pub_status, const uint8_t *d_sig_status, const b381_scalar *d_r, size_t n, uint8_t *d_ok) {
+    if (!ctx || n > 0x7FFFFFF0u || !d_ok || (n && (!d_pub || !d_h || !d_sig || !d_r))) return B381_ERR_ARG;
+    void *P, *Q, *rs, *S, *off, *bad;
+    int rc = scratch_get(ctx, 2, (n + 1) * sizeof(b381_g1_affine), &P); if (rc) return rc;
+    rc = scratch_get(ctx, 3, (n + 1) * sizeof(b381_g2_affine), &Q); if (rc) return rc;
+    rc = scratch_get(ctx, 22, (n + 1) * sizeof(b381_g2_affine), &rs); if (rc) return rc;
+    rc = scratch_get(ctx, 23, sizeof(b381_g2_jac) + 64, &S); if (rc) return rc;
+    rc = scratch_get(ctx, 6, 2 * sizeof(uint32_t), &off); if (rc) return rc;
+    bad = (char *)S + sizeof(b381_g2_jac);          // (slot 21 is the tree product's own scalar)
+    CK(cudaMemsetAsync(bad, 0, sizeof(uint32_t), ctx->stream));
+    if (n) {
+        k_rlc_valid<<<grid_for(n, 256), 256, 0, ctx->stream>>>((const g1_affine_pod *)d_pub, (const g2_affine_pod *)d_sig, d_pub_status,
+                                                               d_sig_status, n, (uint32_t *)bad);
+        ctx->launches++;
+        rc = b381_g1_mul_batch_dev(ctx, d_pub, 1, d_r, 1, n, (b381_g1_affine *)P); if (rc) return rc;
+        CK(cudaMemcpyAsync(Q, d_h, n * sizeof(b381_g2_affine), cudaMemcpyDeviceToDevice, ctx->stream));
+        rc = b381_g2_mul_batch_dev(ctx, d_sig, 1, d_r, 1, n, (b381_g2_affine *)rs); if (rc) return rc;
+    }
+    rc = b381_g2_sum_dev(ctx, (const b381_g2_affine *)rs, n, (b381_g2_jac *)S); if (rc) return rc;
+    k_rlc_close<<<1, 128, 0, ctx->stream>>>((const g2_jac_pod *)S, (g1_affine_pod *)P + n, (g2_affine_pod *)Q + n, (uint32_t *)off, (uint32_t)n);
+    ctx->launches++;
+    rc = b381_pairing_product_is_one_dev(ctx, (const b381_g1_affine *)P, (const b381_g2_affine *)Q, n + 1, (const uint32_t *)off, 1, d_ok);
+    if (rc) return rc;
+    k_rlc_finish<<<1, 32, 0, ctx->stream>>>(d_ok, (const uint32_t *)bad);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
 static int verify_wire_host(b381_ctx *ctx, int mode, const uint8_t *pub, const uint8_t *msg, size_t msg_bytes, const void *aux, size_t aux_bytes,
-                            size_t domain_stride, const uint8_t *sig, size_t n, uint8_t *ok) {
+                            size_t domain_stride, const uint8_t *sig, size_t n, uint8_t *ok, const b381_scalar *rlc = nullptr) {
     if (!ctx || domain_stride > 1 || (n && (!pub || !msg || !aux || !sig || !ok))) return B381_ERR_ARG;
     if (!n) return B381_OK;
     CK(cudaSetDevice(ctx->device));
@@ -869,8 +907,13 @@ static int verify_wire_host(b381_ctx *ctx, int mode, const uint8_t *pub, const u
     CK(cudaMemcpyAsync(ds, sig, sb * n, cudaMemcpyHostToDevice, ctx->stream));
     if (msg_bytes) CK(cudaMemcpyAsync(dm, msg, msg_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(da, aux, aux_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    rc = verify_wire_dev(ctx, mode, dp, dm, da, domain_stride, ds, n, (uint8_t *)dok); if (rc) return rc;
-    CK(cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, ctx->stream));
+    void *dr = nullptr;
+    if (rlc) {
+        rc = scratch_get(ctx, 14, n * sizeof(b381_scalar), &dr); if (rc) return rc;
+        CK(cudaMemcpyAsync(dr, rlc, n * sizeof(b381_scalar), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = verify_wire_dev(ctx, mode, dp, dm, da, domain_stride, ds, n, (uint8_t *)dok, (const b381_scalar *)dr); if (rc) return rc;
+    CK(cudaMemcpyAsync(ok, dok, rlc ? 1 : n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return B381_OK;
 }
@@ -919,6 +962,20 @@ int b381_verify_with_domain_batch_dev(b381_ctx *ctx, const uint8_t *d_pub48, con
 int b381_verify_with_domain_batch(b381_ctx *ctx, const uint8_t *pub48, const uint8_t *msg32, const uint8_t *domain8, size_t domain_stride,
                                   const uint8_t *sig96, size_t n, uint8_t *ok) {
     return verify_wire_host(ctx, WIRE_G1PUBS_DOMAIN, pub48, msg32, 32 * n, domain8, 8 * (domain_stride ? n : 1), domain_stride, sig96, n, ok);
+}
+int b381_verify_rlc_dev(b381_ctx *ctx, const b381_g1_affine *d_pub, const b381_g2_affine *d_msg_point, const b381_g2_affine *d_sig,
+                        const b381_scalar *d_r, size_t n, uint8_t *d_ok) {
+    return verify_rlc_core(ctx, d_pub, d_msg_point, d_sig, nullptr, nullptr, d_r, n, d_ok);
+}
+int b381_verify_with_domain_rlc_batch_dev(b381_ctx *ctx, const uint8_t *d_pub48, const uint8_t *d_msg32, const uint8_t *d_domain8,
+                                          size_t domain_stride, const uint8_t *d_sig96, const b381_scalar *d_r, size_t n, uint8_t *d_ok) {
+    if (!d_r) return B381_ERR_ARG;
+    return verify_wire_dev(ctx, WIRE_G1PUBS_DOMAIN, d_pub48, d_msg32, d_domain8, domain_stride, d_sig96, n, d_ok, d_r);
+}
+int b381_verify_with_domain_rlc_batch(b381_ctx *ctx, const uint8_t *pub48, const uint8_t *msg32, const uint8_t *domain8, size_t domain_stride,
+                                      const uint8_t *sig96, const b381_scalar *r, size_t n, uint8_t *ok) {
+    if (!r) return B381_ERR_ARG;
+    return verify_wire_host(ctx, WIRE_G1PUBS_DOMAIN, pub48, msg32, 32 * n, domain8, 8 * (domain_stride ? n : 1), domain_stride, sig96, n, ok, r);
 }
 int b381_g1pubs_verify_batch_dev(b381_ctx *ctx, const uint8_t *d_pub48, const uint8_t *d_msgs, const uint64_t *d_msg_off, const uint8_t *d_sig96,
                                  size_t n, uint8_t *d_ok) {

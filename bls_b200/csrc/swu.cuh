@@ -303,6 +303,38 @@ __global__ void __launch_bounds__(128) k_verify_pairs_g2pubs(const g2_affine_pod
     Q[2 * i] = one;
     Q[2 * i + 1] = pub[i];
 }
+// Random-linear-combination batch check: closes the product  prod_i e(r_i pk_i, H_i) * e(-G1One, sum_i r_i sig_i)  with its
+// last pair (P, Q)[n] = (-G1One, S), S = the normalised Jacobian sum; *all_valid = 0 when any key or signature is the point
+// at infinity or failed to deserialise (status arrays may be null for already-decoded inputs).
+__global__ void __launch_bounds__(128) k_rlc_close(const g2_jac_pod *__restrict__ S, g1_affine_pod *__restrict__ P_last,
+                                                   g2_affine_pod *__restrict__ Q_last, uint32_t *__restrict__ group_off, uint32_t n) {
+    if (blockIdx.x || threadIdx.x) return;
+    group_off[0] = 0; group_off[1] = n + 1;
+    g1_affine_pod one;
+    const uint32_t gx[12] = {B381_G1_GEN_X_LIMBS}, gy[12] = {B381_G1_GEN_Y_LIMBS};
+    fp t;
+    fp_load_tab(t, gx); fp_store_u64(one.x, t);
+    fp_load_tab(t, gy); fp_neg(t, t); fp_store_u64(one.y, t);
+    one.inf = 0;
+    for (int k = 0; k < 7; k++) one.pad[k] = 0;
+    *P_last = one;
+    g2_affine_pod q;
+    uint64_t zor = 0;
+    for (int k = 0; k < 12; k++) { q.x[k] = S->x[k]; q.y[k] = S->y[k]; zor |= S->z[k]; }   // the sum kernels return z = 1 or 0
+    q.inf = zor ? 0 : 1;
+    for (int k = 0; k < 7; k++) q.pad[k] = 0;
+    *Q_last = q;
+}
+__global__ void k_rlc_valid(const g1_affine_pod *__restrict__ pub, const g2_affine_pod *__restrict__ sig, const uint8_t *__restrict__ pub_status,
+                            const uint8_t *__restrict__ sig_status, size_t n, uint32_t *__restrict__ any_bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool bad = pub[i].inf || sig[i].inf || (pub_status && pub_status[i]) || (sig_status && sig_status[i]);
+    if (bad) atomicOr(any_bad, 1u);
+}
+__global__ void k_rlc_finish(uint8_t *__restrict__ ok, const uint32_t *__restrict__ any_bad) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) ok[0] = (ok[0] && !*any_bad) ? 1 : 0;
+}
 #endif
 
 }  // namespace b381

@@ -13,7 +13,9 @@ package bls
 import "C"
 
 import (
+	"encoding/binary"
 	"errors"
+	"io"
 	"unsafe"
 )
 
@@ -232,4 +234,27 @@ func must(rc C.int) {
 	if rc != C.B381_OK {
 		panic(C.GoString(C.b381_last_error(ctx())))
 	}
+}
+
+// VerifyWithDomainRLC checks n wire-format triples with ONE final exponentiation (random linear combination):
+// true iff every VerifyWithDomain equation holds, up to a false-accept probability of 2^-64.  The weights must be
+// drawn after the signatures are fixed, from a cryptographic source.
+func VerifyWithDomainRLC(pubs [][48]byte, msgs [][32]byte, domain [8]byte, sigs [][96]byte, rnd io.Reader) bool {
+	n := len(pubs)
+	if n == 0 {
+		return true
+	}
+	w := make([]FRRepr, n)
+	var b [8]byte
+	for i := range w {
+		if _, err := io.ReadFull(rnd, b[:]); err != nil {
+			panic(err)
+		}
+		w[i][0] = binary.LittleEndian.Uint64(b[:]) | 1
+	}
+	var ok C.uint8_t
+	must(C.b381_verify_with_domain_rlc_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&pubs[0])), (*C.uint8_t)(unsafe.Pointer(&msgs[0])),
+		(*C.uint8_t)(unsafe.Pointer(&domain[0])), 0, (*C.uint8_t)(unsafe.Pointer(&sigs[0])),
+		(*C.b381_scalar)(unsafe.Pointer(&w[0])), C.size_t(n), &ok))
+	return ok != 0
 }

@@ -214,6 +214,24 @@ int b381_g2pubs_verify_batch(b381_ctx *ctx, const uint8_t *pub96, const uint8_t 
 int b381_g2pubs_verify_batch_dev(b381_ctx *ctx, const uint8_t *d_pub96, const uint8_t *d_msgs, const uint64_t *d_msg_off,
                                  const uint8_t *d_sig48, size_t n, uint8_t *d_ok);
 
+/* Random-linear-combination batch verification: ONE boolean for n (public key, message point, signature) triples,
+ *   *ok = [ prod_i e(r_i pk_i, H_i) * e(-G1One, sum_i r_i sig_i) == 1 ],
+ * i.e. every g1pubs.Verify* equation e(G1One, sig_i) == e(pk_i, H_i) (g1pubs/bls.go:165-174, pairing.go:140-147) holds,
+ * up to a false-accept probability of about 2^-bits(r_i) for independent uniformly random weights r_i chosen by the
+ * caller AFTER the signatures are fixed (64-bit weights recommended; r is an array of canonical scalars, upper limbs
+ * zero).  n + 1 Miller loops and a single final exponentiation instead of n checks; the reference has no batch
+ * verification, this is the addition SURVEY.md 8d names for the attestation workload.  *ok = 0 when any key or
+ * signature is the point at infinity or fails to deserialise.  The _rlc_batch forms take wire bytes like
+ * b381_verify_with_domain_batch. */
+int b381_verify_rlc_dev(b381_ctx *ctx, const b381_g1_affine *d_pub, const b381_g2_affine *d_msg_point,
+                        const b381_g2_affine *d_sig, const b381_scalar *d_r, size_t n, uint8_t *d_ok);
+int b381_verify_with_domain_rlc_batch(b381_ctx *ctx, const uint8_t *pub48, const uint8_t *msg32, const uint8_t *domain8,
+                                      size_t domain_stride, const uint8_t *sig96, const b381_scalar *r, size_t n,
+                                      uint8_t *ok);
+int b381_verify_with_domain_rlc_batch_dev(b381_ctx *ctx, const uint8_t *d_pub48, const uint8_t *d_msg32,
+                                          const uint8_t *d_domain8, size_t domain_stride, const uint8_t *d_sig96,
+                                          const b381_scalar *d_r, size_t n, uint8_t *d_ok);
+
 /* ---- measurement -------------------------------------------------------------------------------- */
 /* Integer-pipe roofline probe: launches blocks x threads threads that each issue iters * 8
  * independent IMAD.WIDE.U32 (the 32x32->64 multiply-accumulate an Fq multiplication is made of).

@@ -117,3 +117,25 @@ def test_plain_verify_against_host_mirror(ctx, pkg):
     for i in (0, 2, 5, 8, 11):
         pk = mod.DeserializePublicKey(pubs[i].tobytes()); sg = mod.DeserializeSignature(sigs[i].tobytes())
         assert mod.Verify(msgs[i], pk, sg) == bool(expect[i])
+
+
+def test_rlc_batch_verification(ctx):
+    """b381_verify_with_domain_rlc_batch: one boolean for the batch; accepts the all-valid batch and rejects as soon as one
+    triple is wrong (wrong message, swapped signatures, undecodable key, infinity signature), for several weight draws"""
+    n = 1024
+    sk, msgs, domain, pubs, sigs = make_batch(ctx, n, 31)
+    rng = np.random.RandomState(32)
+    w = rng.randint(1, 2**63 - 1, n, dtype=np.int64).astype(np.uint64)
+    assert ctx.verify_with_domain_rlc_batch(pubs, msgs, domain, sigs, w) is True
+    assert ctx.verify_with_domain_rlc_batch(pubs[:1], msgs[:1], domain, sigs[:1], w[:1]) is True
+    m2 = msgs.copy(); m2[777, 5] ^= 4
+    assert ctx.verify_with_domain_rlc_batch(pubs, m2, domain, sigs, w) is False
+    s2 = sigs.copy(); s2[10], s2[11] = sigs[11], sigs[10]
+    assert ctx.verify_with_domain_rlc_batch(pubs, msgs, domain, s2, w) is False
+    p2 = pubs.copy(); p2[3] = np.frombuffer(cc.REF_INVALID_G1, np.uint8)
+    assert ctx.verify_with_domain_rlc_batch(p2, msgs, domain, sigs, w) is False
+    s3 = sigs.copy(); s3[0] = 0; s3[0, 0] = 0xc0
+    assert ctx.verify_with_domain_rlc_batch(pubs, msgs, domain, s3, w) is False
+    # the per-item path agrees on which item is wrong
+    ok = ctx.verify_with_domain_batch(pubs, m2, domain, sigs)
+    assert ok.sum() == n - 1 and ok[777] == 0

@@ -69,6 +69,15 @@ ctx.dev("b381_g2_compress_batch_dev", dSig.data_ptr(), N, dSigC.data_ptr())
 res["verify_with_domain_wire_ms"] = timed(lambda: ctx.dev("b381_verify_with_domain_batch_dev", dPubC.data_ptr(), dM.data_ptr(), dD.data_ptr(),
                                                              ctypes.c_size_t(0), dSigC.data_ptr(), N, dOk.data_ptr()), reps=2)
 assert bool(dOk.all().item()), "valid signatures must verify"
+# random-linear-combination variants: one boolean per batch
+W = np.zeros((n, 4), np.uint64); W[:, 0] = rng.randint(1, 2**63 - 1, n, dtype=np.int64).astype(np.uint64)
+dW = up(W); dOk1 = torch.zeros(8, dtype=torch.uint8, device=dev)
+res["verify_with_domain_wire_rlc_ms"] = timed(lambda: ctx.dev("b381_verify_with_domain_rlc_batch_dev", dPubC.data_ptr(), dM.data_ptr(), dD.data_ptr(),
+                                                                 ctypes.c_size_t(0), dSigC.data_ptr(), dW.data_ptr(), N, dOk1.data_ptr()), reps=2)
+assert int(dOk1[0].item()) == 1, "valid batch must pass the RLC check"
+res["verify_rlc_resident_points_ms"] = timed(lambda: ctx.dev("b381_verify_rlc_dev", dPub.data_ptr(), dH.data_ptr(), dSig.data_ptr(), dW.data_ptr(), N,
+                                                                dOk1.data_ptr()), reps=2)
+assert int(dOk1[0].item()) == 1
 # SWU hashing and the plain Verify from wire bytes (64-byte messages)
 ml = 64
 dMsg = up(rng.randint(0, 256, (n, ml), dtype=np.uint8)); dOff = up((np.arange(n + 1, dtype=np.uint64) * ml))

@@ -1,8 +1,8 @@
-"""Host-side (CPU, Python integers) mathematics the Go host keeps doing with the reference's own code when
-the pairing / aggregation work moves to the GPU: hashing to the curve, point (de)compression, scalar
-multiplication for signing and key generation.  The Python mirror of g1pubs / g2pubs (bls_b200/g1pubs.py,
-g2pubs.py) uses this module the way the Go shim uses package bls; it is pinned by the reference's own
-known-answer tests (tests/test_host_api.py: hash_test.go:12-82, g1pubs/bls_test.go:409-420).
+"""TEST INFRASTRUCTURE (oracle): pure-Python-integer restatement of the reference's hashing to the curve (hash.go,
+g1.go:614-714, g2.go:883-1085), point (de)compression, key derivation and the group law, used ONLY by tests/ to
+check the GPU kernels of csrc/hash.cuh, csrc/swu.cuh and csrc/codec.cuh.  Nothing under bls_b200/ imports it.
+Pinned by the reference's own known-answer tests (tests/test_host_api.py: hash_test.go:12-82,
+g1pubs/bls_test.go:409-420) and cross-checked against the C++ oracle (compression, subgroup membership).
 
 Values are canonical integers (NOT Montgomery); Fq2 elements are (c0, c1) tuples; points are affine
 tuples (x, y) or None for infinity.  Conversion to the engine's Montgomery PODs is in hostgen.g1_points /
@@ -12,14 +12,14 @@ import hashlib
 import json
 import os
 
-from . import layout as L
-from .hostgen import _Fq, _Fq2, _dbl, _madd, _mul, _to_affine_batch, G1, G2
+from bls_b200 import layout as L
+from bls_b200.hostgen import _Fq, _Fq2, _dbl, _madd, _mul, _to_affine_batch, G1, G2
 
 Q = L.Q
 R_ORDER = L.R_ORDER
 BLS_X = L.BLS_X
 
-with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "hash_params.json")) as _f:
+with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bls_b200", "hash_params.json")) as _f:
     _P = json.load(_f)
 _h = lambda s: int(s, 16)
 ISO11 = [[_h(c) for c in _P["iso11"][n]] for n in ("xNum11", "xDen11", "yNum11", "yDen11")]

@@ -86,7 +86,7 @@ def test_subgroup_criterion_on_cofactor_points(emu, orc, which):
     """The endomorphism membership tests (codec.cuh) must agree with the reference's [r]P == O (g1.go:137-141,
     g2.go:293-295) on every curve point -- in particular on points of the cofactor subgroups, of small order, and on
     sums of a subgroup point and a cofactor point."""
-    from bls_b200 import hostmath as hm
+    from oracle import hostmath as hm
     grp, dtype, nb = (orc.g1, L.G1_AFFINE, 48) if which == "g1" else (orc.g2, L.G2_AFFINE, 96)
     mul, add = (hm.g1_mul, hm.g1_add) if which == "g1" else (hm.g2_mul, hm.g2_add)
     to_pods = hg.g1_points if which == "g1" else hg.g2_points

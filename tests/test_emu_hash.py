@@ -1,5 +1,5 @@
 """CPU tests of csrc/hash.cuh (host build in tests/emu): SHA-256 against hashlib and HashG2WithDomain against the
-reference's known answer (hash_test.go:72-82) and the host restatement pinned by it (bls_b200/hostmath.py)."""
+reference's known answer (hash_test.go:72-82) and the host restatement pinned by it (oracle/hostmath.py)."""
 import ctypes
 import hashlib
 import os
@@ -8,7 +8,8 @@ import sys
 import numpy as np
 import pytest
 
-from bls_b200 import hostgen as hg, hostmath as hm, layout as L
+from bls_b200 import hostgen as hg, layout as L
+from oracle import hostmath as hm
 
 
 @pytest.fixture(scope="module")

@@ -49,7 +49,8 @@ def test_hash_g1_g2_match_reference(ctx, orc, kats):
     """b381_hash_g1_batch / b381_hash_g2_batch: HashG1 / HashG2 (hash.go:320-331,404-411) against the reference's known
     answers (hash_test.go:12-26,48-62) and the pinned host restatement, messages of every SHA-256 padding class"""
     from test_emu_hash import swu_messages
-    from bls_b200 import hostgen as hg, hostmath as hm
+    from bls_b200 import hostgen as hg
+    from oracle import hostmath as hm
     msgs = swu_messages()
     o1 = ctx.hash_g1_batch(msgs); o2 = ctx.hash_g2_batch(msgs)
     h = kats["hash"]

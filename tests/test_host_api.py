@@ -1,15 +1,16 @@
-"""The Python mirror of g1pubs / g2pubs (bls_b200/g1pubs.py, g2pubs.py, hostmath.py).
+"""The Python mirror of g1pubs / g2pubs (bls_b200/g1pubs.py, g2pubs.py, _pubs.py: every curve operation on the engine).
 
-CPU part: the host-side mathematics (hashing to the curve, key derivation, compression) against the
+CPU part: the pure-Python oracle of the hashing / compression / key-derivation code (oracle/hostmath.py) against the
 reference's own known-answer vectors (tests/golden/ref_kats.json "hash": hash_test.go:12-82,
-g1pubs/bls_test.go:409-433) and against the oracle.
+g1pubs/bls_test.go:409-433) and against the C++ oracle; the key utilities of bls_b200/keys.py.
 GPU part: the reference's API tests (g1pubs/bls_test.go:33-299, g2pubs/bls_test.go:33-213) re-run through the
 engine -- BASELINE.json's first configuration (g2pubs Sign / Verify) included -- with the oracle's
 CompareTwoPairings as the cross-check on the same points."""
 import numpy as np
 import pytest
 
-from bls_b200 import hostgen as hg, hostmath as hm, layout as L
+from bls_b200 import hostgen as hg, keys as K, layout as L
+from oracle import hostmath as hm
 
 
 # ---- CPU: host mathematics -----------------------------------------------------------------------------
@@ -21,6 +22,7 @@ def test_hash_kats(kats):
     assert [hex(q[0][0]), hex(q[0][1]), hex(q[1][0]), hex(q[1][1])] == h["hash_g2_xc0_xc1_yc0_yc1"]   # :48-70
     assert hm.compress_g2(hm.hash_g2_with_domain(bytes(32), bytes(8))).hex() == h["hash_g2_with_domain_zero_compressed"]   # :72-82
     assert hex(hm.hash_secret_key(h["derive_secret_key_in"].encode())) == h["derive_secret_key_out"]  # g1pubs/bls_test.go:409-420
+    assert hex(K.hash_secret_key(h["derive_secret_key_in"].encode())) == h["derive_secret_key_out"]
 
 
 def test_hashed_points_are_in_the_groups():
@@ -30,7 +32,8 @@ def test_hashed_points_are_in_the_groups():
         assert hm.g2_in_subgroup(q)
 
 
-def test_invalid_pubkey_vectors(kats):
+@pytest.mark.gpu
+def test_invalid_pubkey_vectors(kats, pubs):
     """g1pubs/bls_test.go:422-433, g2pubs/bls_test.go:336-347: deserialisation must fail, not crash"""
     from bls_b200 import g1pubs, g2pubs
     with pytest.raises(ValueError):
@@ -55,9 +58,9 @@ def test_compression_matches_oracle(orc):
 def test_rand_key_matches_the_tests_reader(orc):
     """RandKey(NewXORShift(seed)) (g1_test.go:106-124 + crypto/rand.Int): same scalars as the oracle's reader"""
     for seed in (1, 2, 3, 20):
-        r = hm.XorShiftReader(seed)
+        r = K.XorShiftReader(seed)
         exp = orc.XorShift(seed).rand_fr(3)
-        assert [hm.rand_int(r, L.R_ORDER) for _ in range(3)] == [L.scalar_to_int(x) for x in exp]
+        assert [K.rand_int(r, L.R_ORDER) for _ in range(3)] == [L.scalar_to_int(x) for x in exp]
 
 
 # ---- GPU: the reference's API tests through the engine --------------------------------------------------
@@ -75,7 +78,7 @@ def pubs():
 def test_g2pubs_sign_verify(pubs, orc):
     """BASELINE config 1 / g2pubs/bls_test.go:33-45 (xorshift seed 1 keys, the same messages)"""
     _, g2pubs = pubs
-    r = hm.XorShiftReader(1)
+    r = K.XorShiftReader(1)
     for i in range(3):
         priv = g2pubs.RandKey(r)
         pub = g2pubs.PrivToPub(priv)
@@ -84,8 +87,11 @@ def test_g2pubs_sign_verify(pubs, orc):
         assert g2pubs.Verify(msg, pub, sig)
         assert not g2pubs.Verify(msg + b"!", pub, sig)
         # the oracle's CompareTwoPairings(sig, G2One, HashG1(m), pub) on the same points (pairing.go:140-147)
-        P = lambda p: orc.g1.to_proj(hg.g1_points([p])); Qp = lambda q: orc.g2.to_proj(hg.g2_points([q]))
-        assert orc.compare_two_pairings(P(sig.s), Qp(hm.G2), P(hm.hash_g1(msg)), Qp(pub.p))
+        assert orc.compare_two_pairings(orc.g1.to_proj(sig.s), orc.g2.to_proj(hg.g2_mul(1)),
+                                        orc.g1.to_proj(hg.g1_points([hm.hash_g1(msg)])), orc.g2.to_proj(pub.p))
+        # PrivToPub and Sign on the engine equal the oracle's scalar multiplications of the same points
+        assert pub.p.tobytes() == hg.g2_mul(priv.f).tobytes()
+        assert sig.s.tobytes() == hg.g1_points([hm.g1_mul(hm.hash_g1(msg), priv.f)]).tobytes()
         # serialisation round trips (g2pubs/bls_test.go:279-334)
         assert g2pubs.Verify(msg, g2pubs.DeserializePublicKey(pub.Serialize()), g2pubs.DeserializeSignature(sig.Serialize()))
 
@@ -94,7 +100,7 @@ def test_g2pubs_sign_verify(pubs, orc):
 def test_g1pubs_sign_verify_and_domain(pubs):
     """g1pubs/bls_test.go:33-45 and the WithDomain variants (g1pubs/bls.go:138-141, 171-174)"""
     g1pubs, _ = pubs
-    r = hm.XorShiftReader(1)
+    r = K.XorShiftReader(1)
     priv = g1pubs.RandKey(r)
     pub = g1pubs.PrivToPub(priv)
     msg = b"Hello world! 16 characters 0"
@@ -112,7 +118,7 @@ def test_g1pubs_sign_verify_and_domain(pubs):
 def test_aggregate_common_message(pubs, which):
     """SignVerifyAggregateCommonMessage + the missing-signature negative test (g1pubs/bls_test.go:47-129)"""
     mod = pubs[0] if which == "g1pubs" else pubs[1]
-    r = hm.XorShiftReader(2)
+    r = K.XorShiftReader(2)
     msg = b">16 character identical message"
     keys = [mod.RandKey(r) for _ in range(6)]
     pubkeys = [mod.PrivToPub(k) for k in keys]
@@ -137,7 +143,7 @@ def test_aggregate_common_message(pubs, which):
 def test_aggregate_distinct_messages(pubs, which):
     """SignVerifyAggregate + duplicate-message rejection (g1pubs/bls_test.go:131-218, bls.go:252-282)"""
     mod = pubs[0] if which == "g1pubs" else pubs[1]
-    r = hm.XorShiftReader(3)
+    r = K.XorShiftReader(3)
     keys = [mod.RandKey(r) for _ in range(5)]
     pubkeys = [mod.PrivToPub(k) for k in keys]
     msgs = [b"Hello world! 16 characters %d" % i for i in range(5)]
@@ -156,7 +162,7 @@ def test_g1pubs_aggregate_with_domain(pubs):
     """VerifyAggregateCommonWithDomain / VerifyAggregateWithDomain (g1pubs/bls.go:294-311): the shape of
     verify_benchmark_test.go:33-85 at a small size"""
     g1pubs, _ = pubs
-    r = hm.XorShiftReader(5)
+    r = K.XorShiftReader(5)
     dom = bytes([7]) + bytes(7)
     keys = [g1pubs.RandKey(r) for _ in range(4)]
     pubkeys = [g1pubs.PrivToPub(k) for k in keys]

@@ -103,6 +103,25 @@ def test_g1_msm_closed_form_large(ctx, orc):
     assert got.tobytes() == hg.g1_mul(S).tobytes()
 
 
+def test_full_size_configs_closed_form(ctx, orc):
+    """BASELINE.json's full sizes through closed forms: (config 4) a 2^22-point G1 MSM with canonical 255-bit scalars and
+    (config 3) the aggregate of 2^20 public keys.  2^14 distinct points with known discrete logs are tiled (the work
+    does not depend on the values) and 2^12 distinct scalars repeat, so the expected point is one big-integer sum."""
+    m, s, d = 1 << 14, 0xA66, 0x51
+    base = hg.g1_progression(s, d, m)
+    K, kv = hg.splitmix_scalars(99, 1 << 12)
+    n = 1 << 22
+    # sum_i k_(i mod 4096) * (s + (i mod m) d): i mod 4096 and i mod m are both determined by i mod m (4096 | m)
+    per_tile = sum(kv[i % 4096] * (s + i * d) for i in range(m)) % L.R_ORDER
+    S = per_tile * (n // m) % L.R_ORDER
+    got = orc.g1.to_affine(ctx.g1_msm(np.resize(base, n), np.resize(K, (n, 4))))
+    assert got.tobytes() == hg.g1_mul(S).tobytes()
+    n = 1 << 20
+    sk_sum = sum(s + i * d for i in range(m)) * (n // m) % L.R_ORDER
+    agg = orc.g1.to_affine(ctx.g1_sum(np.resize(base, n)))
+    assert agg.tobytes() == hg.g1_mul(sk_sum).tobytes()
+
+
 @pytest.mark.parametrize("nranks", [2, 3, 8])
 def test_g1_msm_bucket_sharded(ctx, orc, nranks):
     """BASELINE config 4 semantics on one GPU: every rank's window shard, then the fold of the partials"""

@@ -133,6 +133,13 @@ class Ctx:
         self.call("b381_g1_msm", _hp(p), _hp(k), ctypes.c_size_t(p.size), _hp(out))
         return out
 
+    def g2_msm(self, p, k):
+        p = np.ascontiguousarray(p, dtype=L.G2_AFFINE); k = np.ascontiguousarray(k, dtype=np.uint64).reshape(-1, 4)
+        assert p.size == k.shape[0]
+        out = np.zeros(1, dtype=L.G2_JAC)
+        self.call("b381_g2_msm", _hp(p), _hp(k), ctypes.c_size_t(p.size), _hp(out))
+        return out
+
     def g1_msm_shard(self, p, k, rank, nranks):
         """this rank's bucket-sharded partial (Jacobian, not normalised) -- b381_g1_msm_shard_dev"""
         p = np.ascontiguousarray(p, dtype=L.G1_AFFINE); k = np.ascontiguousarray(k, dtype=np.uint64).reshape(-1, 4)

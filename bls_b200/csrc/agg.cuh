@@ -151,9 +151,9 @@ __global__ void k_msm_scatter(const uint64_t *__restrict__ k, msm_geom g, const 
 }
 
 // one thread per chunk: partial sum of <= MSM_CHUNK points of one bucket
-__global__ void __launch_bounds__(128) k_msm_chunk_sum(const g1_affine_pod *__restrict__ pts, const uint32_t *__restrict__ idx, msm_geom g,
+template <class F, class APOD> __global__ void __launch_bounds__(128) k_msm_chunk_sum(const APOD *__restrict__ pts, const uint32_t *__restrict__ idx, msm_geom g,
                                                        const uint32_t *__restrict__ bucket_off, const uint32_t *__restrict__ chunk_off,
-                                                       xyzz<FpInl> *__restrict__ chunks, uint32_t *__restrict__ chunk_bucket) {
+                                                       xyzz<F> *__restrict__ chunks, uint32_t *__restrict__ chunk_bucket) {
     int j = blockIdx.y;
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t *co = chunk_off + (size_t)j * (g.nb + 1), *bo = bucket_off + (size_t)j * (g.nb + 1);
@@ -162,14 +162,14 @@ __global__ void __launch_bounds__(128) k_msm_chunk_sum(const g1_affine_pod *__re
     while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (co[mid] <= q) lo = mid; else hi = mid; }
     uint32_t b = lo, l = q - co[b];
     uint32_t first = bo[b] + l * MSM_CHUNK, last = first + MSM_CHUNK < bo[b + 1] ? first + MSM_CHUNK : bo[b + 1];
-    xyzz<FpInl> acc;
+    xyzz<F> acc;
     msm_bucket_sum(acc, pts, idx + (size_t)j * g.n, first, last);
     chunks[(size_t)j * g.maxchunks + q] = acc;
     chunk_bucket[(size_t)j * g.maxchunks + q] = b;
 }
 
 // round r of the in-bucket tree: chunk l of a bucket absorbs chunk l + 2^r when l % 2^(r+1) == 0
-__global__ void __launch_bounds__(128) k_msm_chunk_tree(xyzz<FpInl> *__restrict__ chunks, const uint32_t *__restrict__ chunk_bucket,
+template <class F> __global__ void __launch_bounds__(128) k_msm_chunk_tree(xyzz<F> *__restrict__ chunks, const uint32_t *__restrict__ chunk_bucket,
                                                         const uint32_t *__restrict__ chunk_off, msm_geom g, int r,
                                                         const uint32_t *__restrict__ maxch) {
     if ((1u << r) >= *maxch) return;
@@ -180,27 +180,27 @@ __global__ void __launch_bounds__(128) k_msm_chunk_tree(xyzz<FpInl> *__restrict_
     uint32_t b = chunk_bucket[(size_t)j * g.maxchunks + q];
     uint32_t l = q - co[b], nch = co[b + 1] - co[b];
     if ((l & ((2u << r) - 1)) || l + (1u << r) >= nch) return;
-    xyzz<FpInl> *base = chunks + (size_t)j * g.maxchunks;
-    xyzz<FpInl> a = base[q];
+    xyzz<F> *base = chunks + (size_t)j * g.maxchunks;
+    xyzz<F> a = base[q];
     xyzz_add(a, base[q + (1u << r)]);
     base[q] = a;
 }
 
 // one thread per (window, segment of MSM_SEG buckets): sum_{d in segment} d * B[d]
-__global__ void __launch_bounds__(128) k_msm_segment_reduce(const xyzz<FpInl> *__restrict__ chunks, const uint32_t *__restrict__ chunk_off,
-                                                            msm_geom g, xyzz<FpInl> *__restrict__ segsum) {
+template <class F> __global__ void __launch_bounds__(128) k_msm_segment_reduce(const xyzz<F> *__restrict__ chunks, const uint32_t *__restrict__ chunk_off,
+                                                            msm_geom g, xyzz<F> *__restrict__ segsum) {
     int j = blockIdx.y;
     uint32_t nseg = g.nb / MSM_SEG;
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nseg) return;
     const uint32_t *co = chunk_off + (size_t)j * (g.nb + 1);
-    const xyzz<FpInl> *base = chunks + (size_t)j * g.maxchunks;
+    const xyzz<F> *base = chunks + (size_t)j * g.maxchunks;
     uint32_t lo = s * MSM_SEG, hi = lo + MSM_SEG;
     if (lo == 0) lo = 1;
-    xyzz<FpInl> running, acc;
+    xyzz<F> running, acc;
     xyzz_set_inf(running); xyzz_set_inf(acc);
     for (uint32_t d = hi; d-- > lo;) {
-        if (co[d + 1] > co[d]) { xyzz<FpInl> bsum = base[co[d]]; xyzz_add(running, bsum); }
+        if (co[d + 1] > co[d]) { xyzz<F> bsum = base[co[d]]; xyzz_add(running, bsum); }
         xyzz_add(acc, running);
     }
     if (lo > 1 && !xyzz_is_inf(running)) { xyzz_mul_small(running, lo - 1); xyzz_add(acc, running); }
@@ -208,39 +208,39 @@ __global__ void __launch_bounds__(128) k_msm_segment_reduce(const xyzz<FpInl> *_
 }
 
 // one block per window: winsum[j] = sum of its segment sums
-__global__ void __launch_bounds__(128) k_msm_window_sum(const xyzz<FpInl> *__restrict__ segsum, uint32_t nseg, xyzz<FpInl> *__restrict__ winsum) {
-    __shared__ xyzz<FpInl> sm[128];
+template <class F> __global__ void __launch_bounds__(128) k_msm_window_sum(const xyzz<F> *__restrict__ segsum, uint32_t nseg, xyzz<F> *__restrict__ winsum) {
+    __shared__ xyzz<F> sm[128];
     int j = blockIdx.x;
-    xyzz<FpInl> acc;
+    xyzz<F> acc;
     xyzz_set_inf(acc);
-    for (uint32_t s = threadIdx.x; s < nseg; s += 128) { xyzz<FpInl> q = segsum[(size_t)j * nseg + s]; xyzz_add(acc, q); }
-    block_reduce_xyzz<FpInl, 128>(acc, sm);
+    for (uint32_t s = threadIdx.x; s < nseg; s += 128) { xyzz<F> q = segsum[(size_t)j * nseg + s]; xyzz_add(acc, q); }
+    block_reduce_xyzz<F, 128>(acc, sm);
     if (threadIdx.x == 0) winsum[j] = acc;
 }
 
 // thread j shifts its window sum to its weight 2^(c * w_j); then a tree adds them; thread 0 writes the
 // result -- normalised (z = 1) for a complete MSM, plain Jacobian for a bucket-sharded partial
-__global__ void __launch_bounds__(64) k_msm_combine(const xyzz<FpInl> *__restrict__ winsum, msm_geom g, int normalise,
-                                                    g1_jac_pod *__restrict__ out) {
-    __shared__ xyzz<FpInl> sm[64];
-    xyzz<FpInl> acc;
+template <class F, class JPOD> __global__ void __launch_bounds__(64) k_msm_combine(const xyzz<F> *__restrict__ winsum, msm_geom g, int normalise,
+                                                    JPOD *__restrict__ out) {
+    __shared__ xyzz<F> sm[64];
+    xyzz<F> acc;
     xyzz_set_inf(acc);
     for (int j = threadIdx.x; j < g.nw; j += 64) {
-        xyzz<FpInl> s = winsum[j];
+        xyzz<F> s = winsum[j];
         int shifts = g.c * (g.w0 + j * g.wstep);
         if (!xyzz_is_inf(s))
             for (int i = 0; i < shifts; i++) xyzz_dbl(s);
         xyzz_add(acc, s);
     }
-    block_reduce_xyzz<FpInl, 64>(acc, sm);
+    block_reduce_xyzz<F, 64>(acc, sm);
     if (threadIdx.x == 0) {
-        fp ox, oy, oz;
+        typename F::T ox, oy, oz;
         if (normalise) xyzz_to_jac_normalised(ox, oy, oz, acc);
-        else if (xyzz_is_inf(acc)) { fp_set_zero(ox); fp_set_one(oy); fp_set_zero(oz); }
+        else if (xyzz_is_inf(acc)) { F::set_zero(ox); F::set_one(oy); F::set_zero(oz); }
         else {   // XYZZ -> Jacobian with Z = ZZZ/ZZ... avoided: (X*ZZZ^2*.., ) use Z = ZZ: X' = X*ZZ, Y' = Y*ZZZ, Z' = ZZ
             // (X/ZZ, Y/ZZZ) == (X*ZZ / ZZ^2, Y*ZZZ / ZZ^3) because ZZZ^2 == ZZ^3
-            fp_mul(ox, acc.x, acc.zz);
-            fp_mul(oy, acc.y, acc.zzz);
+            F::mul(ox, acc.x, acc.zz);
+            F::mul(oy, acc.y, acc.zzz);
             oz = acc.zz;
         }
         store_jac(out, ox, oy, oz);

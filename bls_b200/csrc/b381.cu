@@ -731,13 +731,17 @@ int b381_g1_fold_dev(b381_ctx *ctx, const b381_g1_jac *d_parts, size_t n, b381_g
 }
 
 static inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
-int b381_g1_msm_shard_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_scalar *d_k, size_t n, int rank, int nranks,
-                          b381_g1_jac *d_partial) {
-    if (!ctx || !d_partial || (n && (!d_p || !d_k)) || nranks < 1 || rank < 0 || rank >= nranks || n > 0xFFFFFFF0u) return B381_ERR_ARG;
+}   // extern "C"
+// Pippenger over G1 (F = FpInl) or G2 (F = Fp2Out); nbits = scalar bits that can be non-zero (255 for field scalars, 64 for the
+// weights of the random-linear-combination check): only ceil(nbits / c) windows are formed
+template <class F, class APOD, class JPOD>
+static int msm_shard_dev(b381_ctx *ctx, const APOD *d_p, const b381_scalar *d_k, size_t n, int nbits, int rank, int nranks, JPOD *d_partial) {
+    if (!ctx || !d_partial || (n && (!d_p || !d_k)) || nranks < 1 || rank < 0 || rank >= nranks || n > 0xFFFFFFF0u || nbits < 1 || nbits > 255)
+        return B381_ERR_ARG;
     bool whole = nranks == 1;
     msm_geom g;
     g.c = msm_window_bits(n);
-    int W = msm_num_windows(g.c);
+    int W = (nbits + g.c - 1) / g.c;
     g.w0 = rank; g.wstep = nranks; g.nw = rank < W ? (W - rank + nranks - 1) / nranks : 0;
     g.nb = 1u << g.c; g.n = n;
     g.maxchunks = (uint32_t)(n / MSM_CHUNK) + g.nb + 1;
@@ -746,14 +750,14 @@ int b381_g1_msm_shard_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_s
     // carve one scratch block
     size_t o_count = 0, o_boff = o_count + up256((size_t)nw * g.nb * 4), o_coff = o_boff + up256((size_t)nw * (g.nb + 1) * 4);
     size_t o_max = o_coff + up256((size_t)nw * (g.nb + 1) * 4), o_idx = o_max + 256, o_cb = o_idx + up256((size_t)nw * (n ? n : 1) * 4);
-    size_t o_chunks = o_cb + up256((size_t)nw * g.maxchunks * 4), o_seg = o_chunks + up256((size_t)nw * g.maxchunks * sizeof(xyzz<FpInl>));
-    size_t o_win = o_seg + up256((size_t)nw * nseg * sizeof(xyzz<FpInl>)), total = o_win + up256((size_t)nw * sizeof(xyzz<FpInl>));
+    size_t o_chunks = o_cb + up256((size_t)nw * g.maxchunks * 4), o_seg = o_chunks + up256((size_t)nw * g.maxchunks * sizeof(xyzz<F>));
+    size_t o_win = o_seg + up256((size_t)nw * nseg * sizeof(xyzz<F>)), total = o_win + up256((size_t)nw * sizeof(xyzz<F>));
     char *base;
     int rc = scratch_get(ctx, 5, total, (void **)&base);
     if (rc) return rc;
     uint32_t *count = (uint32_t *)(base + o_count), *boff = (uint32_t *)(base + o_boff), *coff = (uint32_t *)(base + o_coff);
     uint32_t *maxch = (uint32_t *)(base + o_max), *idx = (uint32_t *)(base + o_idx), *cb = (uint32_t *)(base + o_cb);
-    xyzz<FpInl> *chunks = (xyzz<FpInl> *)(base + o_chunks), *seg = (xyzz<FpInl> *)(base + o_seg), *win = (xyzz<FpInl> *)(base + o_win);
+    xyzz<F> *chunks = (xyzz<F> *)(base + o_chunks), *seg = (xyzz<F> *)(base + o_seg), *win = (xyzz<F> *)(base + o_win);
     if (g.nw > 0 && n > 0) {
         CK(cudaMemsetAsync(base, 0, o_idx, ctx->stream));        // count, offsets, maxch
         unsigned pg = grid_for(n, 256);
@@ -761,26 +765,34 @@ int b381_g1_msm_shard_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_s
         k_msm_scan<<<g.nw, 1024, 0, ctx->stream>>>(count, g, boff, coff, maxch);
         k_msm_scatter<<<pg, 256, 0, ctx->stream>>>((const uint64_t *)d_k, g, boff, count, idx);
         dim3 cg(grid_for(g.maxchunks, 128), g.nw);
-        k_msm_chunk_sum<<<cg, 128, 0, ctx->stream>>>((const g1_affine_pod *)d_p, idx, g, boff, coff, chunks, cb);
+        k_msm_chunk_sum<F><<<cg, 128, 0, ctx->stream>>>(d_p, idx, g, boff, coff, chunks, cb);
         ctx->launches += 4;
         for (int r = 0; ((size_t)MSM_CHUNK << r) < n; r++) {
-            k_msm_chunk_tree<<<cg, 128, 0, ctx->stream>>>(chunks, cb, coff, g, r, maxch);
+            k_msm_chunk_tree<F><<<cg, 128, 0, ctx->stream>>>(chunks, cb, coff, g, r, maxch);
             ctx->launches++;
         }
         dim3 sg(grid_for(nseg, 128), g.nw);
-        k_msm_segment_reduce<<<sg, 128, 0, ctx->stream>>>(chunks, coff, g, seg);
-        k_msm_window_sum<<<g.nw, 128, 0, ctx->stream>>>(seg, nseg, win);
+        k_msm_segment_reduce<F><<<sg, 128, 0, ctx->stream>>>(chunks, coff, g, seg);
+        k_msm_window_sum<F><<<g.nw, 128, 0, ctx->stream>>>(seg, nseg, win);
         ctx->launches += 2;
     } else {
         g.nw = 0;
     }
-    k_msm_combine<<<1, 64, 0, ctx->stream>>>(win, g, whole ? 1 : 0, (g1_jac_pod *)d_partial);
+    k_msm_combine<F><<<1, 64, 0, ctx->stream>>>(win, g, whole ? 1 : 0, d_partial);
     ctx->launches++;
     CK(cudaGetLastError());
     return B381_OK;
 }
+extern "C" {
+int b381_g1_msm_shard_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_scalar *d_k, size_t n, int rank, int nranks,
+                          b381_g1_jac *d_partial) {
+    return msm_shard_dev<FpInl>(ctx, (const g1_affine_pod *)d_p, d_k, n, 255, rank, nranks, (g1_jac_pod *)d_partial);
+}
 int b381_g1_msm_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_scalar *d_k, size_t n, b381_g1_jac *d_out) {
     return b381_g1_msm_shard_dev(ctx, d_p, d_k, n, 0, 1, d_out);
+}
+int b381_g2_msm_dev(b381_ctx *ctx, const b381_g2_affine *d_p, const b381_scalar *d_k, size_t n, b381_g2_jac *d_out) {
+    return msm_shard_dev<Fp2Out>(ctx, (const g2_affine_pod *)d_p, d_k, n, 255, 0, 1, (g2_jac_pod *)d_out);
 }
 
 int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_registry, const uint32_t *d_key_idx,
@@ -865,11 +877,11 @@ static int verify_wire_dev(b381_ctx *ctx, int mode, const uint8_t *d_pub, const 
 // n + 1 Miller loops, one tree product, one final exponentiation, n short scalar multiplications in G1 and G2.
 static int verify_rlc_core(b381_ctx *ctx, const b381_g1_affine *d_pub, const b381_g2_affine *d_h, const b381_g2_affine *d_sig,
                            const uint8_t *d_pub_status, const uint8_t *d_sig_status, const b381_scalar *d_r, size_t n, uint8_t *d_ok) {
+    const int rlc_bits = 255;          // weights are full scalars; callers that use 64-bit weights only pay for empty windows' scans
     if (!ctx || n > 0x7FFFFFF0u || !d_ok || (n && (!d_pub || !d_h || !d_sig || !d_r))) return B381_ERR_ARG;
-    void *P, *Q, *rs, *S, *off, *bad;
+    void *P, *Q, *S, *off, *bad;
     int rc = scratch_get(ctx, 2, (n + 1) * sizeof(b381_g1_affine), &P); if (rc) return rc;
     rc = scratch_get(ctx, 3, (n + 1) * sizeof(b381_g2_affine), &Q); if (rc) return rc;
-    rc = scratch_get(ctx, 22, (n + 1) * sizeof(b381_g2_affine), &rs); if (rc) return rc;
     rc = scratch_get(ctx, 23, sizeof(b381_g2_jac) + 64, &S); if (rc) return rc;
     rc = scratch_get(ctx, 6, 2 * sizeof(uint32_t), &off); if (rc) return rc;
     bad = (char *)S + sizeof(b381_g2_jac);          // (slot 21 is the tree product's own scalar)
@@ -880,9 +892,9 @@ static int verify_rlc_core(b381_ctx *ctx, const b381_g1_affine *d_pub, const b38
         ctx->launches++;
         rc = b381_g1_mul_batch_dev(ctx, d_pub, 1, d_r, 1, n, (b381_g1_affine *)P); if (rc) return rc;
         CK(cudaMemcpyAsync(Q, d_h, n * sizeof(b381_g2_affine), cudaMemcpyDeviceToDevice, ctx->stream));
-        rc = b381_g2_mul_batch_dev(ctx, d_sig, 1, d_r, 1, n, (b381_g2_affine *)rs); if (rc) return rc;
     }
-    rc = b381_g2_sum_dev(ctx, (const b381_g2_affine *)rs, n, (b381_g2_jac *)S); if (rc) return rc;
+    // S = sum_i r_i sig_i as one Pippenger MSM over G2 (the weights are scalars like any other)
+    rc = msm_shard_dev<Fp2Out>(ctx, (const g2_affine_pod *)d_sig, d_r, n, rlc_bits, 0, 1, (g2_jac_pod *)S); if (rc) return rc;
     k_rlc_close<<<1, 128, 0, ctx->stream>>>((const g2_jac_pod *)S, (g1_affine_pod *)P + n, (g2_affine_pod *)Q + n, (uint32_t *)off, (uint32_t)n);
     ctx->launches++;
     rc = b381_pairing_product_is_one_dev(ctx, (const b381_g1_affine *)P, (const b381_g2_affine *)Q, n + 1, (const uint32_t *)off, 1, d_ok);
@@ -1034,6 +1046,26 @@ int b381_g1_msm(b381_ctx *ctx, const b381_g1_affine *p, const b381_scalar *k, si
     rc = b381_g1_msm_dev(ctx, (const b381_g1_affine *)dp, (const b381_scalar *)dk, n, (b381_g1_jac *)dout);
     if (rc) return rc;
     CK(cudaMemcpyAsync(out, dout, sizeof(b381_g1_jac), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B381_OK;
+}
+int b381_g2_msm(b381_ctx *ctx, const b381_g2_affine *p, const b381_scalar *k, size_t n, b381_g2_jac *out) {
+    if (!ctx || !out || (n && (!p || !k))) return B381_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    void *dp, *dk, *dout;
+    int rc = scratch_get(ctx, 2, (n ? n : 1) * sizeof(b381_g2_affine), &dp);
+    if (rc) return rc;
+    rc = scratch_get(ctx, 3, (n ? n : 1) * sizeof(b381_scalar), &dk);
+    if (rc) return rc;
+    rc = scratch_get(ctx, 7, sizeof(b381_g2_jac), &dout);
+    if (rc) return rc;
+    if (n) {
+        CK(cudaMemcpyAsync(dp, p, n * sizeof(b381_g2_affine), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(dk, k, n * sizeof(b381_scalar), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    rc = b381_g2_msm_dev(ctx, (const b381_g2_affine *)dp, (const b381_scalar *)dk, n, (b381_g2_jac *)dout);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, dout, sizeof(b381_g2_jac), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return B381_OK;
 }

@@ -116,6 +116,10 @@ int b381_g2_sum_dev(b381_ctx *ctx, const b381_g2_affine *d_p, size_t n, b381_g2_
 int b381_g1_msm(b381_ctx *ctx, const b381_g1_affine *p, const b381_scalar *k, size_t n, b381_g1_jac *out);
 int b381_g1_msm_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_scalar *d_k, size_t n,
                     b381_g1_jac *d_out);
+/* The same multi-scalar multiplication over G2 (weighted signature aggregation, g1pubs/bls.go:177-183 with weights;
+ * the reference folds G2Affine.MulFR results, g2.go:92-102): out = sum_i k[i] * p[i], normalised (z = 1). */
+int b381_g2_msm(b381_ctx *ctx, const b381_g2_affine *p, const b381_scalar *k, size_t n, b381_g2_jac *out);
+int b381_g2_msm_dev(b381_ctx *ctx, const b381_g2_affine *d_p, const b381_scalar *d_k, size_t n, b381_g2_jac *d_out);
 /* Bucket-sharded MSM for multi-GPU (one process per GPU): this rank accumulates only the windows
  * w with w % nranks == rank and writes its partial sum (Jacobian, already weighted by 2^(c*w)) to
  * *d_partial.  The caller all-gathers the nranks partials and folds them with b381_g1_fold_dev.  */

@@ -122,6 +122,28 @@ def test_full_size_configs_closed_form(ctx, orc):
     assert agg.tobytes() == hg.g1_mul(sk_sum).tobytes()
 
 
+def test_g2_msm(ctx, orc):
+    """b381_g2_msm against the fold of G2Affine.MulFR (g2.go:92-102) on a small case, the closed form
+    sum k_i (s + i d) G2 on 2^14 points, 64-bit weights (the random-linear-combination shape) and degenerate inputs"""
+    n = 1 << 14
+    s, d = 0x5EED5, 0x9E3779B9
+    P = hg.g2_progression(s, d, n)
+    K, vals = hg.splitmix_scalars(7, n)
+    S = sum(k * (s + i * d) for i, k in enumerate(vals)) % L.R_ORDER
+    assert orc.g2.to_affine(ctx.g2_msm(P, K)).tobytes() == hg.g2_mul(S).tobytes()
+    m = 40
+    exp = orc.g2.sum_proj(orc.g2.mul_fr(P[:m], K[:m], threads=8))
+    assert orc.g2.to_affine(ctx.g2_msm(P[:m], K[:m])).tobytes() == orc.g2.to_affine(exp).tobytes()
+    K64 = K.copy(); K64[:, 1:] = 0
+    S64 = sum(int(K64[i, 0]) * (s + i * d) for i in range(n)) % L.R_ORDER
+    assert orc.g2.to_affine(ctx.g2_msm(P, K64)).tobytes() == hg.g2_mul(S64).tobytes()
+    Z = np.zeros_like(K[:8])
+    assert not ctx.g2_msm(P[:8], Z)["z"].any()                       # all-zero scalars: the point at infinity
+    same = np.repeat(K[:1], 3000, axis=0)                            # every point in one bucket per window
+    Ssame = vals[0] * sum(s + i * d for i in range(3000)) % L.R_ORDER
+    assert orc.g2.to_affine(ctx.g2_msm(P[:3000], same)).tobytes() == hg.g2_mul(Ssame).tobytes()
+
+
 @pytest.mark.parametrize("nranks", [2, 3, 8])
 def test_g1_msm_bucket_sharded(ctx, orc, nranks):
     """BASELINE config 4 semantics on one GPU: every rank's window shard, then the fold of the partials"""

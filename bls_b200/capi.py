@@ -282,6 +282,32 @@ class Ctx:
         self.call("b381_verify_with_domain_rlc_batch", _hp(p), _hp(m), _hp(d), ctypes.c_size_t(0), _hp(s), _hp(r), ctypes.c_size_t(n), _hp(ok))
         return bool(ok[0])
 
+    # -- multi-GPU random-linear-combination check: per-rank partial products and the finishing step ----------------
+    def verify_rlc_partial(self, pub, msg_point, sig, weights):
+        """(partial Fq12 product as a 1-element FP12 array, valid flag) for this rank's triples -- b381_verify_rlc_partial_dev"""
+        pub = np.ascontiguousarray(pub, dtype=L.G1_AFFINE); h = np.ascontiguousarray(msg_point, dtype=L.G2_AFFINE)
+        sig = np.ascontiguousarray(sig, dtype=L.G2_AFFINE)
+        n = pub.size
+        r = np.zeros((n, 4), np.uint64); r[:, 0] = np.asarray(weights, np.uint64)
+        bufs = [self.to_device(a) for a in (pub, h, sig, r)]
+        dpart, dval = self.dev_empty(576), self.dev_empty(8)
+        self.call("b381_verify_rlc_partial_dev", *[b.ptr for b in bufs], ctypes.c_size_t(n), dpart.ptr, dval.ptr)
+        return self.from_device(dpart, np.uint64, 72).reshape(1, 72), int(self.from_device(dval, np.uint8, 1)[0])
+
+    def fp12_product_final_exp_is_one(self, parts):
+        """FinalExponentiation(prod parts) == 1 -- b381_fp12_product_final_exp_is_one_dev"""
+        parts = np.ascontiguousarray(parts, dtype=np.uint64).reshape(-1, 72)
+        dp, dok = self.to_device(parts), self.dev_empty(8)
+        self.call("b381_fp12_product_final_exp_is_one_dev", dp.ptr, ctypes.c_size_t(parts.shape[0]), dok.ptr)
+        return bool(self.from_device(dok, np.uint8, 1)[0])
+
+    def miller_product(self, p, q):
+        """prod_i MillerLoop(p[i], q[i]) without the final exponentiation -- b381_miller_product_dev"""
+        p = np.ascontiguousarray(p, dtype=L.G1_AFFINE); q = np.ascontiguousarray(q, dtype=L.G2_AFFINE)
+        dp, dq, do = self.to_device(p), self.to_device(q), self.dev_empty(576)
+        self.call("b381_miller_product_dev", dp.ptr, dq.ptr, ctypes.c_size_t(p.size), do.ptr)
+        return self.from_device(do, np.uint64, 72).reshape(1, 72)
+
     # -- raw device buffers owned by the engine (b381_dev_alloc / b381_h2d / b381_d2h) ----------
     def dev_empty(self, nbytes):
         return DevBuf(self, nbytes)

@@ -568,36 +568,32 @@ int b381_pairing_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_
     if (rc) return rc;
     return b381_final_exp_batch_dev(ctx, d_out, n, d_out, nullptr);
 }
-int b381_pairing_product_is_one_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_affine *d_q,
-                                    size_t npairs, const uint32_t *d_group_off, size_t ngroups, uint8_t *d_ok) {
-    if (!ctx || (ngroups && (!d_group_off || !d_ok)) || (npairs && (!d_p || !d_q))) return B381_ERR_ARG;
-    if (!ngroups) return B381_OK;
-    void *ml = nullptr, *prod = nullptr;
-    int rc = scratch_get(ctx, 0, (npairs ? npairs : 1) * sizeof(b381_fp12), &ml);
-    if (rc) return rc;
-    rc = scratch_get(ctx, 1, ngroups * sizeof(b381_fp12), &prod);
-    if (rc) return rc;
-    rc = b381_miller_loop_batch_dev(ctx, d_p, d_q, npairs, (b381_fp12 *)ml);
-    if (rc) return rc;
-    int tree = npairs > 2 * ngroups;               // some group has more than two factors: fold groups as trees
+// prod[g] = product of the Fq12 values ml[group_off[g] .. group_off[g+1]) (ml is overwritten when groups are folded as trees)
+static int group_products(b381_ctx *ctx, void *ml, size_t nvals, const uint32_t *d_group_off, size_t ngroups, void *prod) {
+    int tree = nvals > 2 * ngroups;               // some group has more than two factors: fold groups as trees
     if (tree) {
         void *mx;
-        rc = scratch_get(ctx, 21, sizeof(uint32_t), &mx);
+        int rc = scratch_get(ctx, 21, sizeof(uint32_t), &mx);
         if (rc) return rc;
         CK(cudaMemsetAsync(mx, 0, sizeof(uint32_t), ctx->stream));
         k_group_maxsize<<<grid_for(ngroups, 256), 256, 0, ctx->stream>>>(d_group_off, ngroups, (uint32_t *)mx);
         ctx->launches++;
-        for (int level = 0; ((size_t)1 << level) < npairs; level++) {
-            k_group_tree<<<grid_for(npairs, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>((uint64_t *)ml, d_group_off, ngroups, npairs,
-                                                                                            level, (const uint32_t *)mx);
+        for (int level = 0; ((size_t)1 << level) < nvals; level++) {
+            k_group_tree<<<grid_for(nvals, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>((uint64_t *)ml, d_group_off, ngroups, nvals,
+                                                                                           level, (const uint32_t *)mx);
             ctx->launches++;
         }
     }
     k_group_product<<<grid_for(ngroups, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>(
         (const uint64_t *)ml, d_group_off, ngroups, (uint64_t *)prod, tree);
     ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+// ok[g] = FinalExponentiation(prod[g]) == 1 (prod is overwritten)
+static int final_exp_is_one(b381_ctx *ctx, void *prod, size_t ngroups, uint8_t *d_ok) {
     if (vm_for(ctx, ngroups)) {          // few groups: the warp-cooperative final exponentiation has 3x lower latency
-        rc = b381_final_exp_batch_dev(ctx, (const b381_fp12 *)prod, ngroups, (b381_fp12 *)prod, d_ok);
+        int rc = b381_final_exp_batch_dev(ctx, (const b381_fp12 *)prod, ngroups, (b381_fp12 *)prod, d_ok);
         if (rc) return rc;
         k_fp12_is_one<<<grid_for(ngroups, 128), 128, 0, ctx->stream>>>((const uint64_t *)prod, ngroups, d_ok);
         ctx->launches++;
@@ -609,6 +605,55 @@ int b381_pairing_product_is_one_dev(b381_ctx *ctx, const b381_g1_affine *d_p, co
     ctx->launches++;
     CK(cudaGetLastError());
     return B381_OK;
+}
+int b381_pairing_product_is_one_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_affine *d_q,
+                                    size_t npairs, const uint32_t *d_group_off, size_t ngroups, uint8_t *d_ok) {
+    if (!ctx || (ngroups && (!d_group_off || !d_ok)) || (npairs && (!d_p || !d_q))) return B381_ERR_ARG;
+    if (!ngroups) return B381_OK;
+    void *ml = nullptr, *prod = nullptr;
+    int rc = scratch_get(ctx, 0, (npairs ? npairs : 1) * sizeof(b381_fp12), &ml);
+    if (rc) return rc;
+    rc = scratch_get(ctx, 1, ngroups * sizeof(b381_fp12), &prod);
+    if (rc) return rc;
+    rc = b381_miller_loop_batch_dev(ctx, d_p, d_q, npairs, (b381_fp12 *)ml);
+    if (rc) return rc;
+    rc = group_products(ctx, ml, npairs, d_group_off, ngroups, prod);
+    if (rc) return rc;
+    return final_exp_is_one(ctx, prod, ngroups, d_ok);
+}
+// out = prod_i MillerLoop(p[i], q[i]) WITHOUT the final exponentiation: one rank's factor of a product that is finished
+// elsewhere (the multi-GPU random-linear-combination check: all-gather of 576-byte partials)
+int b381_miller_product_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_affine *d_q, size_t npairs, b381_fp12 *d_out) {
+    if (!ctx || !d_out || npairs > 0x7FFFFFF0u || (npairs && (!d_p || !d_q))) return B381_ERR_ARG;
+    void *ml = nullptr, *off = nullptr;
+    int rc = scratch_get(ctx, 0, (npairs ? npairs : 1) * sizeof(b381_fp12), &ml);
+    if (rc) return rc;
+    rc = scratch_get(ctx, 6, 2 * sizeof(uint32_t), &off);
+    if (rc) return rc;
+    uint32_t h_off[2] = {0, (uint32_t)npairs};
+    CK(cudaMemcpyAsync(off, h_off, sizeof h_off, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));        // h_off lives on this stack frame
+    rc = b381_miller_loop_batch_dev(ctx, d_p, d_q, npairs, (b381_fp12 *)ml);
+    if (rc) return rc;
+    return group_products(ctx, ml, npairs, (const uint32_t *)off, 1, d_out);
+}
+// *ok = [ FinalExponentiation(prod_i parts[i]) == 1 ]: the finishing step on every rank after the all-gather
+int b381_fp12_product_final_exp_is_one_dev(b381_ctx *ctx, const b381_fp12 *d_parts, size_t n, uint8_t *d_ok) {
+    if (!ctx || !d_ok || n > 0x7FFFFFF0u || (n && !d_parts)) return B381_ERR_ARG;
+    void *ml = nullptr, *prod = nullptr, *off = nullptr;
+    int rc = scratch_get(ctx, 0, (n ? n : 1) * sizeof(b381_fp12), &ml);
+    if (rc) return rc;
+    rc = scratch_get(ctx, 1, sizeof(b381_fp12), &prod);
+    if (rc) return rc;
+    rc = scratch_get(ctx, 6, 2 * sizeof(uint32_t), &off);
+    if (rc) return rc;
+    uint32_t h_off[2] = {0, (uint32_t)n};
+    CK(cudaMemcpyAsync(off, h_off, sizeof h_off, cudaMemcpyHostToDevice, ctx->stream));
+    if (n) CK(cudaMemcpyAsync(ml, d_parts, n * sizeof(b381_fp12), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    rc = group_products(ctx, ml, n, (const uint32_t *)off, 1, prod);
+    if (rc) return rc;
+    return final_exp_is_one(ctx, prod, 1, d_ok);
 }
 
 // ---- pairing, host buffers (copies inside) -------------------------------------------------------
@@ -824,7 +869,8 @@ enum { WIRE_G1PUBS_DOMAIN = 0, WIRE_G1PUBS = 1, WIRE_G2PUBS = 2 };
 // mode WIRE_G1PUBS_DOMAIN: msg = n x 32 bytes, aux = domain (8 bytes x (stride ? n : 1)); otherwise msg = packed messages and
 // aux = n + 1 u64 offsets.  g1pubs: keys 48 B / signatures 96 B; g2pubs: keys 96 B / signatures 48 B.
 static int verify_rlc_core(b381_ctx *ctx, const b381_g1_affine *d_pub, const b381_g2_affine *d_h, const b381_g2_affine *d_sig,
-                           const uint8_t *d_pub_status, const uint8_t *d_sig_status, const b381_scalar *d_r, size_t n, uint8_t *d_ok);
+                           const uint8_t *d_pub_status, const uint8_t *d_sig_status, const b381_scalar *d_r, size_t n, uint8_t *d_ok,
+                           b381_fp12 *d_partial);
 static int verify_wire_dev(b381_ctx *ctx, int mode, const uint8_t *d_pub, const uint8_t *d_msg, const void *d_aux, size_t domain_stride,
                            const uint8_t *d_sig, size_t n, uint8_t *d_ok, const b381_scalar *d_rlc = nullptr) {
     if (!ctx || domain_stride > 1 || n > 0x7FFFFFF0u || (n && (!d_pub || !d_msg || !d_aux || !d_sig || !d_ok))) return B381_ERR_ARG;
@@ -849,7 +895,7 @@ static int verify_wire_dev(b381_ctx *ctx, int mode, const uint8_t *d_pub, const 
             rc = b381_hash_g2_batch_dev(ctx, d_msg, (const uint64_t *)d_aux, n, (b381_g2_affine *)H);
         if (rc) return rc;
         if (d_rlc)       // one boolean for the whole batch
-            return verify_rlc_core(ctx, (const b381_g1_affine *)pub, (const b381_g2_affine *)H, (const b381_g2_affine *)sig, st_pub, st_sig, d_rlc, n, d_ok);
+            return verify_rlc_core(ctx, (const b381_g1_affine *)pub, (const b381_g2_affine *)H, (const b381_g2_affine *)sig, st_pub, st_sig, d_rlc, n, d_ok, nullptr);
         k_verify_pairs<<<grid_for(n, 128), 128, 0, ctx->stream>>>((const g1_affine_pod *)pub, st_pub, (const g2_affine_pod *)sig, st_sig,
                                                                   (const g2_affine_pod *)H, n, (g1_affine_pod *)P, (g2_affine_pod *)Q,
                                                                   (uint32_t *)off, valid);
@@ -875,15 +921,18 @@ static int verify_wire_dev(b381_ctx *ctx, int mode, const uint8_t *d_pub, const 
 // ok = [ prod_i e(r_i pk_i, H_i) * e(-G1One, sum_i r_i sig_i) == 1 ]: with independent random r_i this accepts iff every
 // e(G1One, sig_i) == e(pk_i, H_i) holds (g1pubs.Verify*, g1pubs/bls.go:165-174), except with probability ~2^-bits(r).
 // n + 1 Miller loops, one tree product, one final exponentiation, n short scalar multiplications in G1 and G2.
+// d_partial (optional) receives prod_i ML(r_i pk_i, H_i) * ML(-G1One, sum_i r_i sig_i) without the final exponentiation and
+// *d_ok the validity flag only (1 = no infinite / undecodable input); with d_partial == nullptr the check is finished here.
 static int verify_rlc_core(b381_ctx *ctx, const b381_g1_affine *d_pub, const b381_g2_affine *d_h, const b381_g2_affine *d_sig,
-                           const uint8_t *d_pub_status, const uint8_t *d_sig_status, const b381_scalar *d_r, size_t n, uint8_t *d_ok) {
+                           const uint8_t *d_pub_status, const uint8_t *d_sig_status, const b381_scalar *d_r, size_t n, uint8_t *d_ok,
+                           b381_fp12 *d_partial = nullptr) {
     const int rlc_bits = 255;          // weights are full scalars; callers that use 64-bit weights only pay for empty windows' scans
     if (!ctx || n > 0x7FFFFFF0u || !d_ok || (n && (!d_pub || !d_h || !d_sig || !d_r))) return B381_ERR_ARG;
     void *P, *Q, *S, *off, *bad;
     int rc = scratch_get(ctx, 2, (n + 1) * sizeof(b381_g1_affine), &P); if (rc) return rc;
     rc = scratch_get(ctx, 3, (n + 1) * sizeof(b381_g2_affine), &Q); if (rc) return rc;
     rc = scratch_get(ctx, 23, sizeof(b381_g2_jac) + 64, &S); if (rc) return rc;
-    rc = scratch_get(ctx, 6, 2 * sizeof(uint32_t), &off); if (rc) return rc;
+    rc = scratch_get(ctx, 22, 2 * sizeof(uint32_t), &off); if (rc) return rc;
     bad = (char *)S + sizeof(b381_g2_jac);          // (slot 21 is the tree product's own scalar)
     CK(cudaMemsetAsync(bad, 0, sizeof(uint32_t), ctx->stream));
     if (n) {
@@ -897,8 +946,16 @@ static int verify_rlc_core(b381_ctx *ctx, const b381_g1_affine *d_pub, const b38
     rc = msm_shard_dev<Fp2Out>(ctx, (const g2_affine_pod *)d_sig, d_r, n, rlc_bits, 0, 1, (g2_jac_pod *)S); if (rc) return rc;
     k_rlc_close<<<1, 128, 0, ctx->stream>>>((const g2_jac_pod *)S, (g1_affine_pod *)P + n, (g2_affine_pod *)Q + n, (uint32_t *)off, (uint32_t)n);
     ctx->launches++;
-    rc = b381_pairing_product_is_one_dev(ctx, (const b381_g1_affine *)P, (const b381_g2_affine *)Q, n + 1, (const uint32_t *)off, 1, d_ok);
-    if (rc) return rc;
+    if (d_partial) {
+        void *ml;
+        rc = scratch_get(ctx, 0, (n + 1) * sizeof(b381_fp12), &ml); if (rc) return rc;
+        rc = b381_miller_loop_batch_dev(ctx, (const b381_g1_affine *)P, (const b381_g2_affine *)Q, n + 1, (b381_fp12 *)ml); if (rc) return rc;
+        rc = group_products(ctx, ml, n + 1, (const uint32_t *)off, 1, d_partial); if (rc) return rc;
+        CK(cudaMemsetAsync(d_ok, 1, 1, ctx->stream));
+    } else {
+        rc = b381_pairing_product_is_one_dev(ctx, (const b381_g1_affine *)P, (const b381_g2_affine *)Q, n + 1, (const uint32_t *)off, 1, d_ok);
+        if (rc) return rc;
+    }
     k_rlc_finish<<<1, 32, 0, ctx->stream>>>(d_ok, (const uint32_t *)bad);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -978,6 +1035,11 @@ int b381_verify_with_domain_batch(b381_ctx *ctx, const uint8_t *pub48, const uin
 int b381_verify_rlc_dev(b381_ctx *ctx, const b381_g1_affine *d_pub, const b381_g2_affine *d_msg_point, const b381_g2_affine *d_sig,
                         const b381_scalar *d_r, size_t n, uint8_t *d_ok) {
     return verify_rlc_core(ctx, d_pub, d_msg_point, d_sig, nullptr, nullptr, d_r, n, d_ok);
+}
+int b381_verify_rlc_partial_dev(b381_ctx *ctx, const b381_g1_affine *d_pub, const b381_g2_affine *d_msg_point, const b381_g2_affine *d_sig,
+                                const b381_scalar *d_r, size_t n, b381_fp12 *d_partial, uint8_t *d_valid) {
+    if (!d_partial) return B381_ERR_ARG;
+    return verify_rlc_core(ctx, d_pub, d_msg_point, d_sig, nullptr, nullptr, d_r, n, d_valid, d_partial);
 }
 int b381_verify_with_domain_rlc_batch_dev(b381_ctx *ctx, const uint8_t *d_pub48, const uint8_t *d_msg32, const uint8_t *d_domain8,
                                           size_t domain_stride, const uint8_t *d_sig96, const b381_scalar *d_r, size_t n, uint8_t *d_ok) {

@@ -7,6 +7,10 @@
   of the G partials followed by a local fold on every rank.  NCCL has no user-defined reduction,
   so the north star's "all-reduce of partial bucket sums" is all-gather + fold.
 
+* random-linear-combination batch verification: every rank forms the Miller product of its own triples
+  (576 bytes, no final exponentiation), one all-gather, and every rank finishes with the product of the partials and
+  a single final exponentiation (`verify_rlc_sharded`).
+
 The arithmetic is always the engine's (a `capi.Ctx`, or in the CPU test-suite a stand-in with the
 same two methods); this module only moves 144-byte partials.
 """
@@ -61,3 +65,15 @@ def msm_bucket_sharded_dev(ctx, d_points, d_scalars, n, d_parts, d_out, group=No
     dist.all_gather_into_tensor(d_parts, mine.clone(), group=group)
     ctx.dev("b381_g1_fold_dev", d_parts.data_ptr(), ctypes.c_size_t(world), d_out.data_ptr())
     return d_out
+
+
+def verify_rlc_sharded(engine, pubs, msg_points, sigs, weights, group=None):
+    """One boolean for the union of every rank's (public key, message point, signature) triples.  Each rank passes ITS
+    tile; `engine` provides verify_rlc_partial(pub, h, sig, w) -> (one Fq12 value as 72 u64, valid) and
+    fp12_product_final_exp_is_one(parts) (capi.Ctx does).  The single exchange step is an all-gather of 576 + 1 bytes."""
+    part, valid = engine.verify_rlc_partial(pubs, msg_points, sigs, weights)
+    mine = torch.from_numpy(np.concatenate([np.ascontiguousarray(part).view(np.uint8).reshape(-1), np.array([valid], np.uint8)]).copy())
+    allp = gather_bytes(mine, group).numpy().reshape(-1, 577)
+    if not allp[:, 576].all():
+        return False
+    return bool(engine.fp12_product_final_exp_is_one(np.ascontiguousarray(allp[:, :576]).view(np.uint64).reshape(-1, 72)))

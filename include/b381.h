@@ -236,6 +236,18 @@ int b381_verify_with_domain_rlc_batch_dev(b381_ctx *ctx, const uint8_t *d_pub48,
                                           const uint8_t *d_domain8, size_t domain_stride, const uint8_t *d_sig96,
                                           const b381_scalar *d_r, size_t n, uint8_t *d_ok);
 
+/* Multi-GPU form of the random-linear-combination check: every rank forms the factor of ITS triples,
+ *   partial = prod_i MillerLoop(r_i pk_i, H_i) * MillerLoop(-G1One, sum_i r_i sig_i)      (no final exponentiation),
+ * the ranks all-gather the 576-byte partials, and each finishes with b381_fp12_product_final_exp_is_one_dev.
+ * *d_valid = 0 when one of the rank's keys or signatures is the point at infinity.  b381_miller_product_dev is the
+ * same building block for arbitrary pairs: prod_i MillerLoop(p[i], q[i]) (pairing.go:16-75 with len(items) = n). */
+int b381_verify_rlc_partial_dev(b381_ctx *ctx, const b381_g1_affine *d_pub, const b381_g2_affine *d_msg_point,
+                                const b381_g2_affine *d_sig, const b381_scalar *d_r, size_t n, b381_fp12 *d_partial,
+                                uint8_t *d_valid);
+int b381_miller_product_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_affine *d_q, size_t npairs,
+                            b381_fp12 *d_out);
+int b381_fp12_product_final_exp_is_one_dev(b381_ctx *ctx, const b381_fp12 *d_parts, size_t n, uint8_t *d_ok);
+
 /* ---- measurement -------------------------------------------------------------------------------- */
 /* Integer-pipe roofline probe: launches blocks x threads threads that each issue iters * 8
  * independent IMAD.WIDE.U32 (the 32x32->64 multiply-accumulate an Fq multiplication is made of).

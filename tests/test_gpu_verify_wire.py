@@ -139,3 +139,34 @@ def test_rlc_batch_verification(ctx):
     # the per-item path agrees on which item is wrong
     ok = ctx.verify_with_domain_batch(pubs, m2, domain, sigs)
     assert ok.sum() == n - 1 and ok[777] == 0
+
+
+def test_rlc_partials_combine_like_the_unsharded_check(ctx):
+    """the multi-GPU form on one device: three 'ranks' form partial Miller products of their tiles; the product of the
+    partials passes the final exponentiation iff the unsharded batch does (b381_verify_rlc_partial_dev +
+    b381_fp12_product_final_exp_is_one_dev, the exchange of bls_b200/dist.py::verify_rlc_sharded)"""
+    n = 96
+    sk, msgs, domain, pubs, sigs = make_batch(ctx, n, 41)
+    P, _ = ctx.g1_decompress_batch(pubs.tobytes()); S, _ = ctx.g2_decompress_batch(sigs.tobytes())
+    H = ctx.hash_g2_with_domain_batch(msgs, domain)
+    w = np.random.RandomState(42).randint(1, 2**63 - 1, n, dtype=np.int64).astype(np.uint64)
+    cuts = [0, 17, 64, 96]
+
+    def sharded(Hx):
+        parts, valid = [], []
+        for a, b in zip(cuts, cuts[1:]):
+            p, v = ctx.verify_rlc_partial(P[a:b], Hx[a:b], S[a:b], w[a:b])
+            parts.append(p); valid.append(v)
+        return all(valid) and ctx.fp12_product_final_exp_is_one(np.concatenate(parts))
+    assert sharded(H) is True
+    H2 = H.copy(); H2[70] = H[71]
+    assert sharded(H2) is False
+    # the partial of an empty tile is the neutral element
+    p0, v0 = ctx.verify_rlc_partial(P[:0], H[:0], S[:0], w[:0])
+    assert v0 == 1 and ctx.fp12_product_final_exp_is_one(p0)
+    # b381_miller_product_dev against the product of the oracle-checked Miller loops
+    # b381_miller_product_dev: e(aG1, bG2) * e(-(ab)G1, G2) has Miller product whose final exponentiation is one
+    a, b = 0x1234, 0x5678
+    Pp = np.concatenate([hg.g1_mul(a), hg.g1_neg(hg.g1_mul(a * b))]); Qq = np.concatenate([hg.g2_mul(b), hg.g2_mul(1)])
+    assert ctx.fp12_product_final_exp_is_one(ctx.miller_product(Pp, Qq))
+    assert not ctx.fp12_product_final_exp_is_one(ctx.miller_product(Pp[:1], Qq[:1]))

@@ -48,6 +48,17 @@ __global__ void __launch_bounds__(PAIRING_BLOCK, PAIRING_MIN_BLOCKS) k_miller_lo
     fp12_store_u64(out + 72 * i, &f);
 }
 
+// prod[g] = MillerLoop of the two pairs (p, q)[2g], (p, q)[2g+1] with a shared accumulator (pairing.go:16-75, two items)
+__global__ void __launch_bounds__(PAIRING_BLOCK, PAIRING_MIN_BLOCKS) k_miller_loop2(const g1_affine_pod *__restrict__ p,
+                                                                  const g2_affine_pod *__restrict__ q, size_t ngroups,
+                                                                  uint64_t *__restrict__ out) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    fp12 f;
+    miller_loop_two(&f, p + 2 * g, q + 2 * g);
+    fp12_store_u64(out + 72 * g, &f);
+}
+
 // out[i] = FinalExponentiation(in[i])   (pairing.go:79-129); in-place allowed
 __global__ void __launch_bounds__(PAIRING_BLOCK, PAIRING_MIN_BLOCKS) k_final_exp(const uint64_t *in, size_t n, uint64_t *out,
                                                                uint8_t *ok) {
@@ -621,6 +632,21 @@ int b381_pairing_product_is_one_dev(b381_ctx *ctx, const b381_g1_affine *d_p, co
     if (rc) return rc;
     return final_exp_is_one(ctx, prod, ngroups, d_ok);
 }
+// ok[g] = [ FE(ML((p,q)[2g], (p,q)[2g+1])) == 1 ]: the engine's CompareTwoPairings for n checks whose pairs are laid out two by
+// two (the verify paths build them that way); large batches use the shared-accumulator Miller loop
+static int pairs2_product_is_one(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_affine *d_q, size_t ngroups,
+                                 const uint32_t *d_group_off, uint8_t *d_ok) {
+    if (!ngroups) return B381_OK;
+    if (vm_for(ctx, 2 * ngroups)) return b381_pairing_product_is_one_dev(ctx, d_p, d_q, 2 * ngroups, d_group_off, ngroups, d_ok);
+    void *prod;
+    int rc = scratch_get(ctx, 1, ngroups * sizeof(b381_fp12), &prod);
+    if (rc) return rc;
+    k_miller_loop2<<<grid_for(ngroups, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>((const g1_affine_pod *)d_p, (const g2_affine_pod *)d_q,
+                                                                                       ngroups, (uint64_t *)prod);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return final_exp_is_one(ctx, prod, ngroups, d_ok);
+}
 // out = prod_i MillerLoop(p[i], q[i]) WITHOUT the final exponentiation: one rank's factor of a product that is finished
 // elsewhere (the multi-GPU random-linear-combination check: all-gather of 576-byte partials)
 int b381_miller_product_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_affine *d_q, size_t npairs, b381_fp12 *d_out) {
@@ -860,7 +886,7 @@ int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *
                                                                     (uint32_t *)off);
     ctx->launches++;
     CK(cudaGetLastError());
-    return b381_pairing_product_is_one_dev(ctx, (b381_g1_affine *)P, (b381_g2_affine *)Q, 2 * nattest, (uint32_t *)off, nattest, d_ok);
+    return pairs2_product_is_one(ctx, (b381_g1_affine *)P, (b381_g2_affine *)Q, nattest, (uint32_t *)off, d_ok);
 }
 
 // ---- Verify / VerifyWithDomain from wire bytes: deserialise + hash + 2-pair check per item, all on the device -----------------
@@ -910,7 +936,7 @@ static int verify_wire_dev(b381_ctx *ctx, int mode, const uint8_t *d_pub, const 
     }
     ctx->launches++;
     CK(cudaGetLastError());
-    rc = b381_pairing_product_is_one_dev(ctx, (b381_g1_affine *)P, (b381_g2_affine *)Q, 2 * n, (uint32_t *)off, n, d_ok);
+    rc = pairs2_product_is_one(ctx, (b381_g1_affine *)P, (b381_g2_affine *)Q, n, (uint32_t *)off, d_ok);
     if (rc) return rc;
     k_and_bytes<<<grid_for(n, 256), 256, 0, ctx->stream>>>(d_ok, valid, n);
     ctx->launches++;

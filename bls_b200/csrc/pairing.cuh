@@ -134,6 +134,44 @@ HD void miller_loop_one(fp12 *f, const g1_affine_pod *P, const g2_affine_pod *Q)
     fp12_conj(f, f);                                    // blsIsNegative, pairing.go:71-73
 }
 
+// Miller loop of TWO pairs sharing the accumulator: f_{|x|,Q1}(P1) * f_{|x|,Q2}(P2), conjugated -- pairing.go:16-75 with
+// len(items) == 2, the shape of CompareTwoPairings (pairing.go:140-147) and of every Verify*.  One Fq12 squaring per
+// iteration serves both pairs (62 x 36 Fq multiplications and the product of the two Miller values saved per check).
+// A pair with P or Q at infinity contributes the factor 1, as in miller_loop_one.
+HD void miller_loop_two(fp12 *f, const g1_affine_pod *P, const g2_affine_pod *Q) {
+    fp12_set_one(f);
+    fp px[2], py[2];
+    fp2 qx[2], qy[2];
+    g2_jac r[2];
+    bool live[2];
+#pragma unroll 1
+    for (int k = 0; k < 2; k++) {
+        live[k] = !(P[k].inf || Q[k].inf);
+        fp_load_u64(px[k], P[k].x); fp_load_u64(py[k], P[k].y);
+        fp_load_u64(qx[k].c0, Q[k].x); fp_load_u64(qx[k].c1, Q[k].x + 6);
+        fp_load_u64(qy[k].c0, Q[k].y); fp_load_u64(qy[k].c1, Q[k].y + 6);
+        r[k].x = qx[k]; r[k].y = qy[k]; fp2_set_one(r[k].z);
+    }
+    if (!live[0] && !live[1]) return;
+    fp2 c0, c1, c2;
+    const uint64_t xr = 0xd201000000010000ULL >> 1;
+#pragma unroll 1
+    for (int bit = 61; bit >= -1; bit--) {
+#pragma unroll 1
+        for (int k = 0; k < 2; k++) {
+            if (!live[k]) continue;
+            line_double(&r[k], &c0, &c1, &c2);
+            ell(f, &c0, &c1, &c2, &px[k], &py[k]);
+            if (bit >= 0 && ((xr >> bit) & 1)) {
+                line_add(&r[k], &qx[k], &qy[k], &c0, &c1, &c2);
+                ell(f, &c0, &c1, &c2, &px[k], &py[k]);
+            }
+        }
+        if (bit >= 0) fp12_sqr(f, f);
+    }
+    fp12_conj(f, f);
+}
+
 // conj(f^x) for f in the cyclotomic subgroup   (ExpByX, pairing.go:92-98)
 HDN void exp_by_x(fp12 *r, const fp12 *f, uint64_t x) {
     fp12 acc;

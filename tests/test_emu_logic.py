@@ -80,6 +80,21 @@ def test_miller_loop_and_final_exp(emu, orc, kats):
     assert (fe[0] == exp).all()                                   # RELIC vector, pairing_test.go:9-58
 
 
+def test_miller_loop_two_pairs_shared_accumulator(emu, orc):
+    """miller_loop_two (pairing.go:16-75 with two items, the core of CompareTwoPairings pairing.go:140-147): equal to the
+    oracle's multi-item MillerLoop when it exposes one, and always to the product of the two single-pair Miller values;
+    an infinity on either side of a pair drops that pair"""
+    P = hg.g1_progression(0x31, 5, 6); Q = hg.g2_progression(0x47, 3, 6)
+    P["inf"][4] = 1                                                 # groups: (0,1) (2,3) (4,5) with pair 4 at infinity
+    out = np.zeros(3, dtype=L.FP12)
+    emu.emu_miller_loop2(_p(P), _p(Q), ctypes.c_size_t(3), _p(out))
+    for g in range(3):
+        a = orc.miller_loop(P[2 * g:2 * g + 1], Q[2 * g:2 * g + 1]) if not P["inf"][2 * g] else None
+        b = orc.miller_loop(P[2 * g + 1:2 * g + 2], Q[2 * g + 1:2 * g + 2])
+        exp = b if a is None else orc.fq12("mul", a, b)
+        assert (out[g] == exp).all(), g
+
+
 def test_group_sums(emu, orc):
     P = hg.g1_progression(21, 5, 40)
     P = np.concatenate([P, P[:3], hg.g1_neg(P[5:7])]); P["inf"][9] = 1

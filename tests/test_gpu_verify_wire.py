@@ -170,3 +170,21 @@ def test_rlc_partials_combine_like_the_unsharded_check(ctx):
     Pp = np.concatenate([hg.g1_mul(a), hg.g1_neg(hg.g1_mul(a * b))]); Qq = np.concatenate([hg.g2_mul(b), hg.g2_mul(1)])
     assert ctx.fp12_product_final_exp_is_one(ctx.miller_product(Pp, Qq))
     assert not ctx.fp12_product_final_exp_is_one(ctx.miller_product(Pp[:1], Qq[:1]))
+
+
+def test_empty_and_single_item_batches(ctx):
+    """ragged ends of every new entry point: n = 0 and n = 1"""
+    assert ctx.verify_with_domain_batch(np.zeros((0, 48), np.uint8), np.zeros((0, 32), np.uint8), bytes(8), np.zeros((0, 96), np.uint8)).size == 0
+    assert ctx.g1pubs_verify_batch(np.zeros((0, 48), np.uint8), [], np.zeros((0, 96), np.uint8)).size == 0
+    assert ctx.g2pubs_verify_batch(np.zeros((0, 96), np.uint8), [], np.zeros((0, 48), np.uint8)).size == 0
+    assert ctx.hash_g1_batch([]).size == 0 and ctx.hash_g2_batch([]).size == 0
+    assert not ctx.g2_msm(np.zeros(0, dtype=L.G2_AFFINE), np.zeros((0, 4), np.uint64))["z"].any()
+    sk, msgs, domain, pubs, sigs = make_batch(ctx, 1, 77)
+    assert ctx.verify_with_domain_batch(pubs, msgs, domain, sigs).tolist() == [1]
+    assert ctx.verify_with_domain_rlc_batch(pubs, msgs, domain, sigs, np.array([12345], np.uint64)) is True
+    msgs[0, 0] ^= 1
+    assert ctx.verify_with_domain_batch(pubs, msgs, domain, sigs).tolist() == [0]
+    assert ctx.verify_with_domain_rlc_batch(pubs, msgs, domain, sigs, np.array([12345], np.uint64)) is False
+    m1, p1, s1 = make_plain_batch(ctx, 1, 78)
+    assert ctx.g1pubs_verify_batch(p1, m1, s1).tolist() == [1]
+    assert ctx.g1pubs_verify_batch(p1, [b""], s1).tolist() == [0]          # the empty message is a valid input to HashG2

@@ -193,6 +193,7 @@ struct b381_ctx {
     // warp-cooperative VM programs resident on the device (csrc/vm.cuh)
     struct { uint4 *code, *consts; int lanes, nsteps, nslots, spill_fq; } vm[3];
     int use_vm;
+    int vm_split;
 };
 enum { VM_ML1 = 0, VM_FE_A = 1, VM_FE_C = 2 };
 
@@ -223,6 +224,7 @@ static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n
 #define VM_MAX_UNITS 12288      // measured crossover on B200 (tools/small_bench.py): 8192 pairings 11.8 ms (VM) vs 24.1 ms; 16384: 23.2 vs 24.2
 static inline bool vm_for(const b381_ctx *ctx, size_t n) { return ctx->use_vm < 0 ? n <= VM_MAX_UNITS : ctx->use_vm != 0; }
 static inline size_t vm_smem_bytes(int lanes, int nslots) { return (size_t)VM2_WARPS * (32 / lanes) * nslots * 96; }
+#define VM_SPLIT_MAX_UNITS 592     // up to one warp of 4 units per SM: below this only latency matters -> two lanes per Fq2 operation
 
 // run VM program `which` over n units; seg[i] = (base, stride) of the per-unit global areas
 static int vm_run(b381_ctx *ctx, int which, const vm_seg seg[4], size_t n, const unsigned char *flag_a, size_t fsa,
@@ -234,7 +236,10 @@ static int vm_run(b381_ctx *ctx, int which, const vm_seg seg[4], size_t n, const
     A.nsteps = ctx->vm[which].nsteps; A.nslots = ctx->vm[which].nslots; A.n = n;
     A.flag_a = flag_a; A.flag_b = flag_b; A.flag_stride_a = fsa; A.flag_stride_b = fsb; A.ok = ok;
     int lanes = ctx->vm[which].lanes, upb = VM2_WARPS * (32 / lanes);
-    k_vm2<4><<<grid_for(n, upb), VM2_WARPS * 32, vm_smem_bytes(lanes, A.nslots), ctx->stream>>>(A);
+    if (n <= VM_SPLIT_MAX_UNITS && ctx->vm_split)
+        k_vm2<4, 2><<<grid_for(n, upb / 2), VM2_WARPS * 32, vm_smem_bytes(2 * lanes, A.nslots), ctx->stream>>>(A);
+    else
+        k_vm2<4, 1><<<grid_for(n, upb), VM2_WARPS * 32, vm_smem_bytes(lanes, A.nslots), ctx->stream>>>(A);
     ctx->launches++;
     CK(cudaGetLastError());
     return B381_OK;
@@ -274,12 +279,14 @@ int b381_init(int device, b381_ctx **out) {
         if (sm > max_smem) max_smem = sm;
     }
     if (max_smem < 200 * 1024) max_smem = 200 * 1024;
-    if (cudaFuncSetAttribute(k_vm2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess) { b381_free(ctx); return B381_ERR_CUDA; }
+    if (cudaFuncSetAttribute(k_vm2<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess) { b381_free(ctx); return B381_ERR_CUDA; }
     // Two schedules of the same arithmetic: the warp-cooperative VM (8 pairings per warp, state in shared memory:
     // 2-3x lower latency, no DRAM traffic, fills the GPU from ~8 k pairings) and one pairing per thread (higher
     // throughput once ~65 k threads are resident).  Default: by batch size; B381_VM=0/1 forces one of them for A/B measurements.
     const char *ev = getenv("B381_VM");
     ctx->use_vm = ev ? (ev[0] == '0' ? 0 : 1) : -1;
+    const char *es = getenv("B381_VM_SPLIT");       // 0 disables the two-lanes-per-operation latency form (A/B measurements)
+    ctx->vm_split = es ? (es[0] != '0') : 1;
     *out = ctx;
     return B381_OK;
 }
@@ -371,8 +378,8 @@ int b381_vm_exec_dev(b381_ctx *ctx, const void *code, int lanes, int nsteps, int
     A.flag_a = A.flag_b = nullptr; A.flag_stride_a = A.flag_stride_b = 0; A.ok = nullptr;
     size_t sm = vm_smem_bytes(lanes, nslots);
     if (sm > 200 * 1024) { cudaFree(dcode); cudaFree(dconst); return B381_ERR_ARG; }
-    CK(cudaFuncSetAttribute(k_vm2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    k_vm2<4><<<grid_for(n, VM2_WARPS * (32 / lanes)), VM2_WARPS * 32, sm, ctx->stream>>>(A);
+    CK(cudaFuncSetAttribute(k_vm2<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k_vm2<4, 1><<<grid_for(n, VM2_WARPS * (32 / lanes)), VM2_WARPS * 32, sm, ctx->stream>>>(A);
     ctx->launches++;
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     cudaFree(dcode); cudaFree(dconst);

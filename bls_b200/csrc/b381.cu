@@ -64,11 +64,11 @@ __global__ void __launch_bounds__(PAIRING_BLOCK, PAIRING_MIN_BLOCKS) k_final_exp
                                                                uint8_t *ok) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fp12 f, r;
+    fp12 f;
     fp12_load_u64(&f, in + 72 * i);
-    fp12_set_one(&r);
-    bool good = final_exp_one(&r, &f);
-    fp12_store_u64(out + 72 * i, &r);
+    bool good = final_exp_one(&f, &f);                 // in place; f == 0 leaves f untouched: report 1 like the VM path
+    if (!good) fp12_set_one(&f);
+    fp12_store_u64(out + 72 * i, &f);
     if (ok) ok[i] = good ? 1 : 0;
 }
 
@@ -122,10 +122,10 @@ __global__ void __launch_bounds__(PAIRING_BLOCK, PAIRING_MIN_BLOCKS) k_final_exp
                                                                       uint8_t *__restrict__ ok) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    fp12 f, r;
+    fp12 f;
     fp12_load_u64(&f, prod + 72 * i);
-    bool good = final_exp_one(&r, &f);
-    ok[i] = (good && fp12_is_one(&r)) ? 1 : 0;
+    bool good = final_exp_one(&f, &f);
+    ok[i] = (good && fp12_is_one(&f)) ? 1 : 0;
 }
 
 // ok[i] &= (fe[i] == 1)   (the Equals(FQ12One) of pairing.go:146 after a separate final-exponentiation pass)

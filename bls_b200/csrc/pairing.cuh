@@ -186,37 +186,40 @@ HDN void exp_by_x(fp12 *r, const fp12 *f, uint64_t x) {
     fp12_conj(r, &acc);
 }
 
-// FinalExponentiation   (pairing.go:79-129).  Returns false for f == 0 (the reference returns nil).
+// FinalExponentiation   (pairing.go:79-129).  Returns false for f == 0 (the reference returns nil).  `out` may alias `in`
+// and doubles as the y1 of the reference's chain: four Fq12 temporaries instead of six keep the per-thread stack -- which
+// lives in L2/DRAM for a 2^16 batch -- 1.1 KB smaller.
 HD bool final_exp_one(fp12 *out, const fp12 *in) {
     const uint64_t X = 0xd201000000010000ULL;
-    fp12 r, y0, y1, y2, y3;
+    fp12 r, y0, y2, y3;
+    fp12 *y1 = out;
     fp12_conj(&y0, in);                 // f1
-    if (!fp12_inv(&y1, in)) return false;   // f2
-    fp12_mul(&r, &y0, &y1);
-    fp12_copy(&y1, &r);
+    if (!fp12_inv(y1, in)) return false;    // f2 (in place when out == in)
+    fp12_mul(&r, &y0, y1);
+    fp12_copy(y1, &r);
     fp12_frobenius(&r, &r, 2);
-    fp12_mul(&r, &r, &y1);              // r = f^((q^6-1)(q^2+1)), cyclotomic from here on
+    fp12_mul(&r, &r, y1);               // r = f^((q^6-1)(q^2+1)), cyclotomic from here on
     fp12_cyclotomic_sqr(&y0, &r);
-    exp_by_x(&y1, &y0, X);
-    exp_by_x(&y2, &y1, X >> 1);
+    exp_by_x(y1, &y0, X);
+    exp_by_x(&y2, y1, X >> 1);
     fp12_conj(&y3, &r);
-    fp12_mul(&y1, &y1, &y3);
-    fp12_conj(&y1, &y1);
-    fp12_mul(&y1, &y1, &y2);
-    exp_by_x(&y2, &y1, X);
+    fp12_mul(y1, y1, &y3);
+    fp12_conj(y1, y1);
+    fp12_mul(y1, y1, &y2);
+    exp_by_x(&y2, y1, X);
     exp_by_x(&y3, &y2, X);
-    fp12_conj(&y1, &y1);
-    fp12_mul(&y3, &y3, &y1);
-    fp12_conj(&y1, &y1);
-    fp12_frobenius(&y1, &y1, 3);
+    fp12_conj(y1, y1);
+    fp12_mul(&y3, &y3, y1);
+    fp12_conj(y1, y1);
+    fp12_frobenius(y1, y1, 3);
     fp12_frobenius(&y2, &y2, 2);
-    fp12_mul(&y1, &y1, &y2);
+    fp12_mul(y1, y1, &y2);
     exp_by_x(&y2, &y3, X);
     fp12_mul(&y2, &y2, &y0);
     fp12_mul(&y2, &y2, &r);
-    fp12_mul(&y1, &y1, &y2);
+    fp12_mul(y1, y1, &y2);
     fp12_frobenius(&y3, &y3, 1);
-    fp12_mul(out, &y1, &y3);
+    fp12_mul(out, y1, &y3);
     return true;
 }
 

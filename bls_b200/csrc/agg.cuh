@@ -228,8 +228,18 @@ template <class F, class JPOD> __global__ void __launch_bounds__(64) k_msm_combi
     for (int j = threadIdx.x; j < g.nw; j += 64) {
         xyzz<F> s = winsum[j];
         int shifts = g.c * (g.w0 + j * g.wstep);
-        if (!xyzz_is_inf(s))
-            for (int i = 0; i < shifts; i++) xyzz_dbl(s);
+        if (!xyzz_is_inf(s) && shifts) {           // the shift is a chain of doublings: Jacobian form (2M + 5S each),
+            typedef typename shift_policy<F>::type FS;   // multiplications inlined so that independent products overlap
+            jac_pt<FS> js;
+            F::mul(js.x, s.x, s.zz);               // (X ZZ, Y ZZZ, ZZ) is the same point in Jacobian form
+            F::mul(js.y, s.y, s.zzz);
+            js.z = s.zz;
+#pragma unroll 1
+            for (int i = 0; i < shifts; i++) jac_dbl(js);
+            s.x = js.x; s.y = js.y;
+            F::sqr(s.zz, js.z);
+            F::mul(s.zzz, s.zz, js.z);
+        }
         xyzz_add(acc, s);
     }
     block_reduce_xyzz<F, 64>(acc, sm);

@@ -27,6 +27,14 @@ struct FpInl {
     static HD void set_one(T &r) { fp_set_one(r); }
     static HD void inv(T &r, const T &a) { fp_inv(&r, &a); }
 };
+// multiplications inlined at every use: for latency-bound single-thread chains (the MSM window shifts), where ptxas can
+// overlap the independent products of a doubling; far too much code for the throughput kernels
+struct FpIlp : FpInl {
+    static HD void mul(T &r, const T &a, const T &b) { fp_mul_inl(r, a, b); }
+    static HD void sqr(T &r, const T &a) { fp_mul_inl(r, a, a); }
+};
+template <class F> struct shift_policy { typedef F type; };
+template <> struct shift_policy<FpInl> { typedef FpIlp type; };
 struct FpOut : FpInl {
     static HD void mul(T &r, const T &a, const T &b) { fp_mul_n(&r, &a, &b); }
     static HD void sqr(T &r, const T &a) { fp_sqr_n(&r, &a); }
@@ -175,6 +183,79 @@ template <class F> HD void xyzz_mul_small(xyzz<F> &p, uint32_t k) {
         if ((k >> b) & 1) xyzz_add(acc, p);
     }
     p = acc;
+}
+
+// ---- Jacobian points for doubling-heavy work (ladders, window shifts): the reference's own formulas -------------------
+// doubling 2M + 5S (G1Projective.Double, g1.go:343-397: dbl-2009-l), mixed addition 7M + 4S (AddAffine, g1.go:485-559:
+// madd-2007-bl); the XYZZ doubling above costs 6M + 3S.
+template <class F> struct jac_pt { typename F::T x, y, z; };          // infinity <=> z == 0
+template <class F> HD void jac_dbl(jac_pt<F> &p) {
+    if (F::is_zero(p.z)) return;
+    typename F::T a, b, c, d, e, f;
+    F::sqr(a, p.x);
+    F::sqr(b, p.y);
+    F::sqr(c, b);
+    F::add(d, p.x, b);
+    F::sqr(d, d);
+    F::sub(d, d, a);
+    F::sub(d, d, c);
+    F::dbl(d, d);                      // D = 2((X + B)^2 - A - C)
+    F::dbl(e, a); F::add(e, e, a);     // E = 3A
+    F::sqr(f, e);
+    F::mul(p.z, p.y, p.z);
+    F::dbl(p.z, p.z);                  // Z3 = 2 Y Z
+    F::sub(p.x, f, d);
+    F::sub(p.x, p.x, d);               // X3 = F - 2D
+    F::sub(d, d, p.x);
+    F::mul(d, e, d);
+    F::dbl(c, c); F::dbl(c, c); F::dbl(c, c);
+    F::sub(p.y, d, c);                 // Y3 = E(D - X3) - 8C
+}
+template <class F> HD void jac_madd(jac_pt<F> &p, const typename F::T &x2, const typename F::T &y2) {
+    if (F::is_zero(p.z)) { p.x = x2; p.y = y2; F::set_one(p.z); return; }
+    typename F::T z1z1, u2, s2, h, hh, i, j, r, v, t;
+    F::sqr(z1z1, p.z);
+    F::mul(u2, x2, z1z1);
+    F::mul(s2, y2, p.z);
+    F::mul(s2, s2, z1z1);
+    F::sub(h, u2, p.x);
+    F::sub(r, s2, p.y);
+    if (F::is_zero(h)) {
+        if (F::is_zero(r)) { p.x = x2; p.y = y2; F::set_one(p.z); jac_dbl(p); }   // same point (g1.go:506-509)
+        else { F::set_one(p.x); F::set_one(p.y); F::set_zero(p.z); }              // P + (-P)
+        return;
+    }
+    F::dbl(r, r);
+    F::sqr(hh, h);
+    F::dbl(i, hh); F::dbl(i, i);       // I = 4 HH
+    F::mul(j, h, i);
+    F::mul(v, p.x, i);
+    F::add(t, p.z, h);                 // Z3 = (Z1 + H)^2 - Z1Z1 - HH
+    F::sqr(t, t);
+    F::sub(t, t, z1z1);
+    F::sub(p.z, t, hh);
+    F::sqr(p.x, r);
+    F::sub(p.x, p.x, j);
+    F::sub(p.x, p.x, v);
+    F::sub(p.x, p.x, v);               // X3 = r^2 - J - 2V
+    F::sub(v, v, p.x);
+    F::mul(v, r, v);
+    F::mul(t, p.y, j);
+    F::dbl(t, t);
+    F::sub(p.y, v, t);                 // Y3 = r(V - X3) - 2 Y1 J
+}
+template <class F> HD void jac_to_xyzz(xyzz<F> &o, const jac_pt<F> &p) {
+    if (F::is_zero(p.z)) { xyzz_set_inf(o); return; }
+    o.x = p.x; o.y = p.y;
+    F::sqr(o.zz, p.z);
+    F::mul(o.zzz, o.zz, p.z);
+}
+// XYZZ -> Jacobian without an inversion: (X ZZ, Y ZZZ, ZZ) represents the same point (ZZZ^2 = ZZ^3)
+template <class F> HD void xyzz_to_jac_pt(jac_pt<F> &o, const xyzz<F> &p) {
+    if (xyzz_is_inf(p)) { F::set_one(o.x); F::set_one(o.y); F::set_zero(o.z); return; }
+    F::mul(o.x, p.x, p.zz);
+    F::mul(o.y, p.y, p.zzz);
+    o.z = p.zz;
 }
 
 // ---- loads / stores of the ABI PODs --------------------------------------------------------------

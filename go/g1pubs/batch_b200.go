@@ -46,8 +46,9 @@ func (s *Signature) VerifyAggregateB200(pubKeys []*PublicKey, msgs [][]byte) boo
 	g := bls.G1AffineOne.Copy()
 	g.NegAssign()
 	p[0], q[0] = *g, *s.s.ToAffine()
+	hs := bls.HashG2Batch(msgs) // HashG2 of every message on the device (go/bls/codec_b200.go)
 	for i := range pubKeys {
-		p[i+1], q[i+1] = *pubKeys[i].p.ToAffine(), *bls.HashG2(msgs[i]) // hashing stays on the host (SURVEY N1)
+		p[i+1], q[i+1] = *pubKeys[i].p.ToAffine(), hs[i]
 	}
 	return bls.PairingProductsAreOne(p, q, []uint32{0, uint32(n + 1)})[0]
 }
@@ -60,12 +61,12 @@ func VerifyBatchCommonWithDomain(sigs []*Signature, committees [][]*PublicKey, m
 	p := make([]bls.G1Affine, 0, 2*n)
 	q := make([]bls.G2Affine, 0, 2*n)
 	off := make([]uint32, 1, n+1)
+	hs := bls.HashG2WithDomainBatch(msgs, domain) // one launch for all message points
 	for i := range sigs {
 		agg := AggregatePublicKeysB200(committees[i]).p.ToAffine()
 		agg.NegAssign()
-		h := bls.HashG2WithDomain(msgs[i], domain).ToAffine()
 		p = append(p, *bls.G1AffineOne, *agg)
-		q = append(q, *sigs[i].s.ToAffine(), *h)
+		q = append(q, *sigs[i].s.ToAffine(), hs[i])
 		off = append(off, uint32(len(p)))
 	}
 	return bls.PairingProductsAreOne(p, q, off)

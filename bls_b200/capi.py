@@ -308,6 +308,21 @@ class Ctx:
         self.call("b381_miller_product_dev", dp.ptr, dq.ptr, ctypes.c_size_t(p.size), do.ptr)
         return self.from_device(do, np.uint64, 72).reshape(1, 72)
 
+    def verify_aggregate_common_with_domain_batch(self, registry, key_idx, key_off, sigs96, msgs32, domain8, msg_idx):
+        """ok[a] for attestations given with compressed signatures and 32-byte message hashes --
+        b381_verify_aggregate_common_with_domain_batch_dev"""
+        registry = np.ascontiguousarray(registry, dtype=L.G1_AFFINE)
+        key_idx = np.ascontiguousarray(key_idx, dtype=np.uint32); key_off = np.ascontiguousarray(key_off, dtype=np.uint32)
+        sig = np.ascontiguousarray(sigs96, np.uint8).reshape(-1, 96); msg = np.ascontiguousarray(msgs32, np.uint8).reshape(-1, 32)
+        dom = np.frombuffer(bytes(domain8), np.uint8).copy(); msg_idx = np.ascontiguousarray(msg_idx, dtype=np.uint32)
+        n = sig.shape[0]
+        assert key_off.size == n + 1 and msg_idx.size == n and dom.size == 8
+        b = [self.to_device(a) for a in (registry, key_idx, key_off, sig, msg, dom, msg_idx)]
+        dok = self.dev_empty(max(n, 1))
+        self.call("b381_verify_aggregate_common_with_domain_batch_dev", b[0].ptr, b[1].ptr, b[2].ptr, b[3].ptr, b[4].ptr,
+                  ctypes.c_size_t(msg.shape[0]), b[5].ptr, b[6].ptr, ctypes.c_size_t(n), dok.ptr)
+        return self.from_device(dok, np.uint8, n)
+
     # -- raw device buffers owned by the engine (b381_dev_alloc / b381_h2d / b381_d2h) ----------
     def dev_empty(self, nbytes):
         return DevBuf(self, nbytes)

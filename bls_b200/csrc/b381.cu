@@ -896,6 +896,31 @@ int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *
     return pairs2_product_is_one(ctx, (b381_g1_affine *)P, (b381_g2_affine *)Q, nattest, (uint32_t *)off, d_ok);
 }
 
+// VerifyAggregateCommonWithDomain (g1pubs/bls.go:294-297) for a batch of attestations given as they arrive: compressed
+// aggregate signatures and 32-byte message hashes; the committee keys come from a resident, already validated registry.
+// Device: DeserializeSignature (subgroup-checked) per attestation, HashG2WithDomain per DISTINCT message, per-attestation key
+// aggregation, one CompareTwoPairings per attestation.
+int b381_verify_aggregate_common_with_domain_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_registry, const uint32_t *d_key_idx,
+                                                       const uint32_t *d_key_off, const uint8_t *d_sig96, const uint8_t *d_msg32, size_t nmsg,
+                                                       const uint8_t *d_domain8, const uint32_t *d_msg_idx, size_t nattest, uint8_t *d_ok) {
+    if (!ctx || nattest > 0x7FFFFFF0u) return B381_ERR_ARG;
+    if (!nattest) return B381_OK;
+    if (!d_registry || !d_key_idx || !d_key_off || !d_sig96 || !d_msg32 || !nmsg || !d_domain8 || !d_msg_idx || !d_ok) return B381_ERR_ARG;
+    void *sig, *H, *st;
+    int rc = scratch_get(ctx, 16, nattest * sizeof(b381_g2_affine), &sig); if (rc) return rc;
+    rc = scratch_get(ctx, 17, nmsg * sizeof(b381_g2_affine), &H); if (rc) return rc;
+    rc = scratch_get(ctx, 18, nattest, &st); if (rc) return rc;
+    rc = b381_g2_decompress_batch_dev(ctx, d_sig96, nattest, 1, (b381_g2_affine *)sig, (uint8_t *)st); if (rc) return rc;
+    rc = b381_hash_g2_with_domain_batch_dev(ctx, d_msg32, d_domain8, 0, nmsg, (b381_g2_affine *)H); if (rc) return rc;
+    rc = b381_verify_aggregate_common_batch_dev(ctx, d_registry, d_key_idx, d_key_off, (const b381_g2_affine *)sig, (const b381_g2_affine *)H,
+                                                d_msg_idx, nattest, d_ok);
+    if (rc) return rc;
+    k_and_status_g2<<<grid_for(nattest, 256), 256, 0, ctx->stream>>>(d_ok, (const uint8_t *)st, (const g2_affine_pod *)sig, nattest);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+
 // ---- Verify / VerifyWithDomain from wire bytes: deserialise + hash + 2-pair check per item, all on the device -----------------
 }   // extern "C"
 enum { WIRE_G1PUBS_DOMAIN = 0, WIRE_G1PUBS = 1, WIRE_G2PUBS = 2 };

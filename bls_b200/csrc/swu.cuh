@@ -335,6 +335,11 @@ __global__ void k_rlc_valid(const g1_affine_pod *__restrict__ pub, const g2_affi
 __global__ void k_rlc_finish(uint8_t *__restrict__ ok, const uint32_t *__restrict__ any_bad) {
     if (blockIdx.x == 0 && threadIdx.x == 0) ok[0] = (ok[0] && !*any_bad) ? 1 : 0;
 }
+// ok[i] &= (status[i] == 0 && !pt[i].inf): a deserialisation failure (or an infinite signature) makes the check false
+__global__ void k_and_status_g2(uint8_t *__restrict__ ok, const uint8_t *__restrict__ status, const g2_affine_pod *__restrict__ pt, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ok[i] = (ok[i] && status[i] == 0 && !pt[i].inf) ? 1 : 0;
+}
 #endif
 
 }  // namespace b381

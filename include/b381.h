@@ -137,6 +137,16 @@ int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *
                                            const uint32_t *d_key_idx, const uint32_t *d_key_off,
                                            const b381_g2_affine *d_sig, const b381_g2_affine *d_msg_hash,
                                            const uint32_t *d_msg_idx, size_t nattest, uint8_t *d_ok);
+/* The same batch as the attestations arrive on the wire: compressed aggregate signatures (n x 96 bytes) and 32-byte
+ * message hashes (nmsg DISTINCT messages, msg_idx[a] selects one) with one 8-byte domain.  On the device:
+ * DeserializeSignature with the subgroup check (g1pubs/bls.go:38-45), HashG2WithDomain per distinct message
+ * (g2.go:1041-1085), key aggregation, CompareTwoPairings.  ok[a] = 0 also when the signature fails to deserialise or is
+ * the point at infinity.  The registry holds validated keys (b381_g1_decompress_batch with the subgroup check). */
+int b381_verify_aggregate_common_with_domain_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_registry,
+                                                       const uint32_t *d_key_idx, const uint32_t *d_key_off,
+                                                       const uint8_t *d_sig96, const uint8_t *d_msg32, size_t nmsg,
+                                                       const uint8_t *d_domain8, const uint32_t *d_msg_idx, size_t nattest,
+                                                       uint8_t *d_ok);
 
 /* ---- wire formats and scalar multiplication (the callers on either side of the verification path) ------------ */
 /* DecompressG1 (check_subgroup != 0, g1.go:185-195) / DecompressG1Unchecked (g1.go:199-227) over n x 48 bytes;

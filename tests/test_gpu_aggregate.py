@@ -198,3 +198,32 @@ def test_verify_aggregate_empty_committee_and_batch(ctx, orc):
     ok = ctx.verify_aggregate_common_batch(reg, kidx, koff2, sig, H, midx)
     assert ok.tolist() == [expect[0], 0, 0]
     assert ctx.verify_aggregate_common_batch(reg, kidx[:0], np.zeros(1, np.uint32), sig[:0], H, midx[:0]).size == 0
+
+
+def test_attestations_from_wire(ctx, orc):
+    """b381_verify_aggregate_common_with_domain_batch_dev: VerifyAggregateCommonWithDomain (g1pubs/bls.go:294-297) with
+    compressed aggregate signatures and 32-byte message hashes; verdicts by construction (known secret keys), an
+    undecodable signature and an infinite one are false, and the pre-hashed entry point agrees"""
+    m, s0, d0 = 64, 0xA66, 0x51
+    keys = hg.g1_progression(s0, d0, m)
+    rng = np.random.RandomState(5)
+    natt, comm, nmsg = 24, 9, 3
+    msgs = rng.randint(0, 256, (nmsg, 32), dtype=np.uint8)
+    domain = bytes(range(8))
+    H = ctx.hash_g2_with_domain_batch(msgs, domain)
+    tk = rng.randint(0, m, size=(natt, comm))
+    midx = (np.arange(natt) % nmsg).astype(np.uint32)
+    sk = [sum(s0 + int(i) * d0 for i in tk[a]) % L.R_ORDER for a in range(natt)]
+    expect = np.ones(natt, np.uint8)
+    sk[4] += 1; expect[4] = 0                                                # wrong aggregate signature
+    K = np.array([L.int_to_limbs(k, 4) for k in sk], np.uint64)
+    sig_aff = ctx.g2_mul_batch(H[midx], K)                                   # sum of the members' signatures on H(m)
+    sigs = ctx.g2_compress_batch(sig_aff)
+    sigs[7, 0] &= 0x7f; expect[7] = 0                                        # compression bit cleared
+    sigs[9] = 0; sigs[9, 0] = 0xc0; expect[9] = 0                            # infinity
+    kidx = tk.reshape(-1).astype(np.uint32); koff = (np.arange(natt + 1) * comm).astype(np.uint32)
+    ok = ctx.verify_aggregate_common_with_domain_batch(keys, kidx, koff, sigs, msgs, domain, midx)
+    assert ok.tolist() == expect.tolist()
+    good = [a for a in range(natt) if a not in (7, 9)]
+    ok2 = ctx.verify_aggregate_common_batch(keys, kidx, koff, sig_aff, H, midx)
+    assert ok2[good].tolist() == expect[good].tolist()

@@ -105,9 +105,16 @@ def _rlc_worker(rank, world, port, q, corrupt):
 
 
 @pytest.mark.parametrize("corrupt", [False, True])
+def _prebuild():
+    """compile the host build of the device code ONCE in the parent, so that the spawned ranks only dlopen it"""
+    import __graft_entry__ as g
+    g.build_emu()
+
+
 def test_rlc_verification_world2(corrupt):
     """SURVEY.md 8e, RLC variant: each rank's partial Miller product, one all-gather of 577 bytes, product + one final
     exponentiation on every rank; a single bad signature on rank 1 makes every rank answer False"""
+    _prebuild()
     ctxm = mp.get_context("spawn")
     q = ctxm.Queue()
     port = 31500 + os.getpid() % 2000 + (7 if corrupt else 0)
@@ -141,6 +148,7 @@ def _worker(rank, world, port, q):
 
 def test_bucket_sharded_msm_world2(orc):
     from bls_b200 import hostgen as hg
+    _prebuild()
     ctxm = mp.get_context("spawn")
     q = ctxm.Queue()
     port = 29500 + os.getpid() % 2000

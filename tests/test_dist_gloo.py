@@ -104,13 +104,13 @@ def _rlc_worker(rank, world, port, q, corrupt):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("corrupt", [False, True])
 def _prebuild():
     """compile the host build of the device code ONCE in the parent, so that the spawned ranks only dlopen it"""
     import __graft_entry__ as g
     g.build_emu()
 
 
+@pytest.mark.parametrize("corrupt", [False, True])
 def test_rlc_verification_world2(corrupt):
     """SURVEY.md 8e, RLC variant: each rank's partial Miller product, one all-gather of 577 bytes, product + one final
     exponentiation on every rank; a single bad signature on rank 1 makes every rank answer False"""

@@ -389,23 +389,37 @@ HD void fp4_sqr(fp2 &o0, fp2 &o1, const fp2 &a, const fp2 &b) {
     fp2_mul_nr(t1, t1);
     fp2_add(o0, t0, t1);          // a^2 + xi b^2
 }
+// r = 3t - 2z (plus = 0) or 3t + 2z (plus = 1): the six output rows of the cyclotomic squaring as ONE pass each (three
+// separate add/sub/double passes cost three local-memory round trips per row)
+HDN void fp2_tri(fp2 *r, const fp2 *t, const fp2 *z, int plus) {
+    const fp *tp = &t->c0, *zp = &z->c0;
+    fp *rp = &r->c0;
+#pragma unroll 1
+    for (int i = 0; i < 2; i++) {
+        fp x = tp[i], y = zp[i], u;
+        if (plus) fp_add(u, x, y); else fp_sub(u, x, y);
+        fp_add(u, u, u);
+        fp_add(u, u, x);
+        rp[i] = u;
+    }
+}
 HDN void fp12_cyclotomic_sqr(fp12 *r, const fp12 *a) {
-    fp2 t0, t1, t2, t3, z;
+    fp2 t0, t1, t2, t3;
     fp2 z0 = a->c0.c0, z4 = a->c0.c1, z3 = a->c0.c2, z2 = a->c1.c0, z1 = a->c1.c1, z5 = a->c1.c2;
     // (t0,t1) = fp4sq(z0,z1);  z0' = 3t0 - 2z0;  z1' = 3t1 + 2z1
     fp4_sqr(t0, t1, z0, z1);
-    fp2_sub(z, t0, z0); fp2_dbl(z, z); fp2_add(r->c0.c0, z, t0);
-    fp2_add(z, t1, z1); fp2_dbl(z, z); fp2_add(r->c1.c1, z, t1);
+    fp2_tri(&r->c0.c0, &t0, &z0, 0);
+    fp2_tri(&r->c1.c1, &t1, &z1, 1);
     // (t0,t1) = fp4sq(z2,z3); (t2,t3) = fp4sq(z4,z5)
     fp4_sqr(t0, t1, z2, z3);
     fp4_sqr(t2, t3, z4, z5);
     // z4' = 3t0 - 2z4;  z5' = 3t1 + 2z5
-    fp2_sub(z, t0, z4); fp2_dbl(z, z); fp2_add(r->c0.c1, z, t0);
-    fp2_add(z, t1, z5); fp2_dbl(z, z); fp2_add(r->c1.c2, z, t1);
+    fp2_tri(&r->c0.c1, &t0, &z4, 0);
+    fp2_tri(&r->c1.c2, &t1, &z5, 1);
     // z2' = 3 xi t3 + 2z2;  z3' = 3t2 - 2z3
     fp2_mul_nr(t3, t3);
-    fp2_add(z, t3, z2); fp2_dbl(z, z); fp2_add(r->c1.c0, z, t3);
-    fp2_sub(z, t2, z3); fp2_dbl(z, z); fp2_add(r->c0.c2, z, t2);
+    fp2_tri(&r->c1.c0, &t3, &z2, 1);
+    fp2_tri(&r->c0.c2, &t2, &z3, 0);
 }
 
 }  // namespace b381

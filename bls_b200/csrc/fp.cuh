@@ -305,6 +305,17 @@ HDN fp fp_dot2_v(fp a, fp b, fp c, fp d) {
 #endif
     return r;
 }
+// the same with operands and result in memory: the caller passes five pointers instead of marshalling 48 registers in and 12
+// out around every call (fp2_mul shrinks from 158 to ~40 instructions; the kernels are instruction-cache bound)
+HDN void fp_dot2_p(fp *r, const fp *a, const fp *b, const fp *c, const fp *d) {
+#if defined(__CUDA_ARCH__)
+    fp x = *a, y = *b, z = *c, w = *d, o;
+    fp_dot2_inl(o, x, y, z, w);
+    *r = o;
+#else
+    *r = fp_dot2_v(*a, *b, *c, *d);
+#endif
+}
 HD void fp_mul(fp &r, const fp &a, const fp &b) { r = fp_mul_v(a, b); }
 HD void fp_sqr(fp &r, const fp &a) { r = fp_mul_v(a, a); }   // fq.go:151-198
 

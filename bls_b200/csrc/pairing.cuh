@@ -120,17 +120,16 @@ HD void miller_loop_one(fp12 *f, const g1_affine_pod *P, const g2_affine_pod *Q)
     fp2 c0, c1, c2;
     const uint64_t xr = 0xd201000000010000ULL >> 1;   // blsX >> 1, g2.go:634, pairing.go:44-45
 #pragma unroll 1
-    for (int bit = 61; bit >= 0; bit--) {              // the 62 bits below the leading one
+    for (int bit = 61; bit >= -1; bit--) {             // the 62 bits below the leading one, then the closing doubling step
         line_double(&r, &c0, &c1, &c2);
         ell(f, &c0, &c1, &c2, &px, &py);
+        if (bit < 0) break;                            // (one copy of the step code: the kernel is instruction-cache bound)
         if ((xr >> bit) & 1) {
             line_add(&r, &qx, &qy, &c0, &c1, &c2);
             ell(f, &c0, &c1, &c2, &px, &py);
         }
         fp12_sqr(f, f);
     }
-    line_double(&r, &c0, &c1, &c2);
-    ell(f, &c0, &c1, &c2, &px, &py);
     fp12_conj(f, f);                                    // blsIsNegative, pairing.go:71-73
 }
 

@@ -103,9 +103,13 @@ HDN void fp_inv(fp *r, const fp *a) {
 }
 
 // ---- Fq2 (fq2.go) ----------------------------------------------------------------------------
-HD void fp2_add(fp2 &r, const fp2 &a, const fp2 &b) { fpv_add(&r.c0, &a.c0, &b.c0, 2); }  // fq2.go:104-107
-HD void fp2_sub(fp2 &r, const fp2 &a, const fp2 &b) { fpv_sub(&r.c0, &a.c0, &b.c0, 2); }  // fq2.go:110-113
-HD void fp2_dbl(fp2 &r, const fp2 &a) { fpv_dbl(&r.c0, &a.c0, 2); }                       // fq2.go:92-95
+// three-pointer entry points: ~170 call sites in the Miller loop each save the two constant arguments (length, mode) --
+// the kernel sits at the instruction-cache limit and call-site code is most of what is not a multiplier
+HDN void fp2_add_p(fp2 *r, const fp2 *a, const fp2 *b) { fpv_addsub(&r->c0, &a->c0, &b->c0, 2, 0); }
+HDN void fp2_sub_p(fp2 *r, const fp2 *a, const fp2 *b) { fpv_addsub(&r->c0, &a->c0, &b->c0, 2, 1); }
+HD void fp2_add(fp2 &r, const fp2 &a, const fp2 &b) { fp2_add_p(&r, &a, &b); }            // fq2.go:104-107
+HD void fp2_sub(fp2 &r, const fp2 &a, const fp2 &b) { fp2_sub_p(&r, &a, &b); }            // fq2.go:110-113
+HD void fp2_dbl(fp2 &r, const fp2 &a) { fp2_add_p(&r, &a, &a); }                          // fq2.go:92-95
 HD void fp2_neg(fp2 &r, const fp2 &a) { fpv_neg(&r.c0, &a.c0, 2); }                       // fq2.go:98-101
 HD void fp2_conj(fp2 &r, const fp2 &a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }
 HD bool fp2_is_zero(const fp2 &a) { return fp_is_zero(a.c0) && fp_is_zero(a.c1); }
@@ -124,11 +128,11 @@ HD void fp2_mul_nr(fp2 &r, const fp2 &a) { fp2_mul_nr_p(&r, &a); }
 // r = a * b   (fq2.go:116-130: same value; the two rows are two-product dot products with one reduction each,
 // 888 wide MACs and no Karatsuba fix-up additions instead of 900 + five additions)
 HDN void fp2_mul(fp2 *r, const fp2 *a, const fp2 *b) {
-    fp a0 = a->c0, a1 = a->c1, b0 = b->c0, b1 = b->c1, nb1;
+    fp nb1, b1 = b->c1, c0;
     fp_qminus(nb1, b1);
-    fp c0 = fp_dot2_v(a0, b0, a1, nb1);
-    fp c1 = fp_dot2_v(a0, b1, a1, b0);
-    r->c0 = c0; r->c1 = c1;
+    fp_dot2_p(&c0, &a->c0, &b->c0, &a->c1, &nb1);      // c0 is a temporary: r may alias a or b
+    fp_dot2_p(&r->c1, &a->c0, &b->c1, &a->c1, &b->c0);
+    r->c0 = c0;
 }
 // r = a^2   (fq2.go:75-89; complex squaring, 2 Fq mul; the operand sums stay unreduced, below 2Q)
 HDN void fp2_sqr(fp2 *r, const fp2 *a) {

@@ -408,22 +408,24 @@ HDN void fp2_tri(fp2 *r, const fp2 *t, const fp2 *z, int plus) {
     }
 }
 HDN void fp12_cyclotomic_sqr(fp12 *r, const fp12 *a) {
+    // z0 = a.c0.c0, z4 = a.c0.c1, z3 = a.c0.c2, z2 = a.c1.c0, z1 = a.c1.c1, z5 = a.c1.c2.  In place (r == a) without copies:
+    // every output row is written to the slot its own z operand is read from (fp2_tri reads before it writes), and the two
+    // Fp4 squarings whose outputs cross (z2,z3 -> z4',z5' and z4,z5 -> z2',z3') are both finished before either is written.
     fp2 t0, t1, t2, t3;
-    fp2 z0 = a->c0.c0, z4 = a->c0.c1, z3 = a->c0.c2, z2 = a->c1.c0, z1 = a->c1.c1, z5 = a->c1.c2;
     // (t0,t1) = fp4sq(z0,z1);  z0' = 3t0 - 2z0;  z1' = 3t1 + 2z1
-    fp4_sqr(t0, t1, z0, z1);
-    fp2_tri(&r->c0.c0, &t0, &z0, 0);
-    fp2_tri(&r->c1.c1, &t1, &z1, 1);
+    fp4_sqr(t0, t1, a->c0.c0, a->c1.c1);
+    fp2_tri(&r->c0.c0, &t0, &a->c0.c0, 0);
+    fp2_tri(&r->c1.c1, &t1, &a->c1.c1, 1);
     // (t0,t1) = fp4sq(z2,z3); (t2,t3) = fp4sq(z4,z5)
-    fp4_sqr(t0, t1, z2, z3);
-    fp4_sqr(t2, t3, z4, z5);
+    fp4_sqr(t0, t1, a->c1.c0, a->c0.c2);
+    fp4_sqr(t2, t3, a->c0.c1, a->c1.c2);
     // z4' = 3t0 - 2z4;  z5' = 3t1 + 2z5
-    fp2_tri(&r->c0.c1, &t0, &z4, 0);
-    fp2_tri(&r->c1.c2, &t1, &z5, 1);
+    fp2_tri(&r->c0.c1, &t0, &a->c0.c1, 0);
+    fp2_tri(&r->c1.c2, &t1, &a->c1.c2, 1);
     // z2' = 3 xi t3 + 2z2;  z3' = 3t2 - 2z3
     fp2_mul_nr(t3, t3);
-    fp2_tri(&r->c1.c0, &t3, &z2, 1);
-    fp2_tri(&r->c0.c2, &t2, &z3, 0);
+    fp2_tri(&r->c1.c0, &t3, &a->c1.c0, 1);
+    fp2_tri(&r->c0.c2, &t2, &a->c0.c2, 0);
 }
 
 }  // namespace b381

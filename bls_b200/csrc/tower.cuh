@@ -199,19 +199,18 @@ HDN void fp6_mul(fp6 *r, const fp6 *a, const fp6 *b) {
     fp2_sub(y, y, v1);
     fp2_mul_nr(s, v2);
     fp2_add(y, y, s);
-    // c2 = (a0+a2)(b0+b2) - v0 - v2 + v1
-    fp2 z;
+    // c2 = (a0+a2)(b0+b2) - v0 - v2 + v1: the last use of a and b, so it can go straight to r->c2 even when r aliases them
     fp2_add(s, a->c0, a->c2);
     fp2_add(t, b->c0, b->c2);
-    fp2_mul(&z, &s, &t);
-    fp2_sub(z, z, v0);
-    fp2_sub(z, z, v2);
-    fp2_add(z, z, v1);
-    r->c0 = x; r->c1 = y; r->c2 = z;
+    fp2_mul(&r->c2, &s, &t);
+    fp2_sub(r->c2, r->c2, v0);
+    fp2_sub(r->c2, r->c2, v2);
+    fp2_add(r->c2, r->c2, v1);
+    r->c0 = x; r->c1 = y;
 }
 // r = a * (b0 + b1 v)   (fq6.go:60-90; 5 Fq2 mul)
 HDN void fp6_mul_by_01(fp6 *r, const fp6 *a, const fp2 *b0, const fp2 *b1) {
-    fp2 v0, v1, s, t, x, y, z;
+    fp2 v0, v1, s, t, x, y;
     fp2_mul(&v0, &a->c0, b0);
     fp2_mul(&v1, &a->c1, b1);
     // c0 = v0 + xi*((a1+a2)*b1 - v1)
@@ -226,12 +225,12 @@ HDN void fp6_mul_by_01(fp6 *r, const fp6 *a, const fp2 *b0, const fp2 *b1) {
     fp2_mul(&y, &s, &t);
     fp2_sub(y, y, v0);
     fp2_sub(y, y, v1);
-    // c2 = (a0+a2)*b0 - v0 + v1
+    // c2 = (a0+a2)*b0 - v0 + v1 (last use of a: straight to r->c2)
     fp2_add(s, a->c0, a->c2);
-    fp2_mul(&z, &s, b0);
-    fp2_sub(z, z, v0);
-    fp2_add(z, z, v1);
-    r->c0 = x; r->c1 = y; r->c2 = z;
+    fp2_mul(&r->c2, &s, b0);
+    fp2_sub(r->c2, r->c2, v0);
+    fp2_add(r->c2, r->c2, v1);
+    r->c0 = x; r->c1 = y;
 }
 // r = a * (b1 v)   (fq6.go:40-57; 3 Fq2 mul)
 HDN void fp6_mul_by_1(fp6 *r, const fp6 *a, const fp2 *b1) {
@@ -383,15 +382,15 @@ HDN void fp12_frobenius(fp12 *r, const fp12 *a, int power) {
 // exponentiation (pairing.go:80-90).  Same value as fq12.go:180-195 on such inputs at 18 Fq mul
 // instead of 36; the reference squares generically inside FQ12.Exp (fq12.go:108-120).
 HD void fp4_sqr(fp2 &o0, fp2 &o1, const fp2 &a, const fp2 &b) {
-    fp2 t0, t1, s;
-    fp2_sqr(&t0, &a);
+    fp2 t1;                       // the outputs double as the other two temporaries: 96 B of hot stack instead of 288 B
+    fp2_sqr(&o0, &a);
     fp2_sqr(&t1, &b);
-    fp2_add(s, a, b);
-    fp2_sqr(&s, &s);
-    fp2_sub(s, s, t0);
-    fp2_sub(o1, s, t1);          // 2ab
+    fp2_add(o1, a, b);
+    fp2_sqr(&o1, &o1);
+    fp2_sub(o1, o1, o0);
+    fp2_sub(o1, o1, t1);          // 2ab
     fp2_mul_nr(t1, t1);
-    fp2_add(o0, t0, t1);          // a^2 + xi b^2
+    fp2_add(o0, o0, t1);          // a^2 + xi b^2
 }
 // r = 3t - 2z (plus = 0) or 3t + 2z (plus = 1): the six output rows of the cyclotomic squaring as ONE pass each (three
 // separate add/sub/double passes cost three local-memory round trips per row)

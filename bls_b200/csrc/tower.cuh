@@ -397,12 +397,14 @@ HD void fp4_sqr(fp2 &o0, fp2 &o1, const fp2 &a, const fp2 &b) {
     fp2 t1;                       // the outputs double as the other two temporaries: 96 B of hot stack instead of 288 B
     fp2_sqr(&o0, &a);
     fp2_sqr(&t1, &b);
-    fp2_add(o1, a, b);
+    // (direct calls of the add/sub loop: this runs in the final-exponentiation kernel, where the extra hop through the
+    // three-pointer entry points costs more than their smaller call sites save)
+    fpv_add(&o1.c0, &a.c0, &b.c0, 2);
     fp2_sqr(&o1, &o1);
-    fp2_sub(o1, o1, o0);
-    fp2_sub(o1, o1, t1);          // 2ab
+    fpv_sub(&o1.c0, &o1.c0, &o0.c0, 2);
+    fpv_sub(&o1.c0, &o1.c0, &t1.c0, 2);          // 2ab
     fp2_mul_nr(t1, t1);
-    fp2_add(o0, o0, t1);          // a^2 + xi b^2
+    fpv_add(&o0.c0, &o0.c0, &t1.c0, 2);          // a^2 + xi b^2
 }
 // r = 3t - 2z (plus = 0) or 3t + 2z (plus = 1): the six output rows of the cyclotomic squaring as ONE pass each (three
 // separate add/sub/double passes cost three local-memory round trips per row)

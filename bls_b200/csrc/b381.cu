@@ -206,6 +206,14 @@ enum { VM_ML1 = 0, VM_FE_A = 1, VM_FE_C = 2 };
         }                                                                                             \
     } while (0)
 
+// Grow-only device scratch, one slot per role so that nested entry points never alias each other's buffers:
+//    0  Miller values (n x Fq12)            1  group products (ngroups x Fq12)      2, 3  staged / assembled pairs (G1, G2)
+//    4  partial sums of the point-sum kernels   5  MSM work area (counts, offsets, indices, chunk / segment / window sums)
+//    6  group offsets of assembled checks   7  staged sum / MSM results             8-11  VM: norms, spill, input copy, ok flags
+//   12-14  codec / hash host staging (encoded bytes or messages, decoded points, status or scalars or offsets)
+//   15-18  wire-level verify: decoded keys, decoded signatures, message points, status + validity bytes
+//   19, 20  wire-level verify host staging (inputs, verdicts)                       21  largest group size (tree product)
+//   22  group offsets of the random-linear-combination check                        23  its G2 sum + "any invalid" flag
 static int scratch_get(b381_ctx *ctx, int slot, size_t bytes, void **out) {
     if (ctx->scratch_bytes[slot] < bytes) {
         if (ctx->scratch[slot]) {

@@ -133,8 +133,23 @@ HDN bool fp_sqrt(fp *out, const fp *a) {
     fp_mul(*out, a1, *a);
     return true;
 }
-// FQ2.Sqrt (fq2.go:198-232; Algorithm 9 of eprint 2012/685)
-HDN bool fp2_sqrt(fp2 *out, const fp2 *a) {
+// r = a / 2: (a + (a odd ? Q : 0)) >> 1, valid on the Montgomery representative as well
+HD void fp_half(fp &r, const fp &a) {
+    const uint32_t q[12] = {B381_Q_LIMBS};
+    uint32_t m = 0u - (a.l[0] & 1u), t[13];
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        uint64_t v = (uint64_t)a.l[i] + (q[i] & m) + c;
+        t[i] = (uint32_t)v;
+        c = v >> 32;
+    }
+    t[12] = (uint32_t)c;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = (t[i] >> 1) | (t[i + 1] << 31);
+}
+// FQ2.Sqrt (fq2.go:198-232; Algorithm 9 of eprint 2012/685), the form the reference runs: two Fq2 exponentiations
+HDN bool fp2_sqrt_alg9(fp2 *out, const fp2 *a) {
     if (fp2_is_zero(*a)) { fp2_set_zero(*out); return true; }
     fp2 a1, alpha, a0, neg1;
     field_pow<Fp2Out>(&a1, a, B381_TAB(qm3o4));
@@ -157,6 +172,35 @@ HDN bool fp2_sqrt(fp2 *out, const fp2 *a) {
     fp2_add(alpha, alpha, one);
     field_pow<Fp2Out>(&alpha, &alpha, B381_TAB(qm1o2));
     fp2_mul(out, &alpha, &a1);
+    return true;
+}
+// A square root of a in Fq2 = Fq[u]/(u^2 + 1) through the norm, two Fq exponentiations instead of two Fq2 ones:
+//   n = a0^2 + a1^2 must be a square s^2 in Fq (else a is a non-square);  t = (a0 + s) / 2;  w = t^((Q-3)/4);  x = w t
+//   w^2 t = +1:  (x, a1 w / 2)^2 = a          w^2 t = -1 (t a non-residue, -1 being one):  (a1 w / 2, -x)^2 = a
+// The root may be the negative of the one FQ2.Sqrt returns; every caller in the reference normalises the sign afterwards
+// (GetG2PointFromX g2.go:247-262, HashG2WithDomain g2.go:1066-1070, the SWU sign rule g2.go:1024-1027), which is why the
+// results stay bit-identical (tests compare with fp2_sqrt_alg9 up to sign and with the oracle end to end).
+// second half, given s with s^2 = a0^2 + a1^2 and a1 != 0
+HDN void fp2_sqrt_from_norm_root(fp2 *out, const fp2 *a, const fp *sp) {
+    fp t, w, x, c, one;
+    fp_add(t, a->c0, *sp);
+    fp_half(t, t);
+    field_pow<FpInl>(&w, &t, B381_TAB(qm3o4));
+    fp_mul(x, w, t);
+    fp_mul(c, w, x);                           // t^((Q-1)/2)
+    fp_mul(w, w, a->c1);
+    fp_half(w, w);
+    fp_set_one(one);
+    if (fp_eq(c, one)) { out->c0 = x; out->c1 = w; }
+    else { out->c0 = w; fp_neg(out->c1, x); }
+}
+HDN bool fp2_sqrt(fp2 *out, const fp2 *a) {
+    if (fp_is_zero(a->c1)) return fp2_sqrt_alg9(out, a);
+    fp n, s;
+    fp_sqr(n, a->c0); fp_sqr(s, a->c1);
+    fp_add(n, n, s);
+    if (!fp_sqrt(&s, &n)) return false;
+    fp2_sqrt_from_norm_root(out, a, &s);
     return true;
 }
 

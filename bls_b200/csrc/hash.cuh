@@ -23,12 +23,14 @@ namespace b381 {
 __device__ __constant__ uint32_t d_g2_cofactor[16] = {B381_G2_COFACTOR_LIMBS};
 __device__ __constant__ uint32_t d_g2_cof_pos[16] = {B381_G2_COFACTOR_NAF_POS_LIMBS};
 __device__ __constant__ uint32_t d_g2_cof_neg[16] = {B381_G2_COFACTOR_NAF_NEG_LIMBS};
+__device__ __constant__ uint32_t d_kh2_naf[24] = B381_KH2_DIGITS_NAF_INIT;
 __device__ __constant__ uint32_t d_sha_k[64] = {B381_SHA_K};
 #endif
 #if !defined(__CUDA_ARCH__)
 static const uint32_t h_g2_cofactor[16] = {B381_G2_COFACTOR_LIMBS};
 static const uint32_t h_g2_cof_pos[16] = {B381_G2_COFACTOR_NAF_POS_LIMBS};
 static const uint32_t h_g2_cof_neg[16] = {B381_G2_COFACTOR_NAF_NEG_LIMBS};
+static const uint32_t h_kh2_naf[24] = B381_KH2_DIGITS_NAF_INIT;
 static const uint32_t h_sha_k[64] = {B381_SHA_K};
 #endif
 
@@ -74,6 +76,75 @@ HD void fp_from_digest(fp &r, const uint32_t dg[8]) {
 }
 
 // HashG2WithDomain(messageHash, domain) as an affine point
+// psi on an XYZZ point: conjugate every coordinate, scale X and Y (the affine map of hash.go:341-366)
+HD void g2_psi_xyzz(xyzz<Fp2Out> &p) {
+    fp2 t;
+    g2_psi(t, p.y, p.x, p.y);
+    p.x = t;
+    fp2_conj(p.zz, p.zz);
+    fp2_conj(p.zzz, p.zzz);
+}
+// clearH2 (hash.go:368-389)
+HDN void g2_clear_h2(xyzz<Fp2Out> &acc, const fp2 &x, const fp2 &y) {
+    xyzz<Fp2Out> a, d;
+    fp2 px, py, ny;
+    point_mul<Fp2Out>(&a, &x, &y, B381_TAB(bls_x), 2);       // work = [x]P
+    xyzz_madd(a, x, y);                                 //      + P
+    g2_psi(px, py, x, y);
+    fp2_neg(py, py);                                    // minusPsiP
+    xyzz_madd(a, px, py);                               //      - psi(P)
+    // work = [x]work: double-and-add with a projective base
+    xyzz<Fp2Out> b;
+    xyzz_set_inf(b);
+    const uint32_t *k = B381_TAB(bls_x);
+#pragma unroll 1
+    for (int i = 63; i >= 0; i--) {
+        xyzz_dbl(b);
+        if ((k[i >> 5] >> (i & 31)) & 1) xyzz_add(b, a);
+    }
+    xyzz_madd(b, px, py);                               //      - psi(P)
+    fp2_neg(ny, y);
+    xyzz_madd(b, x, ny);                                //      - P
+    xyzz_dbl_affine(d, x, y);                           // psi(psi(2P))
+    g2_psi_xyzz(d); g2_psi_xyzz(d);
+    xyzz_add(b, d);
+    acc = b;
+}
+// ScaleByCofactor (g2.go:1041-1085 -> [h2] P, a 507-bit scalar) through the 64-bit endomorphism ladder:
+//   [h2] P = [k] Q,  Q = clearH2(P) = [3 (x^2 - 1) h2] P,  k = (3 (x^2 - 1))^-1 mod r          ([h2] P has order r)
+//   [k] Q  = [d0] Q - [d1] psi(Q) + [d2] psi^2(Q) - [d3] psi^3(Q),  k = sum d_i |x|^i           (psi = [x] = [-|x|] on G2)
+// Q is normalised once so that the four bases are affine (psi maps affine coordinates to affine coordinates) and the
+// ladder is 65 Jacobian doublings + 85 mixed additions (the d_i in non-adjacent form) instead of 508 + 176.
+// B381_COFACTOR_LADDER selects the plain [h2] ladder (tests compare both with the oracle).
+HDN void g2_scale_by_cofactor(xyzz<Fp2Out> *acc, const fp2 *px, const fp2 *py) {
+#if defined(B381_COFACTOR_LADDER)
+    point_mul_naf<Fp2Out>(acc, px, py, B381_TAB(g2_cof_pos), B381_TAB(g2_cof_neg), 16);
+#else
+    g2_clear_h2(*acc, *px, *py);
+    if (xyzz_is_inf(*acc)) return;
+    fp2 bx[4], by[4];
+    xyzz_to_affine<Fp2Out>(bx[0], by[0], *acc);
+    for (int i = 1; i < 4; i++) {
+        g2_psi(bx[i], by[i], bx[i - 1], by[i - 1]);    // B_i = -psi(B_{i-1}) = (-1)^i psi^i(Q)
+        fp2_neg(by[i], by[i]);
+    }
+    jac_pt<Fp2Out> a;
+    fp2_set_one(a.x); fp2_set_one(a.y); fp2_set_zero(a.z);
+    const uint32_t *tab = B381_TAB(kh2_naf);
+#pragma unroll 1
+    for (int j = 64; j >= 0; j--) {
+        jac_dbl(a);
+#pragma unroll 1
+        for (int i = 0; i < 4; i++) {
+            uint32_t pos = (tab[6 * i + (j >> 5)] >> (j & 31)) & 1, neg = (tab[6 * i + 3 + (j >> 5)] >> (j & 31)) & 1;
+            if (pos) jac_madd(a, bx[i], by[i]);
+            else if (neg) { fp2 ny; fp2_neg(ny, by[i]); jac_madd(a, bx[i], ny); }
+        }
+    }
+    jac_to_xyzz(*acc, a);
+#endif
+}
+
 HD void hash_g2_with_domain_one(g2_affine_pod *out, const uint8_t *msg32, const uint8_t *domain8) {
     uint8_t buf[41];
     uint32_t dg[8];
@@ -85,26 +156,25 @@ HD void hash_g2_with_domain_one(g2_affine_pod *out, const uint8_t *msg32, const 
     G2Codec::b_coeff(b);
     fp2_set_one(one);
     // FQ2.Sqrt fails exactly when x^3 + b is a non-square, i.e. when its norm is a non-residue of Fq: one Fq
-    // exponentiation (570 multiplications) per rejected candidate instead of an Fq2 exponentiation (1 330), and the
-    // lanes of a warp leave the divergent search before the expensive root
-    fp m1;
-    fp_load_tab(m1, B381_TAB(neg_one));
+    // exponentiation (570 multiplications) per rejected candidate instead of an Fq2 exponentiation (1 330), the lanes
+    // of a warp leave the divergent search before the rest of the root, and the accepted candidate's norm root is
+    // the first half of that root (fp2_sqrt_from_norm_root)
+    fp n0, n1;
     for (;;) {
         fp2_sqr(&t, &x);
         fp2_mul(&t, &t, &x);
         fp2_add(t, t, b);
-        fp n0, n1;
         fp_sqr(n0, t.c0); fp_sqr(n1, t.c1);
         fp_add(n0, n0, n1);
-        field_pow<FpInl>(&n1, &n0, B381_TAB(qm1o2));       // Euler: -1 for a non-residue (0 and 1 are squares)
-        if (!fp_eq(n1, m1)) break;
+        if (fp_sqrt(&n1, &n0)) break;
         fp2_add(x, x, one);
     }
-    fp2_sqrt(&y, &t);
+    if (fp_is_zero(t.c1)) fp2_sqrt_alg9(&y, &t);
+    else fp2_sqrt_from_norm_root(&y, &t, &n1);
     fp2_neg(t, y);
     if (!(fp2_cmp(y, t) > 0)) y = t;                   // "favor the lower y value": keep the one with Parity() true
     xyzz<Fp2Out> acc;
-    point_mul_naf<Fp2Out>(&acc, &x, &y, B381_TAB(g2_cof_pos), B381_TAB(g2_cof_neg), 16);
+    g2_scale_by_cofactor(&acc, &x, &y);
     if (xyzz_is_inf(acc)) { fp2_set_zero(x); fp2_set_one(y); G2Codec::store(out, x, y, true); return; }
     xyzz_to_affine<Fp2Out>(x, y, acc);
     G2Codec::store(out, x, y, false);

@@ -137,40 +137,8 @@ struct G2Swu : G2Codec {
     }
     static HD void iso_coeff(T &c, int idx) { fp_load_tab(c.c0, B381_TAB(iso3) + 24 * idx); fp_load_tab(c.c1, B381_TAB(iso3) + 24 * idx + 12); }
     static HD int iso_len(int m) { const int l[4] = {B381_ISO3_LENS}; return l[m]; }
-    // psi on an XYZZ point: conjugate every coordinate, scale X and Y (the affine map of hash.go:341-366)
-    static HD void psi_xyzz(xyzz<F> &p) {
-        fp2 t;
-        g2_psi(t, p.y, p.x, p.y);
-        p.x = t;
-        fp2_conj(p.zz, p.zz);
-        fp2_conj(p.zzz, p.zzz);
-    }
     // clearH2 (hash.go:368-389)
-    static HD void clear_h(xyzz<F> &acc, const T &x, const T &y) {
-        xyzz<F> a, d;
-        T px, py, ny;
-        point_mul<F>(&a, &x, &y, B381_TAB(bls_x), 2);       // work = [x]P
-        xyzz_madd(a, x, y);                                 //      + P
-        g2_psi(px, py, x, y);
-        fp2_neg(py, py);                                    // minusPsiP
-        xyzz_madd(a, px, py);                               //      - psi(P)
-        // work = [x]work: double-and-add with a projective base
-        xyzz<F> b;
-        xyzz_set_inf(b);
-        const uint32_t *k = B381_TAB(bls_x);
-#pragma unroll 1
-        for (int i = 63; i >= 0; i--) {
-            xyzz_dbl(b);
-            if ((k[i >> 5] >> (i & 31)) & 1) xyzz_add(b, a);
-        }
-        xyzz_madd(b, px, py);                               //      - psi(P)
-        fp2_neg(ny, y);
-        xyzz_madd(b, x, ny);                                //      - P
-        xyzz_dbl_affine(d, x, y);                           // psi(psi(2P))
-        psi_xyzz(d); psi_xyzz(d);
-        xyzz_add(b, d);
-        acc = b;
-    }
+    static HD void clear_h(xyzz<F> &acc, const T &x, const T &y) { g2_clear_h2(acc, x, y); }
 };
 
 // simplified SWU onto y^2 = x^3 + A x + B (optimizedSWUMapHelper g1.go:628-714, OptimizedSWU2MapHelper g2.go:933-1031)

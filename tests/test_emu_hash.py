@@ -94,3 +94,58 @@ def test_hash_g1_g2_kats_and_host(emu, orc, kats):
     assert o2.tobytes() == hg.g2_points([hm.hash_g2(m) for m in msgs]).tobytes()
     for i in range(len(msgs)):
         assert orc.g1.in_subgroup(o1[i:i + 1]) and orc.g2.in_subgroup(o2[i:i + 1])
+
+
+def test_scale_by_cofactor_endomorphism_ladder(emu):
+    """[h2] P (ScaleByCofactor, g2.go:133,1041-1085) through clearH2 and the base-|x| psi ladder equals the plain 507-bit
+    ladder and the host restatement on curve points outside G2, inside G2 and inside the cofactor subgroup"""
+    rng = np.random.RandomState(77)
+    pts = []
+    while len(pts) < 4:
+        x = (int.from_bytes(rng.bytes(47), "big"), int.from_bytes(rng.bytes(47), "big"))
+        y = hm.fq2_sqrt(hm._Fq2.add(hm._Fq2.mul(hm._Fq2.sqr(x), x), (4, 4)))
+        if y is not None:
+            pts.append((x, y))
+    torsion = hm.g2_mul(pts[0], hm.G2_COFACTOR)                  # a point of G2
+    low = hm.g2_mul(pts[1], hm.R_ORDER)                           # order divides h2: [h2] low = O
+    assert hm.g2_in_subgroup(torsion) and low is not None
+    pts += [torsion, hm.g2_neg(torsion), low]
+    src = hg.g2_points(pts)
+    want = hg.g2_points([hm.g2_mul(p, hm.G2_COFACTOR) for p in pts])
+    assert want["inf"][-1] == 1
+    for which in (0, 1):
+        out = np.zeros(len(pts), dtype=L.G2_AFFINE)
+        emu.emu_g2_scale_by_cofactor(which, _p(src), ctypes.c_size_t(len(pts)), _p(out))
+        assert out.tobytes() == want.tobytes(), which
+
+
+def test_fp2_sqrt_norm_method(emu):
+    """fp2_sqrt (two Fq exponentiations through the norm) against FQ2.Sqrt (fq2.go:198-232) as the host restatement and
+    the device's own Algorithm 9: same verdict, and the same root up to the sign every caller normalises"""
+    rng = np.random.RandomState(5)
+    rnd = lambda: int.from_bytes(rng.bytes(47), "big")
+    vals = [(rnd(), rnd()) for _ in range(12)]
+    vals += [hm._Fq2.sqr(v) for v in vals[:4]]                                # certain squares
+    vals += [(0, 0), (1, 0), (hm.Q - 1, 0), (4, 0), (5, 0), (0, 1), (0, hm.Q - 1), (0, rnd()), (rnd(), 0), (3, 4)]
+    a = np.zeros((len(vals), 12), np.uint64)
+    for i, (c0, c1) in enumerate(vals):
+        a[i, :6] = L.fp_from_int(c0); a[i, 6:] = L.fp_from_int(c1)
+    res = []
+    for which in (0, 1):
+        out = np.zeros_like(a); ok = np.zeros(len(vals), np.uint8)
+        emu.emu_fp2_sqrt(which, _p(a), ctypes.c_size_t(len(vals)), _p(out), _p(ok))
+        res.append((out, ok))
+    assert res[0][1].tolist() == res[1][1].tolist()
+    seen = set()
+    for i, v in enumerate(vals):
+        want = hm.fq2_sqrt(v)
+        assert (want is not None) == bool(res[0][1][i]), v
+        if want is None:
+            continue
+        got = (L.fp_to_int(res[0][0][i, :6]), L.fp_to_int(res[0][0][i, 6:]))
+        ref = (L.fp_to_int(res[1][0][i, :6]), L.fp_to_int(res[1][0][i, 6:]))
+        assert ref == want
+        assert got in (want, hm.fq2_neg(want)), v
+        assert hm._Fq2.sqr(got) == (v[0] % hm.Q, v[1] % hm.Q)
+        seen.add(got == want)
+    assert len(vals) - int(res[0][1].sum()) >= 3                             # non-squares were exercised

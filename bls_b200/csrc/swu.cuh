@@ -141,93 +141,126 @@ struct G2Swu : G2Codec {
     static HD void clear_h(xyzz<F> &acc, const T &x, const T &y) { g2_clear_h2(acc, x, y); }
 };
 
-// simplified SWU onto y^2 = x^3 + A x + B (optimizedSWUMapHelper g1.go:628-714, OptimizedSWU2MapHelper g2.go:933-1031)
-template <class S> HDN void swu_map(typename S::T *ox, typename S::T *oy, const typename S::T *tp) {
+// simplified SWU onto y^2 = x^3 + A x + B (optimizedSWUMapHelper g1.go:628-714, OptimizedSWU2MapHelper g2.go:933-1031), split
+// around its one inversion so that the two maps of a hash share a single inversion (Montgomery's trick):
+//   swu_prepare: u = xi t^2, common = u^2 + u, den = A common (xi A when common = 0)    -- den is never zero
+//   swu_finish : x0 = -B (common + 1) / den (B / den when common = 0), the candidate test and the root
+template <class S> struct swu_state { typename S::T t, u, common, den; };
+template <class S> HDN void swu_prepare(swu_state<S> *st, const typename S::T *tp) {
     typedef typename S::T T;
     typedef typename S::F F;
-    T t = *tp, A, B, t2, common, x0, gx, y, u, v, one;
+    T A, t2;
+    S::ell_a(A);
+    st->t = *tp;
+    F::sqr(t2, st->t);
+    S::mul_nqr(st->u, t2);                 // xi t^2
+    F::sqr(st->common, st->u);             // xi^2 t^4
+    F::add(st->common, st->common, st->u);
+    if (F::is_zero(st->common)) S::mul_nqr(st->den, A);
+    else F::mul(st->den, A, st->common);
+}
+template <class S> HDN void swu_finish(typename S::T *ox, typename S::T *oy, const swu_state<S> *st, const typename S::T *inv_den) {
+    typedef typename S::T T;
+    typedef typename S::F F;
+    T A, B, x0, gx, y, v, one;
     S::ell_a(A); S::ell_b(B);
-    F::set_one(one);
-    F::sqr(t2, t);
-    S::mul_nqr(u, t2);                     // xi t^2
-    F::sqr(common, u);                     // xi^2 t^4
-    F::add(common, common, u);
-    if (F::is_zero(common)) {              // x0 = B / (xi A)
-        S::mul_nqr(v, A);
-        F::inv(v, v);
-        F::mul(x0, B, v);
+    if (F::is_zero(st->common)) {          // x0 = B / (xi A)
+        F::mul(x0, B, *inv_den);
     } else {                               // x0 = -B (common + 1) / (A common)
-        F::mul(v, A, common);
-        F::inv(v, v);
-        F::add(common, common, one);
+        F::set_one(one);
+        F::add(v, st->common, one);
         F::neg(gx, B);
-        F::mul(x0, gx, common);
-        F::mul(x0, x0, v);
+        F::mul(x0, gx, v);
+        F::mul(x0, x0, *inv_den);
     }
     F::sqr(gx, x0);
     F::mul(gx, gx, x0);
     F::mul(v, A, x0);
     F::add(gx, gx, v);
     F::add(gx, gx, B);                     // g(x0)
-    bool ok = S::sqrt(&y, &gx);
-    if (ok) { F::sqr(v, y); ok = S::eq(v, gx); }
-    if (!ok) {                             // x1 = xi t^2 x0, g(x1) = xi^3 t^6 g(x0)
-        F::mul(x0, u, x0);
+    // the reference takes sqrt(g(x0)) and falls back to x1 when it fails; which of the two happens is decided here by a
+    // Jacobi symbol, so that every lane of the warp runs ONE square root, on its own candidate
+    if (!S::is_square(gx)) {               // x1 = xi t^2 x0, g(x1) = xi^3 t^6 g(x0)
+        F::mul(x0, st->u, x0);
         F::sqr(gx, x0);
         F::mul(gx, gx, x0);
         F::mul(v, A, x0);
         F::add(gx, gx, v);
         F::add(gx, gx, B);
-        S::sqrt(&y, &gx);
     }
-    if (S::sign(t) != S::sign(y)) F::neg(y, y);
+    S::sqrt(&y, &gx);
+    if (S::sign(st->t) != S::sign(y)) F::neg(y, y);
     *ox = x0; *oy = y;
 }
-// rational map (xNum/xDen, y yNum/yDen) by Horner (iso11 hash.go:185-203, iso3 hash.go:282-303)
-template <class S> HDN void iso_map(typename S::T *px, typename S::T *py) {
+// The rational map (xNum/xDen, y yNum/yDen) (iso11 hash.go:185-203, iso3 hash.go:282-303) applied to a finite XYZZ point
+// (x = X/ZZ, y = Y/ZZZ) without normalising it first: each polynomial p of degree d is evaluated in homogeneous form,
+//   P = ZZ^d p(X/ZZ) = sum c_i X^i ZZ^(d-i)   (Horner: acc = acc X + c_(d-k) ZZ^k, the powers of ZZ shared by the four),
+// so that x' = P0 / (P1 ZZ^(d0-d1)), y' = Y P2 / (ZZZ P3 ZZ^(d2-d3)) and ONE inversion yields the affine image -- the same
+// field elements as ToAffine followed by the affine map.
+template <class S> HDN void iso_map_xyzz(typename S::T *ox, typename S::T *oy, const xyzz<typename S::F> *p) {
     typedef typename S::T T;
     typedef typename S::F F;
-    T x = *px, v[4], c;
-    int base = 0;
-#pragma unroll 1
+    T acc[4], pw, c;
+    int deg[4], base[4], maxd = 0, b0 = 0;
     for (int m = 0; m < 4; m++) {
-        int len = S::iso_len(m);
-        S::iso_coeff(v[m], base + len - 1);
-#pragma unroll 1
-        for (int i = len - 2; i >= 0; i--) {
-            F::mul(v[m], v[m], x);
-            S::iso_coeff(c, base + i);
-            F::add(v[m], v[m], c);
-        }
-        base += len;
+        deg[m] = S::iso_len(m) - 1;
+        base[m] = b0;
+        b0 += deg[m] + 1;
+        if (deg[m] > maxd) maxd = deg[m];
+        S::iso_coeff(acc[m], base[m] + deg[m]);
     }
+    pw = p->zz;
+#pragma unroll 1
+    for (int k = 1; k <= maxd; k++) {
+#pragma unroll 1
+        for (int m = 0; m < 4; m++) {
+            if (k > deg[m]) continue;
+            F::mul(acc[m], acc[m], p->x);
+            S::iso_coeff(c, base[m] + deg[m] - k);
+            F::mul(c, c, pw);
+            F::add(acc[m], acc[m], c);
+        }
+        if (k < maxd) F::mul(pw, pw, p->zz);
+    }
+    // balance the powers of ZZ between numerators and denominators (d0 - d1 = 1, d2 = d3 for both curves)
+    for (int k = deg[1]; k < deg[0]; k++) F::mul(acc[1], acc[1], p->zz);
+    for (int k = deg[0]; k < deg[1]; k++) F::mul(acc[0], acc[0], p->zz);
+    for (int k = deg[3]; k < deg[2]; k++) F::mul(acc[3], acc[3], p->zz);
+    for (int k = deg[2]; k < deg[3]; k++) F::mul(acc[2], acc[2], p->zz);
+    F::mul(acc[2], acc[2], p->y);
+    F::mul(acc[3], acc[3], p->zzz);
     // one inversion for both denominators
     T d, di;
-    F::mul(d, v[1], v[3]);
+    F::mul(d, acc[1], acc[3]);
     F::inv(di, d);
-    F::mul(c, di, v[3]);                   // 1 / xDen
-    F::mul(*px, v[0], c);
-    F::mul(c, di, v[1]);                   // 1 / yDen
-    F::mul(c, c, v[2]);
-    F::mul(*py, *py, c);
+    F::mul(c, di, acc[3]);                 // 1 / xDen
+    F::mul(*ox, acc[0], c);
+    F::mul(c, di, acc[1]);                 // 1 / yDen
+    F::mul(*oy, acc[2], c);
 }
-// HashG1(msg) / HashG2(msg) as an affine point
+// HashG1(msg) / HashG2(msg) as an affine point: three inversions (the two SWU maps together, the isogeny, the result)
 template <class S> HD void hash_to_curve_one(typename S::APOD *out, const uint8_t *msg, size_t len) {
     typedef typename S::T T;
     typedef typename S::F F;
     uint32_t mh[8];
     sha256_prefixed(mh, 0x01, msg, len);
-    T t, x1, y1, x2, y2;
+    T t, x1, y1, x2, y2, inv, i1, i2;
+    swu_state<S> s1, s2;
     S::field_of_hash(t, mh, 0);
-    swu_map<S>(&x1, &y1, &t);
+    swu_prepare<S>(&s1, &t);
     S::field_of_hash(t, mh, 1);
-    swu_map<S>(&x2, &y2, &t);
+    swu_prepare<S>(&s2, &t);
+    F::mul(inv, s1.den, s2.den);
+    F::inv(inv, inv);
+    F::mul(i1, inv, s2.den);
+    F::mul(i2, inv, s1.den);
+    swu_finish<S>(&x1, &y1, &s1, &i1);
+    swu_finish<S>(&x2, &y2, &s2, &i2);
     xyzz<F> acc;
     acc.x = x1; acc.y = y1; F::set_one(acc.zz); F::set_one(acc.zzz);
     xyzz_madd(acc, x2, y2);                // Pp.ToProjective().AddAffine(Pp2)
     if (xyzz_is_inf(acc)) { F::set_zero(x1); F::set_one(y1); S::store(out, x1, y1, true); return; }
-    xyzz_to_affine<F>(x1, y1, acc);
-    iso_map<S>(&x1, &y1);
+    iso_map_xyzz<S>(&x1, &y1, &acc);
     S::clear_h(acc, x1, y1);
     if (xyzz_is_inf(acc)) { F::set_zero(x1); F::set_one(y1); S::store(out, x1, y1, true); return; }
     xyzz_to_affine<F>(x1, y1, acc);

@@ -149,3 +149,19 @@ def test_fp2_sqrt_norm_method(emu):
         assert hm._Fq2.sqr(got) == (v[0] % hm.Q, v[1] % hm.Q)
         seen.add(got == want)
     assert len(vals) - int(res[0][1].sum()) >= 3                             # non-squares were exercised
+
+
+def test_fp_is_square_jacobi(emu):
+    """the binary Jacobi symbol against Euler's criterion on random values, small values, powers of two and Q - small"""
+    rng = np.random.RandomState(9)
+    vals = [int.from_bytes(rng.bytes(48), "big") % hm.Q for _ in range(300)]
+    vals += list(range(0, 40)) + [hm.Q - k for k in range(1, 40)] + [1 << k for k in range(0, 381, 7)]
+    vals += [(1 << 64) * 3, (1 << 352) + (1 << 32), (hm.Q - 1) // 2, (hm.Q + 1) // 2]
+    a = np.zeros((len(vals), 6), np.uint64)
+    for i, v in enumerate(vals):
+        a[i] = np.array(L.int_to_limbs(v), dtype=np.uint64)      # the symbol of the limb integer itself (chi(2^384) = 1)
+    out = np.zeros(len(vals), np.uint8)
+    emu.emu_fp_is_square(_p(a), ctypes.c_size_t(len(vals)), _p(out))
+    want = [1 if v % hm.Q == 0 or pow(v, (hm.Q - 1) // 2, hm.Q) == 1 else 0 for v in vals]
+    assert out.tolist() == want
+    assert 100 < sum(want) < len(vals) - 100

@@ -84,9 +84,9 @@ HDN void fpv_neg(fp *r, const fp *a, int n) {
     for (int i = 0; i < n; i++) { fp x = a[i]; fp_neg(x, x); r[i] = x; }
 }
 
-// a^(Q-2): FQ.Inverse (fq.go:224-266) returns the same canonical value; 0 -> 0 here (the
-// reference returns "no inverse").  Fixed exponent => no divergence inside a warp.
-HDN void fp_inv(fp *r, const fp *a) {
+// a^(Q-2): Fermat inversion with a fixed chain (570 multiplications).  Kept as the cross-check of fp_inv in the tests and
+// behind B381_INV_FERMAT for A/B timing.
+HDN void fp_inv_fermat(fp *r, const fp *a) {
     fp x = *a, acc;
     fp_set_one(acc);
     const uint32_t *e = B381_TAB(q_minus_2);
@@ -100,6 +100,98 @@ HDN void fp_inv(fp *r, const fp *a) {
         }
     }
     *r = acc;
+}
+// FQ.Inverse (fq.go:224-266 is a binary Euclid as well; the value is canonical, so any correct method is bit-identical);
+// 0 -> 0 here (the reference returns "no inverse").  Kaliski's almost-inverse on the twelve limbs of the Montgomery
+// representative A, with the factors of two stripped in batches:
+//   invariants  A r = -+ u 2^k,  A s = +- v 2^k  (mod Q),  u s + v r = Q  (so r, s <= Q: twelve limbs suffice)
+//   v even: v >>= z, r <<= z, k += z        v < u: exchange (u, r) with (v, s), which flips both signs        v -= u, s += r
+// until v = 0, u = 1: A^-1 = -+ r 2^-k with 381 <= k <= 762.  The Montgomery form of the inverse is A^-1 R^2 = -+ r 2^(768-k):
+// two Montgomery products (by R^2 and by the one-bit operand 2^(768-k)).  ~30 k integer instructions against ~190 k
+// for the exponentiation; the trip count depends on the value (lanes of a warp differ by a few per cent).
+HDN void fp_inv(fp *out, const fp *a) {
+#if defined(B381_INV_FERMAT)
+    fp_inv_fermat(out, a);
+#else
+    const uint32_t q[12] = {B381_Q_LIMBS};
+    uint32_t u[12], v[12], r[12], s[12], k = 0, neg = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { u[i] = q[i]; v[i] = a->l[i]; r[i] = 0; s[i] = 0; }
+    s[0] = 1;
+    for (;;) {
+        uint32_t low = v[0];
+        if (low == 0) {
+            uint32_t any = 0;
+#pragma unroll
+            for (int i = 1; i < 12; i++) any |= v[i];
+            if (any == 0) break;
+#pragma unroll
+            for (int i = 0; i < 11; i++) { v[i] = v[i + 1]; r[11 - i] = r[10 - i]; }
+            v[11] = 0; r[0] = 0;
+            k += 32;
+            continue;
+        }
+#if defined(__CUDA_ARCH__)
+        uint32_t z = __ffs(low) - 1;
+#else
+        uint32_t z = (uint32_t)__builtin_ctz(low);
+#endif
+        if (z) {
+#pragma unroll
+            for (int i = 0; i < 11; i++) v[i] = (v[i] >> z) | (v[i + 1] << (32 - z));
+            v[11] >>= z;
+#pragma unroll
+            for (int i = 11; i > 0; i--) r[i] = (r[i] << z) | (r[i - 1] >> (32 - z));
+            r[0] <<= z;
+            k += z;
+        }
+        uint32_t d[12];
+        uint64_t br = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            uint64_t x = (uint64_t)v[i] - u[i] - br;
+            d[i] = (uint32_t)x;
+            br = (x >> 32) & 1u;
+        }
+        if (br) {
+            uint64_t c = 1;
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                u[i] = v[i];
+                uint64_t x = (uint64_t)(~d[i]) + c;
+                d[i] = (uint32_t)x;
+                c = x >> 32;
+                uint32_t t = r[i]; r[i] = s[i]; s[i] = t;
+            }
+            neg ^= 1u;
+        }
+        uint64_t c = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            v[i] = d[i];
+            uint64_t x = (uint64_t)s[i] + r[i] + c;
+            s[i] = (uint32_t)x;
+            c = x >> 32;
+        }
+    }
+    const uint32_t r2[12] = {B381_R2_RAW_LIMBS};
+    fp t, w;
+#pragma unroll
+    for (int i = 0; i < 12; i++) { t.l[i] = r[i]; w.l[i] = r2[i]; }
+    fp_mul(t, t, w);                                   // r R
+    uint32_t e = 768u - k;                             // 6 <= e <= 387
+    if (e > 380u) {                                    // 2^e would not be a reduced operand: go through r R^2 and two factors
+        fp_mul(t, t, w);
+        fp_set_zero(w); w.l[190 >> 5] = 1u << (190 & 31);
+        fp_mul(t, t, w);
+        e -= 190u;
+    }
+    fp_set_zero(w);
+    w.l[e >> 5] = 1u << (e & 31);
+    fp_mul(t, t, w);                                   // r 2^e
+    if (!neg) fp_neg(t, t);
+    *out = t;
+#endif
 }
 
 // ---- Fq2 (fq2.go) ----------------------------------------------------------------------------

@@ -11,7 +11,7 @@ using namespace b381;
 static void ld12(fp12 *a, const uint64_t *s) { fp12_load_u64(a, s); }
 
 extern "C" {
-// op: 0 mul 1 add 2 sub 3 sqr 4 neg 5 dbl 6 inv
+// op: 0 mul 1 add 2 sub 3 sqr 4 neg 5 dbl 6 inv 8 inv by the Fermat chain
 void emu_fp_op(int op, const uint64_t *a, const uint64_t *b, uint64_t *o, size_t n) {
     for (size_t i = 0; i < n; i++) {
         fp x, y, r; fp_load_u64(x, a + 6 * i); fp_load_u64(y, b + 6 * i);
@@ -23,6 +23,7 @@ void emu_fp_op(int op, const uint64_t *a, const uint64_t *b, uint64_t *o, size_t
             case 4: fp_neg(r, x); break;
             case 5: fp_dbl(r, x); break;
             case 6: fp_inv(&r, &x); break;
+            case 8: fp_inv_fermat(&r, &x); break;
             default: r = x;
         }
         fp_store_u64(o + 6 * i, r);

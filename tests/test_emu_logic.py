@@ -37,8 +37,26 @@ def test_fp_ops(emu, orc):
         assert (out == orc.fq(name, a, b)).all(), name
     a[0] = L.fp_from_int(7)
     out = np.empty_like(a[:20])
-    emu.emu_fp_op(6, _p(a), _p(b), _p(out), ctypes.c_size_t(20))     # Fermat inverse == binary-Euclid inverse (fq.go:224-266)
+    emu.emu_fp_op(6, _p(a), _p(b), _p(out), ctypes.c_size_t(20))     # fp_inv == the oracle's binary-Euclid inverse (fq.go:224-266)
     assert (out == orc.fq("inverse", a[:20])).all()
+
+
+def test_fp_inv_almost_inverse(emu):
+    """fp_inv (Kaliski's almost-inverse with batched shifts) on limb patterns that drive every branch -- 0, 1 (few shifts: the
+    2^e > Q correction), powers of two (whole-limb shifts), Q - small, random -- against pow(-1) and the Fermat chain"""
+    rng = np.random.RandomState(21)
+    vals = [0, 1, 2, 3, L.Q - 1, L.Q - 2, (L.Q - 1) // 2, (L.Q + 1) // 2, 1 << 32, 1 << 64, 1 << 352, 1 << 380, (1 << 380) + 1,
+            3 << 96, (1 << 381) - 1 - (1 << 200), 0xffffffff, 1 << 31] + [1 << k for k in range(5, 380, 17)]
+    vals += [int.from_bytes(rng.bytes(48), "big") % L.Q for _ in range(400)]
+    a = np.zeros((len(vals), 6), U64)
+    for i, v in enumerate(vals):
+        a[i] = np.array(L.int_to_limbs(v), dtype=U64)       # the limb integer A itself; the result is A^-1 R^2 mod Q
+    for op in (6, 8):
+        out = np.empty_like(a)
+        emu.emu_fp_op(op, _p(a), _p(a), _p(out), ctypes.c_size_t(len(vals)))
+        for i, v in enumerate(vals):
+            want = 0 if v == 0 else pow(v, -1, L.Q) * L.MONT_R * L.MONT_R % L.Q
+            assert L.limbs_to_int(out[i]) == want, (op, hex(v))
 
 
 def test_fp12_ops(emu, orc):

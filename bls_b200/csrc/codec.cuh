@@ -6,7 +6,7 @@
 //   FQ.Sqrt (fq.go:203-217), FQ2.Sqrt (fq2.go:198-232), FQ.Cmp / FQ2.Cmp (fq.go:134-137, fq2.go:31-37)
 //   G1Affine.MulFR / G2Affine.MulFR + ToAffine (g1.go:80-90,322-340; g2.go:92-102,365-386): PrivToPub and Sign
 // One thread per point.  Results are canonical field elements / bytes / status codes, so they are the reference's
-// bits whatever formulas run underneath (here: XYZZ double-and-add from curve.cuh and Fermat inversion).
+// bits whatever formulas run underneath (here: Jacobian / XYZZ double-and-add from curve.cuh and the integer almost-inverse).
 #pragma once
 #include "curve.cuh"
 

@@ -3,7 +3,7 @@
 // (fq.go:41-45).  Replaces the reference's L0/L1 layers on the hot path:
 //   MultiplyFQRepr + MontReduce (stub_fallback.go:11-116, primitivefuncs_amd64.s) -> fp_mul
 //   FQ.AddAssign/SubAssign/NegAssign/DoubleAssign (fq.go:65-143)                 -> fp_add/...
-//   FQ.Inverse (fq.go:224-266, binary Euclid)        -> fp_inv (Fermat, fixed chain, same value)
+//   FQ.Inverse (fq.go:224-266, binary Euclid)        -> fp_inv (almost-inverse on the limbs, tower.cuh; same value)
 // Memory layout of an element is the reference's FQRepr: 6 x u64 little-endian limbs = 12 x u32.
 //
 // The arithmetic bodies are __host__ __device__: the device path is inline PTX (carry chains that

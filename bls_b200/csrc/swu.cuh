@@ -7,7 +7,7 @@
 //   the 11- / 3-isogeny  iso11 (hash.go:185-203), iso3 (hash.go:282-303)
 //   cofactor clearing  ClearH = [x + 1]P with x = 0xd201000000010000 (hash.go:305-309), clearH2 with psi (hash.go:341-389)
 // One thread per message.  Every intermediate the reference normalises is a canonical affine point, so the formulas
-// underneath (XYZZ accumulators, psi applied in XYZZ form, Fermat inversions) are free; roots are fixed by the
+// underneath (XYZZ accumulators, psi applied in XYZZ form, shared inversions) are free; roots are fixed by the
 // reference's sign rule, not by which root a square-root algorithm happens to return.
 #pragma once
 #include "hash.cuh"

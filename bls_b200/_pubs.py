@@ -56,7 +56,8 @@ class Group:
         return pts
 
     def mul(self, p, k):
-        return self.f("mul_batch")(p, np.array([L.int_to_limbs(k % L.R_ORDER, 4)], np.uint64))
+        """k * p for a point of the group (the generator or a hash to the curve): PrivToPub / Sign"""
+        return self.f("mul_subgroup_batch")(p, np.array([L.int_to_limbs(k % L.R_ORDER, 4)], np.uint64))
 
     def sum(self, pts):
         j = self.f("sum")(np.concatenate(pts)) if pts else None

@@ -210,6 +210,13 @@ class Ctx:
     def g2_mul_batch(self, p, k):
         return self._mul("b381_g2_mul_batch", L.G2_AFFINE, p, k)
 
+    def g1_mul_subgroup_batch(self, p, k):
+        """the same product through the endomorphism ladder; every p[i] must lie in G1 (generator, hash, checked key)"""
+        return self._mul("b381_g1_mul_subgroup_batch", L.G1_AFFINE, p, k)
+
+    def g2_mul_subgroup_batch(self, p, k):
+        return self._mul("b381_g2_mul_subgroup_batch", L.G2_AFFINE, p, k)
+
     def hash_g2_with_domain_batch(self, msgs32, domains8):
         """HashG2WithDomain over n 32-byte message hashes; domains8 is one 8-byte domain or n of them -> affine points"""
         m = np.frombuffer(b"".join(bytes(x) for x in msgs32), np.uint8) if not isinstance(msgs32, np.ndarray) else np.ascontiguousarray(msgs32, np.uint8).reshape(-1)

@@ -445,17 +445,17 @@ static int compress_host(b381_ctx *ctx, const APOD *in, size_t n, uint8_t *out) 
     CK(cudaStreamSynchronize(ctx->stream));
     return B381_OK;
 }
-template <class C, class APOD>
+template <class C, bool TORSION, class APOD>
 static int mul_dev(b381_ctx *ctx, const APOD *d_p, size_t p_stride, const b381_scalar *d_k, size_t k_stride, size_t n, APOD *d_out) {
     if (!ctx || p_stride > 1 || k_stride > 1 || (n && (!d_p || !d_k || !d_out))) return B381_ERR_ARG;
     if (!n) return B381_OK;
-    k_point_mul<C><<<grid_for(n, 64), 64, 0, ctx->stream>>>((const typename C::APOD *)d_p, p_stride, (const uint64_t *)d_k, k_stride, n,
+    k_point_mul<C, TORSION><<<grid_for(n, 64), 64, 0, ctx->stream>>>((const typename C::APOD *)d_p, p_stride, (const uint64_t *)d_k, k_stride, n,
                                                              (typename C::APOD *)d_out);
     ctx->launches++;
     CK(cudaGetLastError());
     return B381_OK;
 }
-template <class C, class APOD>
+template <class C, bool TORSION, class APOD>
 static int mul_host(b381_ctx *ctx, const APOD *p, size_t p_stride, const b381_scalar *k, size_t k_stride, size_t n, APOD *out) {
     if (!ctx || p_stride > 1 || k_stride > 1 || (n && (!p || !k || !out))) return B381_ERR_ARG;
     if (!n) return B381_OK;
@@ -467,7 +467,7 @@ static int mul_host(b381_ctx *ctx, const APOD *p, size_t p_stride, const b381_sc
     rc = scratch_get(ctx, 14, nk * sizeof(b381_scalar), &dk); if (rc) return rc;
     CK(cudaMemcpyAsync(dp, p, np * sizeof(APOD), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(dk, k, nk * sizeof(b381_scalar), cudaMemcpyHostToDevice, ctx->stream));
-    rc = mul_dev<C, APOD>(ctx, (const APOD *)dp, p_stride, (const b381_scalar *)dk, k_stride, n, (APOD *)dout); if (rc) return rc;
+    rc = mul_dev<C, TORSION, APOD>(ctx, (const APOD *)dp, p_stride, (const b381_scalar *)dk, k_stride, n, (APOD *)dout); if (rc) return rc;
     CK(cudaMemcpyAsync(out, dout, n * sizeof(APOD), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return B381_OK;
@@ -490,16 +490,28 @@ int b381_g1_compress_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_in, size_t
 int b381_g2_compress_batch(b381_ctx *ctx, const b381_g2_affine *in, size_t n, uint8_t *out) { return compress_host<G2Codec>(ctx, in, n, out); }
 int b381_g2_compress_batch_dev(b381_ctx *ctx, const b381_g2_affine *d_in, size_t n, uint8_t *d_out) { return compress_dev<G2Codec>(ctx, d_in, n, d_out); }
 int b381_g1_mul_batch(b381_ctx *ctx, const b381_g1_affine *p, size_t p_stride, const b381_scalar *k, size_t k_stride, size_t n, b381_g1_affine *out) {
-    return mul_host<G1Codec>(ctx, p, p_stride, k, k_stride, n, out);
+    return mul_host<G1Codec, false>(ctx, p, p_stride, k, k_stride, n, out);
 }
 int b381_g1_mul_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, size_t p_stride, const b381_scalar *d_k, size_t k_stride, size_t n, b381_g1_affine *d_out) {
-    return mul_dev<G1Codec>(ctx, d_p, p_stride, d_k, k_stride, n, d_out);
+    return mul_dev<G1Codec, false>(ctx, d_p, p_stride, d_k, k_stride, n, d_out);
 }
 int b381_g2_mul_batch(b381_ctx *ctx, const b381_g2_affine *p, size_t p_stride, const b381_scalar *k, size_t k_stride, size_t n, b381_g2_affine *out) {
-    return mul_host<G2Codec>(ctx, p, p_stride, k, k_stride, n, out);
+    return mul_host<G2Codec, false>(ctx, p, p_stride, k, k_stride, n, out);
 }
 int b381_g2_mul_batch_dev(b381_ctx *ctx, const b381_g2_affine *d_p, size_t p_stride, const b381_scalar *d_k, size_t k_stride, size_t n, b381_g2_affine *d_out) {
-    return mul_dev<G2Codec>(ctx, d_p, p_stride, d_k, k_stride, n, d_out);
+    return mul_dev<G2Codec, false>(ctx, d_p, p_stride, d_k, k_stride, n, d_out);
+}
+int b381_g1_mul_subgroup_batch(b381_ctx *ctx, const b381_g1_affine *p, size_t p_stride, const b381_scalar *k, size_t k_stride, size_t n, b381_g1_affine *out) {
+    return mul_host<G1Codec, true>(ctx, p, p_stride, k, k_stride, n, out);
+}
+int b381_g1_mul_subgroup_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, size_t p_stride, const b381_scalar *d_k, size_t k_stride, size_t n, b381_g1_affine *d_out) {
+    return mul_dev<G1Codec, true>(ctx, d_p, p_stride, d_k, k_stride, n, d_out);
+}
+int b381_g2_mul_subgroup_batch(b381_ctx *ctx, const b381_g2_affine *p, size_t p_stride, const b381_scalar *k, size_t k_stride, size_t n, b381_g2_affine *out) {
+    return mul_host<G2Codec, true>(ctx, p, p_stride, k, k_stride, n, out);
+}
+int b381_g2_mul_subgroup_batch_dev(b381_ctx *ctx, const b381_g2_affine *d_p, size_t p_stride, const b381_scalar *d_k, size_t k_stride, size_t n, b381_g2_affine *d_out) {
+    return mul_dev<G2Codec, true>(ctx, d_p, p_stride, d_k, k_stride, n, d_out);
 }
 int b381_hash_g2_with_domain_batch_dev(b381_ctx *ctx, const uint8_t *d_msg32, const uint8_t *d_domain8, size_t domain_stride, size_t n,
                                        b381_g2_affine *d_out) {

@@ -485,8 +485,157 @@ template <class C> HD void compress_one(uint8_t *out, const typename C::APOD *in
     if (C::cmp(y, ny) > 0) out[0] |= 0x20;
     out[0] |= 0x80;
 }
+// ---- scalar multiplication of r-torsion points through the endomorphisms ----------------------------------------------------
+// For P in G1 / G2 (NOT for other curve points) the 255-bit ladder of MulFR (g1.go:80-90, g2.go:92-102) is replaced by
+//   G2:  k = d0 + d1 X + d2 X^2 + d3 X^3 (X = |x|),  [k]P = [d0]P - [d1]psi(P) + [d2]psi^2(P) - [d3]psi^3(P)   (psi = [x] = [-X])
+//   G1:  k = k0 + k1 X^2,  [k]P = [k0]P + [k1](beta x, -y)                         ((beta x, y) = -[X^2]P, the subgroup test's identity)
+// with joint fixed windows over the bases: 64 doublings + 64 table additions (G2), 128 + 64 (G1), instead of 255 + 255 (a
+// warp pays for an addition at every bit some lane has set, i.e. at every bit).
+// The affine result is the same canonical pair of field elements.  Used for Sign / PrivToPub, whose bases are the generator
+// or a hash to the curve; b381_g{1,2}_mul_batch keeps the plain ladder because it must also serve points outside the subgroup.
+// base-X digits of a 256-bit scalar by restoring division (X has its top bit set); d[4] = 0 whenever k < X^4 (r < X^4)
+HD void scalar_digits_base_x(uint64_t d[5], const uint64_t *k) {
+    const uint64_t X = 0xd201000000010000ull;
+    uint64_t n[4] = {k[0], k[1], k[2], k[3]};
+#pragma unroll 1
+    for (int j = 0; j < 4; j++) {
+        uint64_t rem = 0;
+#pragma unroll 1
+        for (int b = 255; b >= 0; b--) {
+            uint64_t carry = rem >> 63;
+            rem = (rem << 1) | ((n[b >> 6] >> (b & 63)) & 1u);
+            uint64_t ge = (carry | (uint64_t)(rem >= X)) & 1u;
+            if (ge) rem -= X;
+            n[b >> 6] = (n[b >> 6] & ~(1ull << (b & 63))) | (ge << (b & 63));
+        }
+        d[j] = rem;
+    }
+    d[4] = n[0] | n[1] | n[2] | n[3];
+}
+// affine coordinates of n finite XYZZ points with ONE inversion (Montgomery's trick on the ZZZ); n <= 16
+template <class F> HDN void xyzz_batch_to_affine(typename F::T *ox, typename F::T *oy, const xyzz<F> *p, int n) {
+    typename F::T pre[16], acc, inv, t;
+    acc = p[0].zzz;
+    pre[0] = acc;
+#pragma unroll 1
+    for (int i = 1; i < n; i++) { F::mul(acc, acc, p[i].zzz); pre[i] = acc; }
+    F::inv(inv, acc);
+#pragma unroll 1
+    for (int i = n - 1; i >= 0; i--) {
+        typename F::T zi;
+        if (i) { F::mul(zi, inv, pre[i - 1]); F::mul(inv, inv, p[i].zzz); }
+        else zi = inv;
+        F::mul(oy[i], p[i].y, zi);         // y = Y / ZZZ
+        F::mul(t, zi, p[i].zz);            // 1 / Z
+        F::sqr(t, t);
+        F::mul(ox[i], p[i].x, t);          // x = X / ZZ
+    }
+}
+// A warp executes an addition whenever ANY of its lanes needs one, so per-lane sparse digits (NAF) buy nothing under SIMT;
+// what pays is a fixed schedule: every lane adds a table entry at the same steps and only the INDEX depends on its scalar.
+// G2: joint one-bit window over the four bases, T[m] = sum of the B_i with bit i of m set (15 affine entries, built with
+// 11 mixed additions and one shared inversion), then 64 x (doubling + one mixed addition).
+HDN void torsion_mul(xyzz<Fp2Out> *acc, const fp2 *x, const fp2 *y, const uint64_t *k) {
+    uint64_t d[5];
+    scalar_digits_base_x(d, k);
+    if (d[4]) {                                            // k >= X^4 > r: not a canonical scalar, take the plain ladder
+        uint32_t kk[8];
+        for (int i = 0; i < 4; i++) { kk[2 * i] = (uint32_t)k[i]; kk[2 * i + 1] = (uint32_t)(k[i] >> 32); }
+        point_mul<Fp2Out>(acc, x, y, kk, 8);
+        return;
+    }
+    fp2 tx[16], ty[16];                                    // entry m at index m; index 0 unused
+    tx[1] = *x; ty[1] = *y;
+    for (int i = 1; i < 4; i++) {                          // B_i = -psi(B_{i-1}) = (-1)^i psi^i(P) at index 2^i
+        g2_psi(tx[1 << i], ty[1 << i], tx[1 << (i - 1)], ty[1 << (i - 1)]);
+        fp2_neg(ty[1 << i], ty[1 << i]);
+    }
+    {
+        xyzz<Fp2Out> s[11];
+        const uint8_t comp[11] = {3, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15};
+        fp2 sx[11], sy[11];
+#pragma unroll 1
+        for (int j = 0; j < 11; j++) {                     // T[m] = T[m without its top bit] + B_top: the smaller entry is already
+            int m = comp[j], top = m >= 8 ? 8 : (m >= 4 ? 4 : 2), lowm = m - top;   // affine (a base) or an earlier s[]
+            if ((lowm & (lowm - 1)) == 0) { s[j].x = tx[lowm]; s[j].y = ty[lowm]; fp2_set_one(s[j].zz); fp2_set_one(s[j].zzz); }
+            else {
+                int q = 0;
+                while (comp[q] != lowm) q++;
+                s[j] = s[q];
+            }
+            xyzz_madd(s[j], tx[top], ty[top]);
+        }
+        xyzz_batch_to_affine<Fp2Out>(sx, sy, s, 11);
+        for (int j = 0; j < 11; j++) { tx[comp[j]] = sx[j]; ty[comp[j]] = sy[j]; }
+    }
+    jac_pt<Fp2Out> a;
+    fp2_set_one(a.x); fp2_set_one(a.y); fp2_set_zero(a.z);
+#pragma unroll 1
+    for (int j = 63; j >= 0; j--) {
+        jac_dbl(a);
+        int m = (int)(((d[0] >> j) & 1) | (((d[1] >> j) & 1) << 1) | (((d[2] >> j) & 1) << 2) | (((d[3] >> j) & 1) << 3));
+        if (m) jac_madd(a, tx[m], ty[m]);
+    }
+    jac_to_xyzz(*acc, a);
+}
+// G1: k = k0 + k1 X^2 over P and Q = (beta x, -y) = [X^2]P, joint two-bit windows: T[a + 4 b] = a P + b Q (15 affine
+// entries, 14 mixed additions / doublings and one shared inversion), then 64 x (two doublings + one mixed addition).
+HDN void torsion_mul(xyzz<FpOut> *acc, const fp *x, const fp *y, const uint64_t *k) {
+    uint64_t d[5];
+    scalar_digits_base_x(d, k);
+    if (d[4]) {
+        uint32_t kk[8];
+        for (int i = 0; i < 4; i++) { kk[2 * i] = (uint32_t)k[i]; kk[2 * i + 1] = (uint32_t)(k[i] >> 32); }
+        point_mul<FpOut>(acc, x, y, kk, 8);
+        return;
+    }
+    const uint64_t X = 0xd201000000010000ull;
+    uint32_t kw[2][4];
+    for (int i = 0; i < 2; i++) {                          // k_i = d[2i] + d[2i+1] X < X^2 < 2^128, by 32-bit partial products
+        uint32_t *n = kw[i], m[2] = {(uint32_t)d[2 * i + 1], (uint32_t)(d[2 * i + 1] >> 32)}, xs[2] = {(uint32_t)X, (uint32_t)(X >> 32)};
+        n[0] = n[1] = n[2] = n[3] = 0;
+        for (int u = 0; u < 2; u++) {
+            uint64_t c = 0;
+            for (int v = 0; v < 2; v++) {
+                uint64_t t = (uint64_t)m[u] * xs[v] + n[u + v] + c;
+                n[u + v] = (uint32_t)t;
+                c = t >> 32;
+            }
+            n[u + 2] = (uint32_t)c;
+        }
+        uint64_t c = 0, add[4] = {(uint32_t)d[2 * i], d[2 * i] >> 32, 0, 0};
+        for (int u = 0; u < 4; u++) {
+            uint64_t t = (uint64_t)n[u] + add[u] + c;
+            n[u] = (uint32_t)t;
+            c = t >> 32;
+        }
+    }
+    fp tx[16], ty[16], qx, qy, beta;
+    fp_load_tab(beta, B381_TAB(beta));
+    fp_mul(qx, *x, beta);
+    fp_neg(qy, *y);
+    {
+        xyzz<FpOut> s[15];                                 // s[m - 1] = T[m]
+        s[0].x = *x; s[0].y = *y; fp_set_one(s[0].zz); fp_set_one(s[0].zzz);
+        xyzz_dbl_affine(s[1], *x, *y);
+        s[2] = s[1]; xyzz_madd(s[2], *x, *y);
+        s[3].x = qx; s[3].y = qy; fp_set_one(s[3].zz); fp_set_one(s[3].zzz);
+#pragma unroll 1
+        for (int m = 5; m <= 15; m++) { s[m - 1] = s[m - 5]; xyzz_madd(s[m - 1], qx, qy); }   // a P + b Q = (a P + (b - 1) Q) + Q
+        xyzz_batch_to_affine<FpOut>(tx + 1, ty + 1, s, 15);
+    }
+    jac_pt<FpOut> a;
+    fp_set_one(a.x); fp_set_one(a.y); fp_set_zero(a.z);
+#pragma unroll 1
+    for (int j = 126; j >= 0; j -= 2) {
+        jac_dbl(a); jac_dbl(a);
+        int m = (int)(((kw[0][j >> 5] >> (j & 31)) & 3u) | (((kw[1][j >> 5] >> (j & 31)) & 3u) << 2));
+        if (m) jac_madd(a, tx[m], ty[m]);
+    }
+    jac_to_xyzz(*acc, a);
+}
 // out = k * p as an affine point (MulFR + ToAffine); p at infinity or k = 0 give the canonical zero (0, 1, inf)
-template <class C> HD void mul_one(typename C::APOD *out, const typename C::APOD *p, const uint64_t *k) {
+template <class C, bool TORSION> HD void mul_one(typename C::APOD *out, const typename C::APOD *p, const uint64_t *k) {
     typedef typename C::T T;
     T x, y;
     uint32_t kk[8];
@@ -495,7 +644,8 @@ template <class C> HD void mul_one(typename C::APOD *out, const typename C::APOD
     xyzz_set_inf(acc);
     if (!p->inf) {
         C::load(x, y, p);
-        point_mul<typename C::F>(&acc, &x, &y, kk, 8);
+        if (TORSION) torsion_mul(&acc, &x, &y, k);
+        else point_mul<typename C::F>(&acc, &x, &y, kk, 8);
     }
     if (xyzz_is_inf(acc)) { C::F::set_zero(x); C::F::set_one(y); C::store(out, x, y, true); return; }
     xyzz_to_affine<typename C::F>(x, y, acc);
@@ -516,12 +666,12 @@ template <class C> __global__ void __launch_bounds__(64) k_compress(const typena
     compress_one<C>(out + (size_t)C::BYTES * i, in + i);
 }
 // out[i] = k[i] * p[i * p_stride]: p_stride 0 multiplies one base by every scalar (PrivToPub: the generator)
-template <class C> __global__ void __launch_bounds__(64, CODEC_MIN_BLOCKS) k_point_mul(const typename C::APOD *__restrict__ p, size_t p_stride,
+template <class C, bool TORSION> __global__ void __launch_bounds__(64, CODEC_MIN_BLOCKS) k_point_mul(const typename C::APOD *__restrict__ p, size_t p_stride,
                                                                      const uint64_t *__restrict__ k, size_t k_stride, size_t n,
                                                                      typename C::APOD *__restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    mul_one<C>(out + i, p + i * p_stride, k + 4 * i * k_stride);
+    mul_one<C, TORSION>(out + i, p + i * p_stride, k + 4 * i * k_stride);
 }
 #endif
 

@@ -174,6 +174,7 @@ HDN void fp_inv(fp *out, const fp *a) {
             c = x >> 32;
         }
     }
+    if (k == 0) { fp_set_zero(*out); return; }         // A = 0 (for 0 < A < Q Kaliski's bound gives 381 <= k <= 762)
     const uint32_t r2[12] = {B381_R2_RAW_LIMBS};
     fp t, w;
 #pragma unroll

@@ -142,6 +142,44 @@ func MulG2Batch(p []G2Affine, k []*FR) []G2Affine {
 	return out
 }
 
+// mulStrides: a single point or a single scalar is broadcast over the batch.
+func mulStrides(np, nk int) (n int, ps, ks C.size_t) {
+	n = np
+	if nk > n {
+		n = nk
+	}
+	ps, ks = 1, 1
+	if np == 1 && n > 1 {
+		ps = 0
+	}
+	if nk == 1 && n > 1 {
+		ks = 0
+	}
+	return
+}
+
+// MulG1SubgroupBatch is MulG1Batch for points known to lie in G1 (the generator, a hash to the curve, a checked key):
+// the engine takes the endomorphism ladder, about twice as fast, same result.  PrivToPub (g2pubs keys live in G2,
+// g1pubs keys in G1) and Sign use these.
+func MulG1SubgroupBatch(p []G1Affine, k []*FR) []G1Affine {
+	n, ps, kst := mulStrides(len(p), len(k))
+	out := make([]G1Affine, n)
+	ks := scalars(k)
+	must(C.b381_g1_mul_subgroup_batch(ctx(), (*C.b381_g1_affine)(unsafe.Pointer(&p[0])), ps,
+		(*C.b381_scalar)(unsafe.Pointer(&ks[0])), kst, C.size_t(n), (*C.b381_g1_affine)(unsafe.Pointer(&out[0]))))
+	return out
+}
+
+// MulG2SubgroupBatch: see MulG1SubgroupBatch.
+func MulG2SubgroupBatch(p []G2Affine, k []*FR) []G2Affine {
+	n, ps, kst := mulStrides(len(p), len(k))
+	out := make([]G2Affine, n)
+	ks := scalars(k)
+	must(C.b381_g2_mul_subgroup_batch(ctx(), (*C.b381_g2_affine)(unsafe.Pointer(&p[0])), ps,
+		(*C.b381_scalar)(unsafe.Pointer(&ks[0])), kst, C.size_t(n), (*C.b381_g2_affine)(unsafe.Pointer(&out[0]))))
+	return out
+}
+
 // HashG2WithDomainBatch: out[i] = HashG2WithDomain(msgs[i], domain).ToAffine() (g2.go:1041-1085).
 func HashG2WithDomainBatch(msgs [][32]byte, domain [8]byte) []G2Affine {
 	out := make([]G2Affine, len(msgs))

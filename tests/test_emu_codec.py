@@ -82,6 +82,31 @@ def test_scalar_mul(emu, orc, which):
 
 
 @pytest.mark.parametrize("which", ["g1", "g2"])
+def test_scalar_mul_endomorphism_ladder(emu, orc, which):
+    """the GLV / psi ladders of b381_g{1,2}_mul_subgroup_batch on points of the group: same affine result as MulFR + ToAffine
+    for scalars that exercise every digit pattern (0, 1, r - 1, |x|^i, |x|^i - 1, digits all ones, values >= r and >= |x|^4)"""
+    grp, dtype = (orc.g1, L.G1_AFFINE) if which == "g1" else (orc.g2, L.G2_AFFINE)
+    X = 0xd201000000010000
+    ks = [0, 1, 2, L.R_ORDER - 1, L.R_ORDER - 2, X, X - 1, X + 1, X * X, X * X - 1, X ** 3, X ** 3 - 1, X ** 3 + X * X + X + 1,
+          (X - 1) * (1 + X + X * X + X ** 3), L.R_ORDER, L.R_ORDER + 5, X ** 4, X ** 4 + 7, (1 << 256) - 1, (1 << 255) + 12345,
+          0xffffffffffffffff, 1 << 64, (1 << 128) - 1, 1 << 128]
+    rnd = orc.XorShift(91).rand_fr(12)
+    k = np.concatenate([np.array([L.int_to_limbs(v, 4) for v in ks], np.uint64), rnd])
+    n = k.shape[0]
+    pts = hg.g1_progression(23, 7, n) if which == "g1" else hg.g2_progression(29, 11, n)
+    plain = np.zeros(n, dtype=dtype); endo = np.zeros(n, dtype=dtype)
+    getattr(emu, "emu_%s_mul" % which)(_p(pts), ctypes.c_size_t(1), _p(k), ctypes.c_size_t(1), ctypes.c_size_t(n), _p(plain))
+    getattr(emu, "emu_%s_mul_subgroup" % which)(_p(pts), ctypes.c_size_t(1), _p(k), ctypes.c_size_t(1), ctypes.c_size_t(n), _p(endo))
+    assert endo.tobytes() == plain.tobytes()
+    canon = [i for i in range(n) if L.limbs_to_int(k[i]) < L.R_ORDER]
+    assert endo[canon].tobytes() == grp.to_affine(grp.mul_fr(pts[canon], k[canon])).tobytes()
+    assert int(endo["inf"][0]) == 1 and int(endo["inf"][ks.index(L.R_ORDER)]) == 1
+    z = np.zeros(1, dtype=dtype); z["inf"] = 1; o = np.zeros(1, dtype=dtype)
+    getattr(emu, "emu_%s_mul_subgroup" % which)(_p(z), ctypes.c_size_t(1), _p(k[5:]), ctypes.c_size_t(1), ctypes.c_size_t(1), _p(o))
+    assert int(o["inf"][0]) == 1
+
+
+@pytest.mark.parametrize("which", ["g1", "g2"])
 def test_subgroup_criterion_on_cofactor_points(emu, orc, which):
     """The endomorphism membership tests (codec.cuh) must agree with the reference's [r]P == O (g1.go:137-141,
     g2.go:293-295) on every curve point -- in particular on points of the cofactor subgroups, of small order, and on

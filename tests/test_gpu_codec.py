@@ -76,6 +76,15 @@ def test_mul_batch(ctx, orc, which):
     # infinity in, infinity out
     z = np.zeros(1, dtype=dtype); z["inf"] = 1
     assert int(mul(z, k[3:4])["inf"][0]) == 1
+    # the endomorphism ladders (b381_g{1,2}_mul_subgroup_batch): same bytes on points of the group, all stride forms
+    smul = ctx.g1_mul_subgroup_batch if which == "g1" else ctx.g2_mul_subgroup_batch
+    assert smul(pts, k).tobytes() == mul(pts, k).tobytes()
+    assert smul(gen, sk).tobytes() == exp.tobytes()
+    assert smul(pts, k[5:6]).tobytes() == got.tobytes()
+    assert int(smul(z, k[3:4])["inf"][0]) == 1
+    X = 0xd201000000010000
+    edge = np.array([L.int_to_limbs(v, 4) for v in (X, X * X - 1, X ** 3, L.R_ORDER, X ** 4 + 7, (1 << 256) - 1)], np.uint64)
+    assert smul(pts[:6], edge).tobytes() == mul(pts[:6], edge).tobytes()
 
 
 def test_empty_batches(ctx):

@@ -52,6 +52,11 @@ for chk in (0, 1):
     assert not dS.any().item() and bytes(dO2.cpu().numpy()) == P2.tobytes()
 res["g1_mul_ms"] = timed(lambda: ctx.dev("b381_g1_mul_batch_dev", dP1.data_ptr(), one, dK.data_ptr(), one, N, dO1.data_ptr()))
 res["g2_mul_ms"] = timed(lambda: ctx.dev("b381_g2_mul_batch_dev", dP2.data_ptr(), one, dK.data_ptr(), one, N, dO2.data_ptr()))
+dO1b = torch.empty_like(dO1); dO2b = torch.empty_like(dO2)
+ctx.dev("b381_g1_mul_batch_dev", dP1.data_ptr(), one, dK.data_ptr(), one, N, dO1.data_ptr())
+res["g1_mul_subgroup_ms"] = timed(lambda: ctx.dev("b381_g1_mul_subgroup_batch_dev", dP1.data_ptr(), one, dK.data_ptr(), one, N, dO1b.data_ptr()))
+res["g2_mul_subgroup_ms"] = timed(lambda: ctx.dev("b381_g2_mul_subgroup_batch_dev", dP2.data_ptr(), one, dK.data_ptr(), one, N, dO2b.data_ptr()))
+assert torch.equal(dO1, dO1b) and torch.equal(dO2, dO2b), "endomorphism ladder differs from the plain ladder"
 rng = np.random.RandomState(1)
 dM = up(rng.randint(0, 256, (n, 32), dtype=np.uint8)); dD = up(np.arange(8, dtype=np.uint8))
 res["hash_g2_with_domain_ms"] = timed(lambda: ctx.dev("b381_hash_g2_with_domain_batch_dev", dM.data_ptr(), dD.data_ptr(), ctypes.c_size_t(0), N, dO2.data_ptr()))

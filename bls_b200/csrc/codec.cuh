@@ -531,6 +531,32 @@ template <class F> HDN void xyzz_batch_to_affine(typename F::T *ox, typename F::
         F::mul(ox[i], p[i].x, t);          // x = X / ZZ
     }
 }
+// acc = k * (x, y) for ANY finite curve point and a per-lane scalar (8 limbs): fixed four-bit windows over the affine table
+// P .. 15 P (one shared inversion) -- 256 doublings + 64 table additions on a schedule common to the warp, where the bitwise
+// ladder pays an addition at every bit some lane has set.  A point of order <= 15 makes a table entry infinite; such inputs
+// take the bitwise ladder.  Same affine result as G1Affine.Mul / G2Affine.Mul (g1.go:59-90).
+template <class F> HDN void point_mul_w4(xyzz<F> *acc, const typename F::T *x, const typename F::T *y, const uint32_t *k) {
+    typename F::T tx[16], ty[16];
+    {
+        xyzz<F> s[15];
+        s[0].x = *x; s[0].y = *y; F::set_one(s[0].zz); F::set_one(s[0].zzz);
+        xyzz_dbl_affine(s[1], *x, *y);
+        bool finite = !xyzz_is_inf(s[1]);
+#pragma unroll 1
+        for (int m = 2; m < 15; m++) { s[m] = s[m - 1]; xyzz_madd(s[m], *x, *y); finite = finite && !xyzz_is_inf(s[m]); }
+        if (!finite) { point_mul<F>(acc, x, y, k, 8); return; }
+        xyzz_batch_to_affine<F>(tx + 1, ty + 1, s, 15);
+    }
+    jac_pt<F> a;
+    F::set_one(a.x); F::set_one(a.y); F::set_zero(a.z);
+#pragma unroll 1
+    for (int j = 252; j >= 0; j -= 4) {
+        jac_dbl(a); jac_dbl(a); jac_dbl(a); jac_dbl(a);
+        int m = (int)((k[j >> 5] >> (j & 31)) & 15u);
+        if (m) jac_madd(a, tx[m], ty[m]);
+    }
+    jac_to_xyzz(*acc, a);
+}
 // A warp executes an addition whenever ANY of its lanes needs one, so per-lane sparse digits (NAF) buy nothing under SIMT;
 // what pays is a fixed schedule: every lane adds a table entry at the same steps and only the INDEX depends on its scalar.
 // G2: joint one-bit window over the four bases, T[m] = sum of the B_i with bit i of m set (15 affine entries, built with
@@ -645,7 +671,7 @@ template <class C, bool TORSION> HD void mul_one(typename C::APOD *out, const ty
     if (!p->inf) {
         C::load(x, y, p);
         if (TORSION) torsion_mul(&acc, &x, &y, k);
-        else point_mul<typename C::F>(&acc, &x, &y, kk, 8);
+        else point_mul_w4<typename C::F>(&acc, &x, &y, kk);
     }
     if (xyzz_is_inf(acc)) { C::F::set_zero(x); C::F::set_one(y); C::store(out, x, y, true); return; }
     xyzz_to_affine<typename C::F>(x, y, acc);

@@ -106,6 +106,40 @@ def test_scalar_mul_endomorphism_ladder(emu, orc, which):
     assert int(o["inf"][0]) == 1
 
 
+def test_scalar_mul_small_order_points(emu, orc):
+    """the windowed ladder of b381_g{1,2}_mul_batch on points whose multiples hit infinity inside the table (order 3 on E(Fq),
+    13 on E'(Fq2)): same result as the reference's double-and-add"""
+    from oracle import hostmath as hm
+    rng = np.random.RandomState(3)
+    h1 = 0x396c8c005555e1568c00aaab0000aaab
+    g1pts, g2pts = [], []
+    while len(g1pts) < 2:
+        x = int.from_bytes(rng.bytes(47), "big")
+        y = hm.fq_sqrt((x * x * x + 4) % L.Q)
+        if y is None:
+            continue
+        p = hm.g1_mul((x, y), h1 * L.R_ORDER // 3)
+        if p is not None and hm.g1_mul(p, 3) is None:
+            g1pts.append(p)
+    while len(g2pts) < 1:
+        x = (int.from_bytes(rng.bytes(47), "big"), int.from_bytes(rng.bytes(47), "big"))
+        y = hm.fq2_sqrt(hm._Fq2.add(hm._Fq2.mul(hm._Fq2.sqr(x), x), (4, 4)))
+        if y is None:
+            continue
+        p = hm.g2_mul((x, y), hm.G2_COFACTOR * L.R_ORDER // 169)       # the 13-part of E'(Fq2) is Z_13 x Z_13
+        if p is not None and hm.g2_mul(p, 13) is None:
+            g2pts.append(p)
+    ks = [1, 2, 3, 10, 11, 12, 13, 26, 0x123456789abcdef, L.R_ORDER - 1]
+    for which, pts, mul, conv in (("g1", g1pts, hm.g1_mul, hg.g1_points), ("g2", g2pts, hm.g2_mul, hg.g2_points)):
+        src = conv([p for p in pts for _ in ks])
+        k = np.array([L.int_to_limbs(v, 4) for _ in pts for v in ks], np.uint64)
+        got = np.zeros(len(src), dtype=src.dtype)
+        getattr(emu, "emu_%s_mul" % which)(_p(src), ctypes.c_size_t(1), _p(k), ctypes.c_size_t(1), ctypes.c_size_t(len(src)), _p(got))
+        want = conv([mul(p, v) for p in pts for v in ks])
+        assert got.tobytes() == want.tobytes(), which
+        assert want["inf"].sum() >= 2
+
+
 @pytest.mark.parametrize("which", ["g1", "g2"])
 def test_subgroup_criterion_on_cofactor_points(emu, orc, which):
     """The endomorphism membership tests (codec.cuh) must agree with the reference's [r]P == O (g1.go:137-141,

@@ -159,7 +159,7 @@ func mulStrides(np, nk int) (n int, ps, ks C.size_t) {
 }
 
 // MulG1SubgroupBatch is MulG1Batch for points known to lie in G1 (the generator, a hash to the curve, a checked key):
-// the engine takes the endomorphism ladder, about twice as fast, same result.  PrivToPub (g2pubs keys live in G2,
+// the engine takes the endomorphism ladder (1.5x / 1.9x faster), same result.  PrivToPub (g2pubs keys live in G2,
 // g1pubs keys in G1) and Sign use these.
 func MulG1SubgroupBatch(p []G1Affine, k []*FR) []G1Affine {
 	n, ps, kst := mulStrides(len(p), len(k))

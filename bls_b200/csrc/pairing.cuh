@@ -171,8 +171,9 @@ HD void miller_loop_two(fp12 *f, const g1_affine_pod *P, const g2_affine_pod *Q)
     fp12_conj(f, f);
 }
 
-// conj(f^x) for f in the cyclotomic subgroup   (ExpByX, pairing.go:92-98)
-HDN void exp_by_x(fp12 *r, const fp12 *f, uint64_t x) {
+// conj(f^x) for f in the cyclotomic subgroup   (ExpByX, pairing.go:92-98): MSB-first square and multiply with
+// Granger-Scott squarings.  The form the reference's loop has; exp_by_x below falls back to it for degenerate values.
+HDN void exp_by_x_gs(fp12 *r, const fp12 *f, uint64_t x) {
     fp12 acc;
     fp12_copy(&acc, f);
     int top = 63;
@@ -183,6 +184,100 @@ HDN void exp_by_x(fp12 *r, const fp12 *f, uint64_t x) {
         if ((x >> bit) & 1) fp12_mul(&acc, &acc, f);
     }
     fp12_conj(r, &acc);
+}
+
+// Compressed squaring in the cyclotomic subgroup (Karabina, "Squaring in cyclotomic subgroups", eprint 2010/542), on the
+// tower Fq12 = Fq4[t]/(t^3 - s), Fq4 = Fq2[s]/(s^2 - xi) with t = w, s = w^3:  f = (g0 + g1 s) + (g2 + g3 s) t + (g4 + g5 s) t^2,
+//   g0 = c0.c0, g1 = c1.c1, g2 = c1.c0, g3 = c0.c2, g4 = c0.c1, g5 = c1.c2   (the Fp4 pairs of fp12_cyclotomic_sqr).
+// The square of (g2, g3, g4, g5) needs four Fq2 multiplications (12 Fq multiplications against 18 for Granger-Scott):
+//   A23 = (g2 + g3)(g2 + xi g3), B23 = g2 g3, A45, B45 likewise
+//   h2 = 2 (g2 + 3 xi B45)    h3 = 3 (A45 - (xi + 1) B45) - 2 g3    h4 = 3 (A23 - (xi + 1) B23) - 2 g4    h5 = 2 (g5 + 3 B23)
+// and g1 = (xi g5^2 + 3 g4^2 - 2 g3) / (4 g2), g0 = (2 g1^2 + g2 g5 - 3 g3 g4) xi + 1 recover the rest (g2 != 0).
+struct cyc4 { fp2 g2, g3, g4, g5; };
+HD void cyc_compress(cyc4 *c, const fp12 *f) { c->g2 = f->c1.c0; c->g3 = f->c0.c2; c->g4 = f->c0.c1; c->g5 = f->c1.c2; }
+HDN void cyc_sqr_compressed(cyc4 *c) {
+    fp2 A, B, t0, t1, n2, n3;
+    fp2_mul_nr(t0, c->g5); fp2_add(t0, t0, c->g4);
+    fp2_add(t1, c->g4, c->g5);
+    fp2_mul(&A, &t0, &t1);                             // A45
+    fp2_mul(&B, &c->g4, &c->g5);                       // B45
+    fp2_mul_nr(t0, B);
+    fp2_sub(A, A, t0); fp2_sub(A, A, B);               // A45 - (xi + 1) B45
+    fp2_dbl(t0, t0);
+    fp2_tri(&n2, &t0, &c->g2, 1);                      // 3 (2 xi B45) + 2 g2
+    fp2_tri(&n3, &A, &c->g3, 0);
+    fp2_mul_nr(t0, c->g3); fp2_add(t0, t0, c->g2);
+    fp2_add(t1, c->g2, c->g3);
+    fp2_mul(&A, &t0, &t1);                             // A23
+    fp2_mul(&B, &c->g2, &c->g3);                       // B23
+    fp2_mul_nr(t0, B);
+    fp2_sub(A, A, t0); fp2_sub(A, A, B);
+    fp2_tri(&c->g4, &A, &c->g4, 0);
+    fp2_dbl(t0, B);
+    fp2_tri(&c->g5, &t0, &c->g5, 1);
+    c->g2 = n2; c->g3 = n3;
+}
+HDN void cyc_decompress(fp12 *f, const cyc4 *c, const fp2 *inv4g2) {
+    fp2 t0, t1, g1;
+    fp2_sqr(&t0, &c->g5); fp2_mul_nr(t0, t0);          // xi g5^2
+    fp2_sqr(&t1, &c->g4);
+    fp2_tri(&t1, &t1, &c->g3, 0);                      // 3 g4^2 - 2 g3
+    fp2_add(t0, t0, t1);
+    fp2_mul(&g1, &t0, inv4g2);
+    fp2_sqr(&t0, &g1); fp2_dbl(t0, t0);                // 2 g1^2
+    fp2_mul(&t1, &c->g2, &c->g5); fp2_add(t0, t0, t1);
+    fp2_mul(&t1, &c->g3, &c->g4);
+    fp2_sub(t0, t0, t1); fp2_dbl(t1, t1); fp2_sub(t0, t0, t1);
+    fp2_mul_nr(t0, t0);
+    fp2_set_one(t1);
+    fp2_add(f->c0.c0, t0, t1);
+    f->c1.c1 = g1; f->c1.c0 = c->g2; f->c0.c2 = c->g3; f->c0.c1 = c->g4; f->c1.c2 = c->g5;
+}
+// conj(f^x) for the two exponents of the final exponentiation, |x| = 2^63 + 2^62 + 2^60 + 2^57 + 2^48 + 2^16 and |x| / 2:
+// with e = 16 or 15, f^x = f^(2^e) f^(2^(e+32)) f^(2^(e+41)) f^(2^(e+44)) f^(2^(e+46)) f^(2^(e+47)).  The first e + 41 squarings
+// run compressed; the three values needed on the way are decompressed with ONE inversion (Montgomery's trick on the 4 g2), the
+// last six squarings are Granger-Scott on the decompressed value.  The result is the same field element as the reference's
+// square-and-multiply; values with a zero g2 on the way (f = 1, ...) take exp_by_x_gs.  r must not alias f.
+HDN void exp_by_x(fp12 *r, const fp12 *f, uint64_t x) {
+#if defined(B381_EXP_GS)
+    exp_by_x_gs(r, f, x);
+#else
+    int e = 0;
+    while (!((x >> e) & 1)) e++;
+    if ((x >> e) != 0xd20100000001ULL) { exp_by_x_gs(r, f, x); return; }
+    cyc4 c[3];
+    cyc_compress(&c[2], f);
+#pragma unroll 1
+    for (int i = 1; i <= e + 41; i++) {
+        cyc_sqr_compressed(&c[2]);
+        if (i == e) c[0] = c[2];
+        if (i == e + 32) c[1] = c[2];
+    }
+    // 1 / (4 g2) for the three values
+    fp2 d[3], p01, inv;
+    for (int i = 0; i < 3; i++) { fp2_dbl(d[i], c[i].g2); fp2_dbl(d[i], d[i]); }
+    if (fp2_is_zero(d[0]) || fp2_is_zero(d[1]) || fp2_is_zero(d[2])) { exp_by_x_gs(r, f, x); return; }
+    fp2_mul(&p01, &d[0], &d[1]);
+    fp2_mul(&inv, &p01, &d[2]);
+    fp2_inv(&inv, &inv);
+    fp2_mul(&p01, &p01, &inv);                         // 1 / d2
+    fp2_mul(&inv, &inv, &d[2]);                        // 1 / (d0 d1)
+    fp2_mul(&d[2], &inv, &d[0]);                       // 1 / d1
+    fp2_mul(&d[0], &inv, &d[1]);                       // 1 / d0
+    fp12 t;
+    cyc_decompress(r, &c[0], &d[0]);
+    cyc_decompress(&t, &c[1], &d[2]);
+    fp12_mul(r, r, &t);
+    cyc_decompress(&t, &c[2], &p01);
+    fp12_mul(r, r, &t);
+    fp12_cyclotomic_sqr(&t, &t); fp12_cyclotomic_sqr(&t, &t); fp12_cyclotomic_sqr(&t, &t);
+    fp12_mul(r, r, &t);                                // 2^(e+44)
+    fp12_cyclotomic_sqr(&t, &t); fp12_cyclotomic_sqr(&t, &t);
+    fp12_mul(r, r, &t);                                // 2^(e+46)
+    fp12_cyclotomic_sqr(&t, &t);
+    fp12_mul(r, r, &t);                                // 2^(e+47)
+    fp12_conj(r, r);
+#endif
 }
 
 // FinalExponentiation   (pairing.go:79-129).  Returns false for f == 0 (the reference returns nil).  `out` may alias `in`

@@ -82,6 +82,17 @@ def test_cyclotomic_square_and_exp_by_x(emu, orc):
     assert (out == orc.fq12("square", f)).all()
     emu.emu_fp12_op(16, ctypes.c_uint64(L.BLS_X), _p(f), _p(f), _p(out), ctypes.c_size_t(2))
     assert (out == orc.fq12("conjugate", orc.fq12("exp", f, None, L.BLS_X))).all()    # ExpByX, pairing.go:92-98
+    # |x| / 2 (the second ExpByX of the chain) and an exponent outside the compressed schedule (Granger-Scott fallback)
+    for x in (L.BLS_X >> 1, 0x1234567):
+        emu.emu_fp12_op(16, ctypes.c_uint64(x), _p(f), _p(f), _p(out), ctypes.c_size_t(2))
+        assert (out == orc.fq12("conjugate", orc.fq12("exp", f, None, x))).all()
+    # the degenerate value 1 (every compressed coordinate is zero; what a pairing with a point at infinity produces): the
+    # decompression would divide by zero, the fallback must give 1
+    one = np.zeros_like(f[:1]); one[0, 0, 0, 0] = L.fp_from_int(1)
+    for v in (one,):
+        o1 = np.empty_like(v)
+        emu.emu_fp12_op(16, ctypes.c_uint64(L.BLS_X), _p(v), _p(v), _p(o1), ctypes.c_size_t(1))
+        assert (o1 == orc.fq12("conjugate", orc.fq12("exp", v, None, L.BLS_X))).all()
 
 
 def test_miller_loop_and_final_exp(emu, orc, kats):

@@ -32,7 +32,7 @@ N_PAIRINGS = 1 << 16
 # Fq multiplications per pairing (mul + sqr), counted by the instrumented host build of the device
 # code (tests/test_emu.py::test_op_counts pins them) and of the reference algorithm
 W_IMPL_MILLER = 6916
-W_IMPL_FINAL_EXP = 7770          # 7768 tower work + 2 for the inversion's fix-up (the almost-inverse itself is plain integer work, not counted)
+W_IMPL_FINAL_EXP = 6411          # 7 770 with Granger-Scott squarings throughout; compressed squarings: 4 x (-342 + 69) + (-336 + 69)
 W_REF = 26546
 MACS_PER_FQ_MUL = 300            # 12x12 product + 12x12 reduction + 12 quotient words (32x32->64 each)
 METRIC = "BLS12-381 pairings/sec (batches of 2^16 independent pairings per GPU)"

@@ -11,7 +11,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01_v5"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01_v6"
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 for f in ("%s_bench.json", "%s_bench_reference_arm.json", "%s_launches.csv", "%s_bench_2gpu.json"):
     src = os.path.join(G, f % tag)

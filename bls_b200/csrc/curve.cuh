@@ -189,7 +189,7 @@ template <class F> HD void xyzz_mul_small(xyzz<F> &p, uint32_t k) {
 // doubling 2M + 5S (G1Projective.Double, g1.go:343-397: dbl-2009-l), mixed addition 7M + 4S (AddAffine, g1.go:485-559:
 // madd-2007-bl); the XYZZ doubling above costs 6M + 3S.
 template <class F> struct jac_pt { typename F::T x, y, z; };          // infinity <=> z == 0
-template <class F> HD void jac_dbl(jac_pt<F> &p) {
+template <class F> HDN void jac_dbl(jac_pt<F> &p) {
     if (F::is_zero(p.z)) return;
     typename F::T a, b, c, d, e, f;
     F::sqr(a, p.x);
@@ -211,7 +211,7 @@ template <class F> HD void jac_dbl(jac_pt<F> &p) {
     F::dbl(c, c); F::dbl(c, c); F::dbl(c, c);
     F::sub(p.y, d, c);                 // Y3 = E(D - X3) - 8C
 }
-template <class F> HD void jac_madd(jac_pt<F> &p, const typename F::T &x2, const typename F::T &y2) {
+template <class F> HDN void jac_madd(jac_pt<F> &p, const typename F::T &x2, const typename F::T &y2) {
     if (F::is_zero(p.z)) { p.x = x2; p.y = y2; F::set_one(p.z); return; }
     typename F::T z1z1, u2, s2, h, hh, i, j, r, v, t;
     F::sqr(z1z1, p.z);

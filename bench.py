@@ -173,7 +173,7 @@ def aggregate_extras(ctx, stream, dev, rank, world, torch, np):
                           np.tile(np.arange(ntmpl) % 8, natt // ntmpl).astype(np.uint32))]
     dOkA = torch.empty(natt, dtype=torch.uint8, device=dev)
     t_att = timed(lambda: ctx.dev("b381_verify_aggregate_common_batch_dev", *[x.data_ptr() for x in dA], ctypes.c_size_t(natt),
-                                  dOkA.data_ptr()), reps=2)
+                                  ctypes.c_size_t(keys.size), ctypes.c_size_t(Hs.size), dOkA.data_ptr()), reps=2)
     assert dOkA.cpu().numpy()[:ntmpl].tolist() == expect, "attestation batch verdicts differ from construction"
     ta = torch.tensor([t_att], dtype=torch.float64, device=dev)
     if world > 1:

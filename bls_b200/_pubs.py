@@ -176,6 +176,8 @@ def build(ns, key_group, doc_prefix):
                 if m == last:
                     return False
                 last = m
+            if _is_inf(self.s) or any(_is_inf(pk.p) for pk in pubKeys):
+                return False                                     # fail closed: the reference panics on these (pairing.go:17-26)
             hs = (engine().hash_g2_batch if key_group == 1 else engine().hash_g1_batch)([bytes(m) for m in msgs])
             prs = [pairs(KG.neg(KG.generator()), self.s)] + [pairs(pk.p, hs[i:i + 1]) for i, pk in enumerate(pubKeys)]
             return product_is_one([a for a, _ in prs], [b for _, b in prs])
@@ -183,8 +185,15 @@ def build(ns, key_group, doc_prefix):
         def VerifyAggregateCommon(self, pubKeys, msg):           # g1pubs/bls.go:287-290
             return Verify(msg, AggregatePublicKeys(pubKeys), self)
 
+    def _is_inf(pt):
+        return bool(np.asarray(pt["inf"]).any())
+
     def _check(pub, sig, h):
-        """CompareTwoPairings(G_key, sig, pub, h) (pairing.go:140-147)"""
+        """CompareTwoPairings(G_key, sig, pub, h) (pairing.go:140-147).  An infinite key or signature is rejected: the engine's
+        Miller loop treats a pair with a point at infinity as the factor 1 (the reference panics there, pairing.go:17-26), so
+        without this guard pub = sig = infinity would verify for every message."""
+        if _is_inf(pub.p) or _is_inf(sig.s):
+            return False
         prs = [pairs(KG.generator(), sig.s), pairs(KG.neg(pub.p), h)]
         return product_is_one([a for a, _ in prs], [b for _, b in prs])
 
@@ -236,6 +245,8 @@ def build(ns, key_group, doc_prefix):
 
         def VerifyAggregateWithDomain(self, pubKeys, msgs32, domain8):
             if len(pubKeys) != len(msgs32):
+                return False
+            if _is_inf(self.s) or any(_is_inf(pk.p) for pk in pubKeys):
                 return False
             hs = engine().hash_g2_with_domain_batch([bytes(m) for m in msgs32], bytes(domain8))
             return product_is_one([KG.neg(KG.generator())] + [pk.p for pk in pubKeys], [self.s] + [hs[i:i + 1] for i in range(len(pubKeys))])

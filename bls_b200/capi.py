@@ -46,13 +46,21 @@ def _hp(a):
 class Ctx:
     """one engine context bound to one CUDA device (b381_init / b381_free)"""
 
-    def __init__(self, device=0):
+    PATHS = {"auto": -1, "thread": 0, "vm": 1, "quad": 2, "duo": 3}
+
+    def __init__(self, device=0, path=None):
         self.lib = load()
         self._h = ctypes.c_void_p()
         rc = self.lib.b381_init(int(device), ctypes.byref(self._h))
         if rc != B381_OK:
             raise B381Error(rc, "b381_init(device=%d)" % device)
         self.device = device
+        if path is not None:
+            self.set_kernel_path(path)
+
+    def set_kernel_path(self, path):
+        """auto | thread | vm | quad | duo: which schedule of the pairing arithmetic is launched (b381_set_kernel_path)"""
+        self.call("b381_set_kernel_path", ctypes.c_int(self.PATHS[path]))
 
     def close(self):
         if self._h:
@@ -71,6 +79,28 @@ class Ctx:
 
     def call(self, name, *args):
         self._ck(getattr(self.lib, name)(self._h, *args))
+
+    # -- test hook --------------------------------------------------------------------------
+    _TEST_IN = {0: 6, 1: 12, 2: 36, 3: 72, 4: 72, 7: 72}
+
+    def test_op(self, family, op, a, b=None, arg=0):
+        """one field / tower / group-law operation of the device build (b381_test_op): returns (out, extra, ok)"""
+        if family in (5, 6):
+            dt, jdt = (L.G1_AFFINE, L.G1_JAC) if family == 5 else (L.G2_AFFINE, L.G2_JAC)
+            a = np.ascontiguousarray(a, dtype=dt); b = a if b is None else np.ascontiguousarray(b, dtype=dt)
+            n = a.size
+            out = np.zeros(n, dtype=jdt)
+        else:
+            w = self._TEST_IN[family]
+            a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, w)
+            b = a if b is None else np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, w)
+            n = a.shape[0]
+            out = np.empty_like(a)
+        assert (b.size if family in (5, 6) else b.shape[0]) == n
+        extra = np.zeros((n, 12), np.uint64); ok = np.ones(n, np.uint8)
+        self.call("b381_test_op", ctypes.c_int(family), ctypes.c_int(op), ctypes.c_uint64(arg), _hp(a), _hp(b), _hp(out), _hp(extra),
+                  _hp(ok), ctypes.c_size_t(n))
+        return out, extra, ok
 
     # -- plumbing ---------------------------------------------------------------------------
     def set_stream(self, cuda_stream_handle):
@@ -164,7 +194,8 @@ class Ctx:
         assert key_off.size == n + 1 and msg_idx.size == n
         bufs = [self.to_device(a) for a in (registry, key_idx, key_off, sig, msg_hash, msg_idx)]
         dok = self.dev_empty(max(n, 1))
-        self.call("b381_verify_aggregate_common_batch_dev", *[b.ptr for b in bufs], ctypes.c_size_t(n), dok.ptr)
+        self.call("b381_verify_aggregate_common_batch_dev", *[b.ptr for b in bufs], ctypes.c_size_t(n), ctypes.c_size_t(registry.size),
+                  ctypes.c_size_t(msg_hash.size), dok.ptr)
         return self.from_device(dok, np.uint8, n)
 
     # -- wire formats and scalar multiplication (csrc/codec.cuh) --------------------------------------------------
@@ -327,7 +358,7 @@ class Ctx:
         b = [self.to_device(a) for a in (registry, key_idx, key_off, sig, msg, dom, msg_idx)]
         dok = self.dev_empty(max(n, 1))
         self.call("b381_verify_aggregate_common_with_domain_batch_dev", b[0].ptr, b[1].ptr, b[2].ptr, b[3].ptr, b[4].ptr,
-                  ctypes.c_size_t(msg.shape[0]), b[5].ptr, b[6].ptr, ctypes.c_size_t(n), dok.ptr)
+                  ctypes.c_size_t(msg.shape[0]), b[5].ptr, b[6].ptr, ctypes.c_size_t(n), ctypes.c_size_t(registry.size), dok.ptr)
         return self.from_device(dok, np.uint8, n)
 
     # -- raw device buffers owned by the engine (b381_dev_alloc / b381_h2d / b381_d2h) ----------

@@ -264,14 +264,20 @@ template <class F, class JPOD> __global__ void __launch_bounds__(64) k_msm_combi
 __global__ void __launch_bounds__(128) k_attest_pairs(const g1_affine_pod *__restrict__ registry, const uint32_t *__restrict__ key_idx,
                                                       const uint32_t *__restrict__ key_off, const g2_affine_pod *__restrict__ sig,
                                                       const g2_affine_pod *__restrict__ msg_hash, const uint32_t *__restrict__ msg_idx,
-                                                      size_t nattest, g1_affine_pod *__restrict__ P, g2_affine_pod *__restrict__ Q,
-                                                      uint32_t *__restrict__ group_off) {
+                                                      size_t nattest, size_t nkeys, size_t nmsg, g1_affine_pod *__restrict__ P,
+                                                      g2_affine_pod *__restrict__ Q, uint32_t *__restrict__ group_off,
+                                                      uint8_t *__restrict__ valid) {
     size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (a == 0) group_off[0] = 0;
     if (a >= nattest) return;
     group_off[a + 1] = (uint32_t)(2 * a + 2);
+    // fail closed (the reference panics on these, pairing.go:17-26 / g1pubs/bls.go:287-290 with no keys): an empty committee, a
+    // key or message index outside the tables, keys that cancel to the point at infinity, an infinite signature
+    const uint32_t lo = key_off[a], hi = key_off[a + 1];
+    bool good = hi > lo && msg_idx[a] < nmsg && !sig[a].inf;
+    for (uint32_t k = lo; k < hi && good; k++) good = key_idx[k] < nkeys;
     xyzz<FpInl> acc;
-    msm_bucket_sum(acc, registry, key_idx, key_off[a], key_off[a + 1]);
+    if (good) msm_bucket_sum(acc, registry, key_idx, lo, hi); else xyzz_set_inf(acc);
     fp ox, oy, oz;
     xyzz_to_jac_normalised(ox, oy, oz, acc);
     g1_affine_pod *neg = P + 2 * a + 1, *one = P + 2 * a;
@@ -288,7 +294,13 @@ __global__ void __launch_bounds__(128) k_attest_pairs(const g1_affine_pod *__res
     one->inf = 0;
     for (int i = 0; i < 7; i++) one->pad[i] = 0;
     Q[2 * a] = sig[a];
-    Q[2 * a + 1] = msg_hash[msg_idx[a]];
+    Q[2 * a + 1] = msg_hash[msg_idx[a] < nmsg ? msg_idx[a] : 0];
+    valid[a] = (good && !inf) ? 1 : 0;
+}
+// ok[i] &= valid[i]
+__global__ void k_and_bytes2(uint8_t *__restrict__ ok, const uint8_t *__restrict__ valid, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ok[i] = (ok[i] && valid[i]) ? 1 : 0;
 }
 
 #endif  // __CUDACC__

@@ -15,6 +15,9 @@
 #include "hash.cuh"
 #include "swu.cuh"
 #include "vm.cuh"
+#include "quad.cuh"
+#include "duo.cuh"
+#include "testops.cuh"
 #include "vm_programs.inc"
 #include <stdlib.h>
 
@@ -140,6 +143,118 @@ __global__ void k_fp12_is_one(const uint64_t *__restrict__ fe, size_t n, uint8_t
     ok[i] = (ok[i] && d == 0) ? 1 : 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// kernels: four lanes per pairing (csrc/quad.cuh), persistent -- every warp walks the batch in rounds of 8 pairings
+// ---------------------------------------------------------------------------------------------
+#ifndef QUAD_BLOCK
+#define QUAD_BLOCK 64          // two warps = 16 pairings per block and round
+#endif
+#ifndef QUAD_MIN_BLOCKS
+#define QUAD_MIN_BLOCKS 7      // 14 warps per SM at <= 144 registers: 2^16 pairings = 3.95 rounds of 148 x 7 x 16
+#endif
+// unit of the calling lane in round `it`, warp-uniform activity; returns false when the whole warp is past the end
+__device__ __forceinline__ bool quad_unit(size_t it, size_t n, size_t &unit, bool &active) {
+    const size_t per_block = QUAD_BLOCK / 4;
+    const size_t warp_first = (it * gridDim.x + blockIdx.x) * per_block + (threadIdx.x >> 5) * 8;
+    if (warp_first >= n) return false;
+    unit = warp_first + ((threadIdx.x & 31u) >> 2);
+    active = unit < n;
+    if (!active) unit = n - 1;                      // idle quads of the last warp recompute the last unit (shuffles need them)
+    return true;
+}
+// out[i] = MillerLoop of the NP pairs (p, q)[NP i .. NP i + NP)   (pairing.go:16-75 fused with g2.go:650-801)
+template <int NP>
+__global__ void __launch_bounds__(QUAD_BLOCK, QUAD_MIN_BLOCKS) k_quad_miller_loop(const g1_affine_pod *__restrict__ p,
+                                                                                   const g2_affine_pod *__restrict__ q, size_t n,
+                                                                                   uint64_t *__restrict__ out) {
+    for (size_t it = 0;; it++) {
+        size_t u; bool active;
+        if (!quad_unit(it, n, u, active)) break;
+        quad::q6 F; quad::qpair S[NP]; quad::qlive lv[NP];
+#pragma unroll
+        for (int k = 0; k < NP; k++) { quad::qpair_load(&S[k], p + NP * u + k, q + NP * u + k); quad::qpair_live(lv[k], p + NP * u + k, q + NP * u + k); }
+        quad::q_miller_loop<NP>(&F, S, lv);
+        if (active) quad::q12_store(out + 72 * u, &F);
+    }
+}
+// out[i] = FinalExponentiation(in[i])   (pairing.go:79-129); in place allowed; MODE 1: ok[i] = (result == 1) and no value is written
+template <int MODE>
+__global__ void __launch_bounds__(QUAD_BLOCK, QUAD_MIN_BLOCKS) k_quad_final_exp(const uint64_t *in, size_t n, uint64_t *out, uint8_t *ok) {
+    for (size_t it = 0;; it++) {
+        size_t u; bool active;
+        if (!quad_unit(it, n, u, active)) break;
+        quad::q6 F; bool good[1], isone[1];
+        quad::q12_load(&F, in + 72 * u);
+        quad::q_final_exp(&F, good);
+        if (MODE == 1) {
+            quad::q12_is_one(isone, &F);
+            if (active && (threadIdx.x & 3u) == 0) ok[u] = (good[0] && isone[0]) ? 1 : 0;
+        } else {
+            if (!good[0]) quad::q12_set_one(&F);           // f == 0: report 1 with ok = 0 like the other paths
+            if (active) {
+                quad::q12_store(out + 72 * u, &F);
+                if (ok && (threadIdx.x & 3u) == 0) ok[u] = good[0] ? 1 : 0;
+            }
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// kernels: two lanes per pairing (csrc/duo.cuh), persistent -- every warp walks the batch in rounds of 16 pairings
+// ---------------------------------------------------------------------------------------------
+#ifndef DUO_BLOCK
+#define DUO_BLOCK 64           // two warps = 32 pairings per block and round
+#endif
+#ifndef DUO_MIN_BLOCKS
+#define DUO_MIN_BLOCKS 7       // 14 warps per SM: 2^16 pairings = 2048 block-rounds = 1.98 rounds of 148 x 7 blocks
+#endif
+__device__ __forceinline__ bool duo_unit(size_t it, size_t n, size_t &unit, bool &active) {
+    const size_t per_block = DUO_BLOCK / 2;
+    const size_t warp_first = (it * gridDim.x + blockIdx.x) * per_block + (threadIdx.x >> 5) * 16;
+    if (warp_first >= n) return false;
+    unit = warp_first + ((threadIdx.x & 31u) >> 1);
+    active = unit < n;
+    if (!active) unit = n - 1;                      // idle pairs of the last warp recompute the last unit (shuffles name all lanes)
+    return true;
+}
+template <int NP>
+__global__ void __launch_bounds__(DUO_BLOCK, DUO_MIN_BLOCKS) k_duo_miller_loop(const g1_affine_pod *__restrict__ p,
+                                                                                const g2_affine_pod *__restrict__ q, size_t n,
+                                                                                uint64_t *__restrict__ out) {
+    for (size_t it = 0;; it++) {
+        size_t u; bool active;
+        if (!duo_unit(it, n, u, active)) break;
+        duo::d12 F; duo::dpair S[NP];
+#pragma unroll
+        for (int k = 0; k < NP; k++) duo::dpair_load(&S[k], p + NP * u + k, q + NP * u + k);
+        duo::d_miller_loop<NP>(&F, S);
+        if (active) duo::d12_store(out + 72 * u, &F);
+    }
+}
+// MODE 0: out[i] = FinalExponentiation(in[i]), ok[i] = (in[i] != 0) if ok;  MODE 1: ok[i] = (FinalExponentiation(in[i]) == 1), no value
+template <int MODE>
+__global__ void __launch_bounds__(DUO_BLOCK, DUO_MIN_BLOCKS) k_duo_final_exp(const uint64_t *in, size_t n, uint64_t *out, uint8_t *ok) {
+    for (size_t it = 0;; it++) {
+        size_t u; bool active;
+        if (!duo_unit(it, n, u, active)) break;
+        duo::d12 F; duo::dflag good, isone;
+        duo::d12_load(&F, in + 72 * u);
+        duo::d_final_exp(&F, good);
+        if (MODE == 1) {
+            duo::d12_is_one(isone, &F);
+            if (active && (threadIdx.x & 1u) == 0) ok[u] = (good.on[0] && isone.on[0]) ? 1 : 0;
+        } else {
+            if (!good.on[0]) duo::d12_set_one(&F);
+            if (active) {
+                duo::d12_store(out + 72 * u, &F);
+                if (ok && (threadIdx.x & 1u) == 0) ok[u] = good.on[0] ? 1 : 0;
+            }
+        }
+    }
+}
+
 // Roofline denominator: sustained issue rate of IMAD.WIDE.U32 (the 32x32->64 multiply-accumulate
 // every Fq multiplication is made of).  8 independent chains per thread; each thread executes
 // iters * 8 wide MACs.
@@ -188,11 +303,11 @@ struct b381_ctx {
     uint64_t launches;
     char err[256];
     // grow-only device scratch
-    void *scratch[24];
-    size_t scratch_bytes[24];
+    void *scratch[32];
+    size_t scratch_bytes[32];
     // warp-cooperative VM programs resident on the device (csrc/vm.cuh)
     struct { uint4 *code, *consts; int lanes, nsteps, nslots, spill_fq; } vm[3];
-    int use_vm;
+    int path;                // -1 by batch size, 0 one pairing per thread, 1 warp-cooperative VM, 2 four lanes per pairing
     int vm_split;
 };
 enum { VM_ML1 = 0, VM_FE_A = 1, VM_FE_C = 2 };
@@ -214,6 +329,7 @@ enum { VM_ML1 = 0, VM_FE_A = 1, VM_FE_C = 2 };
 //   15-18  wire-level verify: decoded keys, decoded signatures, message points, status + validity bytes
 //   19, 20  wire-level verify host staging (inputs, verdicts)                       21  largest group size (tree product)
 //   22  group offsets of the random-linear-combination check                        23  its G2 sum + "any invalid" flag
+//   24  validity bytes of an attestation batch                                      25-27  prepared G2 line coefficients / staging
 static int scratch_get(b381_ctx *ctx, int slot, size_t bytes, void **out) {
     if (ctx->scratch_bytes[slot] < bytes) {
         if (ctx->scratch[slot]) {
@@ -230,7 +346,17 @@ static int scratch_get(b381_ctx *ctx, int slot, size_t bytes, void **out) {
 
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 #define VM_MAX_UNITS 12288      // measured crossover on B200 (tools/small_bench.py): 8192 pairings 11.8 ms (VM) vs 24.1 ms; 16384: 23.2 vs 24.2
-static inline bool vm_for(const b381_ctx *ctx, size_t n) { return ctx->use_vm < 0 ? n <= VM_MAX_UNITS : ctx->use_vm != 0; }
+static inline bool vm_for(const b381_ctx *ctx, size_t n) { return ctx->path < 0 ? n <= VM_MAX_UNITS : ctx->path == 1; }
+static inline bool quad_for(const b381_ctx *ctx, size_t n) { (void)n; return ctx->path == 2; }
+static inline bool duo_for(const b381_ctx *ctx, size_t n) { return ctx->path < 0 ? n > VM_MAX_UNITS : ctx->path == 3; }
+// persistent grid: the block-rounds of the batch spread evenly over the fewest rounds of sms x min_blocks resident blocks
+static inline unsigned lane_grid(const b381_ctx *ctx, size_t n, size_t per_block, size_t min_blocks) {
+    size_t want = (n + per_block - 1) / per_block, cap = (size_t)ctx->sms * min_blocks;
+    size_t rounds = (want + cap - 1) / cap;
+    return (unsigned)(rounds ? (want + rounds - 1) / rounds : 1);
+}
+static inline unsigned quad_grid(const b381_ctx *ctx, size_t n) { return lane_grid(ctx, n, QUAD_BLOCK / 4, QUAD_MIN_BLOCKS); }
+static inline unsigned duo_grid(const b381_ctx *ctx, size_t n) { return lane_grid(ctx, n, DUO_BLOCK / 2, DUO_MIN_BLOCKS); }
 static inline size_t vm_smem_bytes(int lanes, int nslots) { return (size_t)VM2_WARPS * (32 / lanes) * nslots * 96; }
 #define VM_SPLIT_MAX_UNITS 592     // up to one warp of 4 units per SM: below this only latency matters -> two lanes per Fq2 operation
 
@@ -244,7 +370,7 @@ static int vm_run(b381_ctx *ctx, int which, const vm_seg seg[4], size_t n, const
     A.nsteps = ctx->vm[which].nsteps; A.nslots = ctx->vm[which].nslots; A.n = n;
     A.flag_a = flag_a; A.flag_b = flag_b; A.flag_stride_a = fsa; A.flag_stride_b = fsb; A.ok = ok;
     int lanes = ctx->vm[which].lanes, upb = VM2_WARPS * (32 / lanes);
-    if (n <= VM_SPLIT_MAX_UNITS && ctx->vm_split)
+    if ((n <= VM_SPLIT_MAX_UNITS && ctx->vm_split) || ctx->vm_split == 2)
         k_vm2<4, 2><<<grid_for(n, upb / 2), VM2_WARPS * 32, vm_smem_bytes(2 * lanes, A.nslots), ctx->stream>>>(A);
     else
         k_vm2<4, 1><<<grid_for(n, upb), VM2_WARPS * 32, vm_smem_bytes(lanes, A.nslots), ctx->stream>>>(A);
@@ -292,9 +418,11 @@ int b381_init(int device, b381_ctx **out) {
     // 2-3x lower latency, no DRAM traffic, fills the GPU from ~8 k pairings) and one pairing per thread (higher
     // throughput once ~65 k threads are resident).  Default: by batch size; B381_VM=0/1 forces one of them for A/B measurements.
     const char *ev = getenv("B381_VM");
-    ctx->use_vm = ev ? (ev[0] == '0' ? 0 : 1) : -1;
+    ctx->path = ev ? (ev[0] == '0' ? 0 : 1) : -1;
+    const char *ep = getenv("B381_PATH");          // thread | vm | quad | auto (same as b381_set_kernel_path)
+    if (ep) ctx->path = ep[0] == 't' ? 0 : ep[0] == 'v' ? 1 : ep[0] == 'q' ? 2 : ep[0] == 'd' ? 3 : -1;
     const char *es = getenv("B381_VM_SPLIT");       // 0 disables the two-lanes-per-operation latency form (A/B measurements)
-    ctx->vm_split = es ? (es[0] != '0') : 1;
+    ctx->vm_split = es ? (es[0] == '2' ? 2 : es[0] != '0') : 1;      // 2: the two-lane form at every batch size (measurements)
     *out = ctx;
     return B381_OK;
 }
@@ -303,7 +431,7 @@ void b381_free(b381_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 24; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < 32; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     for (int i = 0; i < 3; i++) { if (ctx->vm[i].code) cudaFree(ctx->vm[i].code); if (ctx->vm[i].consts) cudaFree(ctx->vm[i].consts); }
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -319,6 +447,11 @@ int b381_set_stream(b381_ctx *ctx, void *cuda_stream) {
 int b381_use_own_stream(b381_ctx *ctx) {
     if (!ctx) return B381_ERR_ARG;
     ctx->stream = ctx->own_stream;
+    return B381_OK;
+}
+int b381_set_kernel_path(b381_ctx *ctx, int path) {
+    if (!ctx || path < B381_PATH_AUTO || path > B381_PATH_DUO) return B381_ERR_ARG;
+    ctx->path = path;
     return B381_OK;
 }
 int b381_sync(b381_ctx *ctx) {
@@ -392,6 +525,44 @@ int b381_vm_exec_dev(b381_ctx *ctx, const void *code, int lanes, int nsteps, int
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     cudaFree(dcode); cudaFree(dconst);
     if (e != cudaSuccess) { snprintf(ctx->err, sizeof ctx->err, "vm_exec: %s", cudaGetErrorString(e)); return B381_ERR_CUDA; }
+    return B381_OK;
+}
+
+// test hook (csrc/testops.cuh): one field / tower / group-law operation of the DEVICE build over n host-resident operand pairs
+int b381_test_op(b381_ctx *ctx, int family, int op, uint64_t arg, const void *a, const void *b, void *out, void *out2, uint8_t *ok, size_t n) {
+    static const size_t in_sz[8] = {48, 96, 288, 576, 576, sizeof(b381_g1_affine), sizeof(b381_g2_affine), 576};
+    static const size_t out_sz[8] = {48, 96, 288, 576, 576, sizeof(b381_g1_jac), sizeof(b381_g2_jac), 576};
+    if (!ctx || family < 0 || family > 7 || (n && (!a || !b || !out))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    CK(cudaSetDevice(ctx->device));
+    void *da, *db, *dout, *dok;
+    int rc = scratch_get(ctx, 12, n * in_sz[family], &da); if (rc) return rc;
+    rc = scratch_get(ctx, 13, n * in_sz[family], &db); if (rc) return rc;
+    rc = scratch_get(ctx, 14, n * (out_sz[family] + 96), &dout); if (rc) return rc;
+    rc = scratch_get(ctx, 11, n, &dok); if (rc) return rc;
+    uint64_t *dout2 = (uint64_t *)((char *)dout + n * out_sz[family]);
+    CK(cudaMemcpyAsync(da, a, n * in_sz[family], cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(db, b, n * in_sz[family], cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(dok, 1, n, ctx->stream));
+    CK(cudaMemsetAsync(dout2, 0, n * 96, ctx->stream));
+    const uint64_t *ua = (const uint64_t *)da, *ub = (const uint64_t *)db;
+    uint64_t *uo = (uint64_t *)dout;
+    switch (family) {
+        case 0: k_test_fp<<<grid_for(n, 64), 64, 0, ctx->stream>>>(op, ua, ub, uo, n); break;
+        case 1: k_test_fp2<<<grid_for(n, 64), 64, 0, ctx->stream>>>(op, ua, ub, uo, n); break;
+        case 2: k_test_fp6<<<grid_for(n, 64), 64, 0, ctx->stream>>>(op, arg, ua, ub, uo, n); break;
+        case 3: k_test_fp12<<<grid_for(n, 64), 64, 0, ctx->stream>>>(op, arg, ua, ub, uo, (uint8_t *)dok, n); break;
+        case 4: k_test_quad12<<<grid_for(4 * n, 64), 64, 0, ctx->stream>>>(op, arg, ua, ub, uo, dout2, (uint8_t *)dok, n); break;
+        case 7: k_test_duo12<<<grid_for(2 * n, 64), 64, 0, ctx->stream>>>(op, arg, ua, ub, uo, (uint8_t *)dok, n); break;
+        case 5: k_test_group<FpInl, g1_affine_pod, g1_jac_pod><<<grid_for(n, 64), 64, 0, ctx->stream>>>(op, (const g1_affine_pod *)da, (const g1_affine_pod *)db, (g1_jac_pod *)dout, n); break;
+        case 6: k_test_group<Fp2Out, g2_affine_pod, g2_jac_pod><<<grid_for(n, 64), 64, 0, ctx->stream>>>(op, (const g2_affine_pod *)da, (const g2_affine_pod *)db, (g2_jac_pod *)dout, n); break;
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout, n * out_sz[family], cudaMemcpyDeviceToHost, ctx->stream));
+    if (out2) CK(cudaMemcpyAsync(out2, dout2, n * 96, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ok) CK(cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return B381_OK;
 }
 
@@ -552,8 +723,15 @@ int b381_miller_loop_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b
         return vm_run(ctx, VM_ML1, seg, n, (const unsigned char *)d_p + 96, sizeof(b381_g1_affine),
                       (const unsigned char *)d_q + 192, sizeof(b381_g2_affine), nullptr);
     }
-    k_miller_loop<<<grid_for(n, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>(
-        (const g1_affine_pod *)d_p, (const g2_affine_pod *)d_q, n, (uint64_t *)d_out);
+    if (duo_for(ctx, n))
+        k_duo_miller_loop<1><<<duo_grid(ctx, n), DUO_BLOCK, 0, ctx->stream>>>((const g1_affine_pod *)d_p, (const g2_affine_pod *)d_q, n,
+                                                                              (uint64_t *)d_out);
+    else if (quad_for(ctx, n))
+        k_quad_miller_loop<1><<<quad_grid(ctx, n), QUAD_BLOCK, 0, ctx->stream>>>((const g1_affine_pod *)d_p, (const g2_affine_pod *)d_q, n,
+                                                                                (uint64_t *)d_out);
+    else
+        k_miller_loop<<<grid_for(n, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>(
+            (const g1_affine_pod *)d_p, (const g2_affine_pod *)d_q, n, (uint64_t *)d_out);
     ctx->launches++;
     CK(cudaGetLastError());
     return B381_OK;
@@ -586,8 +764,13 @@ int b381_final_exp_batch_dev(b381_ctx *ctx, const b381_fp12 *d_in, size_t n, b38
                         {(unsigned char *)d_out, sizeof(b381_fp12)}, {(unsigned char *)spill, (size_t)ctx->vm[VM_FE_C].spill_fq * sizeof(b381_fp)}};
         return vm_run(ctx, VM_FE_C, sc, n, nullptr, 0, nullptr, 0, (unsigned char *)dok);
     }
-    k_final_exp<<<grid_for(n, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>((const uint64_t *)d_in, n,
-                                                                              (uint64_t *)d_out, d_ok);
+    if (duo_for(ctx, n))
+        k_duo_final_exp<0><<<duo_grid(ctx, n), DUO_BLOCK, 0, ctx->stream>>>((const uint64_t *)d_in, n, (uint64_t *)d_out, d_ok);
+    else if (quad_for(ctx, n))
+        k_quad_final_exp<0><<<quad_grid(ctx, n), QUAD_BLOCK, 0, ctx->stream>>>((const uint64_t *)d_in, n, (uint64_t *)d_out, d_ok);
+    else
+        k_final_exp<<<grid_for(n, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>((const uint64_t *)d_in, n,
+                                                                                  (uint64_t *)d_out, d_ok);
     ctx->launches++;
     CK(cudaGetLastError());
     return B381_OK;
@@ -638,8 +821,13 @@ static int final_exp_is_one(b381_ctx *ctx, void *prod, size_t ngroups, uint8_t *
         CK(cudaGetLastError());
         return B381_OK;
     }
-    k_final_exp_is_one<<<grid_for(ngroups, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>((const uint64_t *)prod,
-                                                                                          ngroups, d_ok);
+    if (duo_for(ctx, ngroups))
+        k_duo_final_exp<1><<<duo_grid(ctx, ngroups), DUO_BLOCK, 0, ctx->stream>>>((const uint64_t *)prod, ngroups, nullptr, d_ok);
+    else if (quad_for(ctx, ngroups))
+        k_quad_final_exp<1><<<quad_grid(ctx, ngroups), QUAD_BLOCK, 0, ctx->stream>>>((const uint64_t *)prod, ngroups, nullptr, d_ok);
+    else
+        k_final_exp_is_one<<<grid_for(ngroups, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>((const uint64_t *)prod,
+                                                                                              ngroups, d_ok);
     ctx->launches++;
     CK(cudaGetLastError());
     return B381_OK;
@@ -668,8 +856,15 @@ static int pairs2_product_is_one(b381_ctx *ctx, const b381_g1_affine *d_p, const
     void *prod;
     int rc = scratch_get(ctx, 1, ngroups * sizeof(b381_fp12), &prod);
     if (rc) return rc;
-    k_miller_loop2<<<grid_for(ngroups, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>((const g1_affine_pod *)d_p, (const g2_affine_pod *)d_q,
-                                                                                       ngroups, (uint64_t *)prod);
+    if (duo_for(ctx, ngroups))
+        k_duo_miller_loop<2><<<duo_grid(ctx, ngroups), DUO_BLOCK, 0, ctx->stream>>>((const g1_affine_pod *)d_p, (const g2_affine_pod *)d_q,
+                                                                                    ngroups, (uint64_t *)prod);
+    else if (quad_for(ctx, ngroups))
+        k_quad_miller_loop<2><<<quad_grid(ctx, ngroups), QUAD_BLOCK, 0, ctx->stream>>>((const g1_affine_pod *)d_p, (const g2_affine_pod *)d_q,
+                                                                                      ngroups, (uint64_t *)prod);
+    else
+        k_miller_loop2<<<grid_for(ngroups, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>((const g1_affine_pod *)d_p, (const g2_affine_pod *)d_q,
+                                                                                           ngroups, (uint64_t *)prod);
     ctx->launches++;
     CK(cudaGetLastError());
     return final_exp_is_one(ctx, prod, ngroups, d_ok);
@@ -896,11 +1091,13 @@ int b381_g2_msm_dev(b381_ctx *ctx, const b381_g2_affine *d_p, const b381_scalar 
 int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_registry, const uint32_t *d_key_idx,
                                            const uint32_t *d_key_off, const b381_g2_affine *d_sig,
                                            const b381_g2_affine *d_msg_hash, const uint32_t *d_msg_idx, size_t nattest,
-                                           uint8_t *d_ok) {
+                                           size_t nkeys, size_t nmsg, uint8_t *d_ok) {
     if (!ctx || nattest > 0x7FFFFFF0u) return B381_ERR_ARG;
     if (!nattest) return B381_OK;
-    if (!d_registry || !d_key_idx || !d_key_off || !d_sig || !d_msg_hash || !d_msg_idx || !d_ok) return B381_ERR_ARG;
-    void *P, *Q, *off;
+    if (!d_registry || !d_key_idx || !d_key_off || !d_sig || !d_msg_hash || !d_msg_idx || !d_ok || !nkeys || !nmsg) return B381_ERR_ARG;
+    void *P, *Q, *off, *valid;
+    int rcv = scratch_get(ctx, 24, nattest, &valid);
+    if (rcv) return rcv;
     int rc = scratch_get(ctx, 2, 2 * nattest * sizeof(b381_g1_affine), &P);
     if (rc) return rc;
     rc = scratch_get(ctx, 3, 2 * nattest * sizeof(b381_g2_affine), &Q);
@@ -909,11 +1106,16 @@ int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *
     if (rc) return rc;
     k_attest_pairs<<<grid_for(nattest, 128), 128, 0, ctx->stream>>>((const g1_affine_pod *)d_registry, d_key_idx, d_key_off,
                                                                     (const g2_affine_pod *)d_sig, (const g2_affine_pod *)d_msg_hash,
-                                                                    d_msg_idx, nattest, (g1_affine_pod *)P, (g2_affine_pod *)Q,
-                                                                    (uint32_t *)off);
+                                                                    d_msg_idx, nattest, nkeys, nmsg, (g1_affine_pod *)P, (g2_affine_pod *)Q,
+                                                                    (uint32_t *)off, (uint8_t *)valid);
     ctx->launches++;
     CK(cudaGetLastError());
-    return pairs2_product_is_one(ctx, (b381_g1_affine *)P, (b381_g2_affine *)Q, nattest, (uint32_t *)off, d_ok);
+    rc = pairs2_product_is_one(ctx, (b381_g1_affine *)P, (b381_g2_affine *)Q, nattest, (uint32_t *)off, d_ok);
+    if (rc) return rc;
+    k_and_bytes2<<<grid_for(nattest, 256), 256, 0, ctx->stream>>>(d_ok, (const uint8_t *)valid, nattest);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
 }
 
 // VerifyAggregateCommonWithDomain (g1pubs/bls.go:294-297) for a batch of attestations given as they arrive: compressed
@@ -922,7 +1124,8 @@ int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *
 // aggregation, one CompareTwoPairings per attestation.
 int b381_verify_aggregate_common_with_domain_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_registry, const uint32_t *d_key_idx,
                                                        const uint32_t *d_key_off, const uint8_t *d_sig96, const uint8_t *d_msg32, size_t nmsg,
-                                                       const uint8_t *d_domain8, const uint32_t *d_msg_idx, size_t nattest, uint8_t *d_ok) {
+                                                       const uint8_t *d_domain8, const uint32_t *d_msg_idx, size_t nattest, size_t nkeys,
+                                                       uint8_t *d_ok) {
     if (!ctx || nattest > 0x7FFFFFF0u) return B381_ERR_ARG;
     if (!nattest) return B381_OK;
     if (!d_registry || !d_key_idx || !d_key_off || !d_sig96 || !d_msg32 || !nmsg || !d_domain8 || !d_msg_idx || !d_ok) return B381_ERR_ARG;
@@ -933,7 +1136,7 @@ int b381_verify_aggregate_common_with_domain_batch_dev(b381_ctx *ctx, const b381
     rc = b381_g2_decompress_batch_dev(ctx, d_sig96, nattest, 1, (b381_g2_affine *)sig, (uint8_t *)st); if (rc) return rc;
     rc = b381_hash_g2_with_domain_batch_dev(ctx, d_msg32, d_domain8, 0, nmsg, (b381_g2_affine *)H); if (rc) return rc;
     rc = b381_verify_aggregate_common_batch_dev(ctx, d_registry, d_key_idx, d_key_off, (const b381_g2_affine *)sig, (const b381_g2_affine *)H,
-                                                d_msg_idx, nattest, d_ok);
+                                                d_msg_idx, nattest, nkeys, nmsg, d_ok);
     if (rc) return rc;
     k_and_status_g2<<<grid_for(nattest, 256), 256, 0, ctx->stream>>>(d_ok, (const uint8_t *)st, (const g2_affine_pod *)sig, nattest);
     ctx->launches++;

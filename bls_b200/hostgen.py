@@ -192,6 +192,18 @@ def g1_neg(p):
     return out
 
 
+def g2_neg(p):
+    """negate affine G2 points (numpy G2_AFFINE): both coefficients of y"""
+    out = p.copy()
+    ys = out["y"].reshape(-1, 2, 6)
+    for i in range(out.size):
+        if not out["inf"].flat[i]:
+            for c in range(2):
+                y = L.limbs_to_int(ys[i, c])
+                ys[i, c] = np.array(L.int_to_limbs((Q - y) % Q), dtype=np.uint64)
+    return out
+
+
 def splitmix_scalars(seed, n):
     """n deterministic canonical scalars < r as (n, 4) u64 (splitmix64 words, reduced mod r)"""
     x = seed & 0xFFFFFFFFFFFFFFFF

@@ -63,6 +63,15 @@ const char *b381_last_error(const b381_ctx *ctx);
 int b381_set_stream(b381_ctx *ctx, void *cuda_stream);
 int b381_use_own_stream(b381_ctx *ctx);
 int b381_sync(b381_ctx *ctx);
+/* Which of the three schedules of the SAME arithmetic (bit-identical results) the pairing entry points launch:
+ * AUTO picks by batch size (small batches: the warp-cooperative VM, low latency; large batches: two lanes per pairing,
+ * k_duo_*, half the tower state per lane); THREAD is one pairing per thread (k_miller_loop / k_final_exp, the round-1
+ * throughput path) and QUAD four lanes per pairing (k_quad_*): both kept for A/B measurements and as further
+ * implementations the parity tests run.  The reference has one
+ * schedule (pairing.go:16-129); this call has no reference counterpart.  Env B381_PATH=auto|thread|vm|quad|duo sets the
+ * initial value. */
+enum { B381_PATH_AUTO = -1, B381_PATH_THREAD = 0, B381_PATH_VM = 1, B381_PATH_QUAD = 2, B381_PATH_DUO = 3 };
+int b381_set_kernel_path(b381_ctx *ctx, int path);
 /* number of kernels this ctx has launched so far */
 uint64_t b381_launch_count(const b381_ctx *ctx);
 
@@ -136,7 +145,7 @@ int b381_g1_fold_dev(b381_ctx *ctx, const b381_g1_jac *d_parts, size_t n, b381_g
 int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_registry,
                                            const uint32_t *d_key_idx, const uint32_t *d_key_off,
                                            const b381_g2_affine *d_sig, const b381_g2_affine *d_msg_hash,
-                                           const uint32_t *d_msg_idx, size_t nattest, uint8_t *d_ok);
+                                           const uint32_t *d_msg_idx, size_t nattest, size_t nkeys, size_t nmsg, uint8_t *d_ok);
 /* The same batch as the attestations arrive on the wire: compressed aggregate signatures (n x 96 bytes) and 32-byte
  * message hashes (nmsg DISTINCT messages, msg_idx[a] selects one) with one 8-byte domain.  On the device:
  * DeserializeSignature with the subgroup check (g1pubs/bls.go:38-45), HashG2WithDomain per distinct message
@@ -146,7 +155,7 @@ int b381_verify_aggregate_common_with_domain_batch_dev(b381_ctx *ctx, const b381
                                                        const uint32_t *d_key_idx, const uint32_t *d_key_off,
                                                        const uint8_t *d_sig96, const uint8_t *d_msg32, size_t nmsg,
                                                        const uint8_t *d_domain8, const uint32_t *d_msg_idx, size_t nattest,
-                                                       uint8_t *d_ok);
+                                                       size_t nkeys, uint8_t *d_ok);
 
 /* ---- wire formats and scalar multiplication (the callers on either side of the verification path) ------------ */
 /* DecompressG1 (check_subgroup != 0, g1.go:185-195) / DecompressG1Unchecked (g1.go:199-227) over n x 48 bytes;
@@ -287,6 +296,14 @@ int b381_fpmul_probe_dev(b381_ctx *ctx, uint32_t *d_out, int blocks, int threads
  * tests/test_gpu_vm.py drives random programs through it against the big-integer emulator.              */
 int b381_vm_exec_dev(b381_ctx *ctx, const void *code, int lanes, int nsteps, int nslots, const void *consts, int nconsts,
                      void *const d_seg[4], const size_t stride[4], size_t n);
+
+/* test hook: ONE operation of the device build of the field / tower / group-law routines over n operand pairs in host
+ * memory, so the reference's known-answer tests (fq_test.go:189-207, fq2_test.go:71-246, g1_test.go:62-104) and edge operands
+ * reach the CUDA code directly (tests/test_gpu_ops.py).  family: 0 Fq (48 B) 1 Fq2 (96 B) 2 Fq6 (288 B) 3 Fq12 one element per
+ * thread (576 B) 4 Fq12 on four lanes (576 B) 5 G1 / 6 G2 group law (affine PODs in, normalised Jacobian out); op codes in
+ * bls_b200/csrc/testops.cuh.  out2 (n x 96 B) and ok (n bytes) may be NULL. */
+int b381_test_op(b381_ctx *ctx, int family, int op, uint64_t arg, const void *a, const void *b, void *out, void *out2, uint8_t *ok,
+                 size_t n);
 
 #ifdef __cplusplus
 }

@@ -67,3 +67,5 @@ void emu_final_exp(const uint64_t *in, size_t n, uint64_t *out, uint8_t *ok) {
 extern "C" void emu_miller_loop2(const g1_affine_pod *p, const g2_affine_pod *q, size_t ngroups, uint64_t *out) {
     for (size_t i = 0; i < ngroups; i++) { fp12 f; miller_loop_two(&f, p + 2 * i, q + 2 * i); fp12_store_u64(out + 72 * i, &f); }
 }
+#include "emu_quad.inc"
+#include "emu_duo.inc"

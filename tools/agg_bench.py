@@ -36,5 +36,5 @@ for natt in (1 << 12, 1 << 15):
     midx = rng.randint(0, 64, size=natt).astype(np.uint32)
     d = [up(x) for x in (base, kidx, koff, sig, H, midx)]
     dok = torch.empty(natt, dtype=torch.uint8, device=dev)
-    res["verify_batch_%d_ms" % natt] = timed(lambda: ctx.dev("b381_verify_aggregate_common_batch_dev", *[x.data_ptr() for x in d], ctypes.c_size_t(natt), dok.data_ptr()), reps=2)
+    res["verify_batch_%d_ms" % natt] = timed(lambda: ctx.dev("b381_verify_aggregate_common_batch_dev", *[x.data_ptr() for x in d], ctypes.c_size_t(natt), ctypes.c_size_t(base.size), ctypes.c_size_t(H.size), dok.data_ptr()), reps=2)
     print(json.dumps(res), flush=True)

@@ -9,10 +9,12 @@ from bls_b200 import hostgen as hg, layout as L
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ctx():
+# the verification tests below run on the VM kernels ("auto" at these sizes), on the one-pairing-per-thread kernels incl. the
+# shared-accumulator k_miller_loop2, and on the two-lane kernels (k_duo_miller_loop<2>): b381_set_kernel_path
+@pytest.fixture(scope="module", params=["auto", "thread", "duo"])
+def ctx(request):
     from bls_b200 import capi
-    c = capi.Ctx(0)
+    c = capi.Ctx(0, path=request.param)
     yield c
     c.close()
 
@@ -198,6 +200,34 @@ def test_verify_aggregate_empty_committee_and_batch(ctx, orc):
     ok = ctx.verify_aggregate_common_batch(reg, kidx, koff2, sig, H, midx)
     assert ok.tolist() == [expect[0], 0, 0]
     assert ctx.verify_aggregate_common_batch(reg, kidx[:0], np.zeros(1, np.uint32), sig[:0], H, midx[:0]).size == 0
+
+
+def test_attestation_batch_fails_closed(ctx, orc):
+    """an attestation must not verify by degenerating.  With an infinite aggregate signature the check of an EMPTY
+    committee (or of keys that cancel) would reduce to 1 == 1, because the engine's Miller loop treats a pair with a point at
+    infinity as the factor 1 where the reference panics (pairing.go:17-26).  Such attestations, and ones whose key / message
+    indices leave the tables, are reported false."""
+    reg, kidx, koff, sig, H, midx, expect = _attestations(orc, 16, 5, 4, 2, 9)
+    base = ctx.verify_aggregate_common_batch(reg, kidx, koff, sig, H, midx).tolist()
+    assert base == expect
+    # (1) empty committee + infinite signature
+    koff1 = koff.copy(); koff1[1:] = koff1[1]
+    sig1 = sig.copy(); sig1["inf"][1] = 1
+    assert ctx.verify_aggregate_common_batch(reg, kidx, koff1, sig1, H, midx).tolist()[1] == 0
+    # (2) a committee whose keys cancel (P and -P) + infinite signature
+    reg2 = np.concatenate([reg, hg.g1_neg(reg[:1])])
+    assert koff[3] - koff[2] == 4
+    kidx2 = kidx.copy(); kidx2[koff[2]:koff[3]] = [0, reg.size, 0, reg.size]
+    sig2 = sig.copy(); sig2["inf"][2] = 1
+    assert ctx.verify_aggregate_common_batch(reg2, kidx2, koff, sig2, H, midx).tolist()[2] == 0
+    # (3) an infinite signature alone
+    sig3 = sig.copy(); sig3["inf"][0] = 1
+    assert ctx.verify_aggregate_common_batch(reg, kidx, koff, sig3, H, midx).tolist()[0] == 0
+    # (4) indices outside the registry / the message table
+    kidx4 = kidx.copy(); kidx4[koff[3]] = reg.size + 7
+    midx4 = midx.copy(); midx4[4] = H.size
+    got = ctx.verify_aggregate_common_batch(reg, kidx4, koff, sig, H, midx4).tolist()
+    assert got[3] == 0 and got[4] == 0 and got[:3] == expect[:3]
 
 
 def test_attestations_from_wire(ctx, orc):

@@ -8,10 +8,13 @@ from bls_b200 import hostgen as hg, layout as L
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ctx():
+# every test of this module runs once per schedule of the pairing arithmetic (b381_set_kernel_path): "auto" takes the
+# warp-cooperative VM for these batch sizes, the others force the one-pairing-per-thread kernels of the 2^16 benchmark
+# (k_miller_loop / k_final_exp / k_group_product), the two-lane kernels (k_duo_*) and the four-lane kernels (k_quad_*)
+@pytest.fixture(scope="module", params=["auto", "thread", "duo", "quad"])
+def ctx(request):
     from bls_b200 import capi
-    c = capi.Ctx(0)
+    c = capi.Ctx(0, path=request.param)
     yield c
     c.close()
 

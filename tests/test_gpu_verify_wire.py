@@ -16,10 +16,10 @@ from bls_b200 import hostgen as hg, layout as L
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["auto", "thread", "duo"])
+def ctx(request):
     from bls_b200 import capi
-    return capi.Ctx(0)
+    return capi.Ctx(0, path=request.param)
 
 
 def make_batch(ctx, n, seed):

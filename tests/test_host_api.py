@@ -174,3 +174,27 @@ def test_g1pubs_aggregate_with_domain(pubs):
     agg2 = g1pubs.AggregateSignatures([g1pubs.SignWithDomain(mi, k, dom) for mi, k in zip(ms, keys)])
     assert agg2.VerifyAggregateWithDomain(pubkeys, ms, dom)
     assert not agg2.VerifyAggregateWithDomain(pubkeys, ms[::-1], dom)
+
+
+@pytest.mark.gpu
+def test_infinite_key_and_signature_do_not_verify(pubs):
+    """Verify(m, Deserialize(infinity), Deserialize(infinity)) must be False for every message.  Both Miller
+    pairs would be skipped (a pair with a point at infinity is the factor 1 in the engine; the reference panics there,
+    pairing.go:17-26), and FE(1) == 1 would accept a zero-key forgery."""
+    g1pubs, g2pubs = pubs
+    inf48 = bytes([0xc0]) + bytes(47)
+    inf96 = bytes([0xc0]) + bytes(95)
+    pk1, sg1 = g1pubs.DeserializePublicKey(inf48), g1pubs.DeserializeSignature(inf96)
+    assert not g1pubs.Verify(b"any message", pk1, sg1)
+    assert not g1pubs.VerifyWithDomain(bytes(32), pk1, sg1, bytes(8))
+    assert not sg1.VerifyAggregate([pk1], [b"m"])
+    assert not sg1.VerifyAggregateCommon([pk1], b"m")
+    assert not sg1.VerifyAggregateWithDomain([pk1], [bytes(32)], bytes(8))
+    pk2, sg2 = g2pubs.DeserializePublicKey(inf96), g2pubs.DeserializeSignature(inf48)
+    assert not g2pubs.Verify(b"any message", pk2, sg2)
+    assert not sg2.VerifyAggregate([pk2], [b"m"])
+    # a valid key with an infinite signature, and the reverse
+    r = K.XorShiftReader(7)
+    priv = g1pubs.RandKey(r); pub = g1pubs.PrivToPub(priv); sig = g1pubs.Sign(b"m", priv)
+    assert g1pubs.Verify(b"m", pub, sig)
+    assert not g1pubs.Verify(b"m", pub, sg1) and not g1pubs.Verify(b"m", pk1, sig)

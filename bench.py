@@ -29,12 +29,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_PAIRINGS = 1 << 16
-# Fq multiplications per pairing (mul + sqr), counted by the instrumented host build of the device
-# code (tests/test_emu.py::test_op_counts pins them) and of the reference algorithm
-W_IMPL_MILLER = 6916
-W_IMPL_FINAL_EXP = 6411          # 7 770 with Granger-Scott squarings throughout; compressed squarings: 4 x (-342 + 69) + (-336 + 69)
-W_REF = 26546
-MACS_PER_FQ_MUL = 300            # 12x12 product + 12x12 reduction + 12 quotient words (32x32->64 each)
+# Wide multiply-accumulates (32x32->64, IMAD.WIDE.U32) the kernels execute per unit, counted by the instrumented host build of the
+# device code and pinned by tests/test_emu_logic.py::test_op_counts: an Fq product or squaring is 300 (12x12 product + 12x12
+# reduction + 12 quotient words), a two-product dot product with one reduction (the rows of an Fq2 product) 444.
+MACS_PER_FQ_MUL = 300
+MACS_IMPL_MILLER = 2052576       # k_miller_loop, one pair (= 6 841.9 Fq multiplications of 300; 1 360 products + 3 704 dot products)
+MACS_IMPL_FINAL_EXP = 1895976    # k_final_exp (= 6 319.9; 690 + 3 804), plus six integer inversions that use no multiplier
+MACS_IMPL_MILLER2 = 3444480      # k_miller_loop2, two pairs sharing the accumulator
+W_IMPL_MILLER = MACS_IMPL_MILLER / MACS_PER_FQ_MUL
+W_IMPL_FINAL_EXP = MACS_IMPL_FINAL_EXP / MACS_PER_FQ_MUL
+W_REF = 26546                    # Fq multiplications per bls.Pairing in the reference (oracle op count, tests/test_oracle_golden.py)
 METRIC = "BLS12-381 pairings/sec (batches of 2^16 independent pairings per GPU)"
 UNIT = "pairings/s"
 
@@ -96,22 +100,39 @@ def run_reference(args):
     emit(line)
 
 
+def pairing_source_hash():
+    """SHA-256 over the sources that determine the code of k_miller_loop / k_final_exp and over the nvcc flags: the stamp that
+    ties an ncu capture (profiles/traffic.json) to the library it was taken from"""
+    import hashlib
+    import __graft_entry__ as ge
+    h = hashlib.sha256(" ".join(ge.NVCC_FLAGS).encode())
+    for f in ("fp.cuh", "fp_mul_asm.inc", "constants.inc", "tower.cuh", "pairing.cuh"):
+        with open(os.path.join(ROOT, "bls_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def traffic_from_profiles(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full
-    summary (profiles/traffic.json, written by tools/ncu_summary.py --traffic); None if not captured"""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
+    (profiles/traffic.json, written by tools/refresh_profiles.py with the source stamp of the library it profiled).
+    Returns (bytes or None, provenance): None when nothing was captured or when the sources changed since the capture."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(kernel)
+            t = json.load(f)
     except (OSError, ValueError):
-        return None
+        return None, "no capture (profiles/traffic.json missing)"
+    if t.get("source_stamp") != pairing_source_hash():
+        return None, "capture %s is of other sources (stamp %s, library %s): not reported" % (t.get("source"), t.get("source_stamp"), pairing_source_hash())
+    return t.get(kernel), "%s, commit %s, source stamp %s" % (t.get("source"), t.get("commit"), t.get("source_stamp"))
 
 
-def aggregate_extras(ctx, stream, dev, rank, world, torch, np):
+def aggregate_extras(ctx, stream, dev, rank, world, torch, np, imad_peak):
     """aggregate-verification side of the metric (BASELINE.json configs 3-5), device-resident inputs, CUDA events:
     (a) one g1pubs VerifyAggregateCommon over 2^20 public keys (sum kernel + one 2-pair check),
     (b) a batch of 2^15 attestations x 128-key committees (Ethereum-beacon shape; 2^18 over 8 GPUs),
-    (c) a 2^20-point G1 MSM with 255-bit scalars; under torchrun also bucket-sharded over the ranks with one
-        all-gather of 144-byte partials (bls_b200/dist.py)."""
+    (c) G1 MSMs of 2^20 and 2^22 points (BASELINE config 4) with 255-bit scalars and per-phase device times; under torchrun
+        also bucket-sharded over the ranks with one all-gather of 144-byte partials (bls_b200/dist.py) and the speed-up over
+        the single-rank time of the same run."""
     import torch.distributed as dist
     from bls_b200 import hostgen as hg, layout as L, dist as bd
     out = {}
@@ -178,7 +199,13 @@ def aggregate_extras(ctx, stream, dev, rank, world, torch, np):
     ta = torch.tensor([t_att], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ta, op=dist.ReduceOp.MAX)
-    out["attestation_batch_2^15_x_128_keys"] = {"ms": float(ta.item()), "aggregate_verifies_per_s": world * natt / (float(ta.item()) * 1e-3)}
+    w_att = comm * 10 + 600 + (MACS_IMPL_MILLER2 + MACS_IMPL_FINAL_EXP) / MACS_PER_FQ_MUL   # key aggregation + normalisation + shared-accumulator Miller loop + final exp
+    out["attestation_batch_2^15_x_128_keys"] = {
+        "ms": float(ta.item()), "aggregate_verifies_per_s": world * natt / (float(ta.item()) * 1e-3),
+        "note": "BASELINE config 5 = 2^18 attestations over 8 GPUs = 2^15 per GPU; pre-hashed message points, resident key registry",
+        "roofline": {"kernels": "k_attest_pairs + k_miller_loop2 + k_final_exp_is_one", "fq_mul_per_attestation": w_att,
+                     "achieved": natt * w_att * MACS_PER_FQ_MUL / (t_att * 1e-3) / 1e12, "peak": imad_peak / 1e12,
+                     "unit": "T wide-MAC/s", "frac": natt * w_att * MACS_PER_FQ_MUL / (t_att * 1e-3) / imad_peak}}
     # (b') g1pubs.VerifyWithDomain from wire bytes: 2^16 (public key, message hash, signature) triples per GPU; deserialisation,
     # subgroup checks, HashG2WithDomain and the 2-pair check all on the device.  Inputs are made with the engine itself
     # (PrivToPub / SignWithDomain / Serialize batches, each parity-tested against the oracle); one triple in 64 is corrupted.
@@ -208,26 +235,55 @@ def aggregate_extras(ctx, stream, dev, rank, world, torch, np):
     out["verify_with_domain_wire_2^16"] = {"ms": float(tw.item()), "verifies_per_s": world * nw / (float(tw.item()) * 1e-3),
                                            "bytes_in_per_verify": 48 + 32 + 96}
     del dKw, dM, dPub, dPubC, dH, dSg, dSgC, dOkW
-    # (c) MSM 2^20, closed-form check on the tiled points: sum k_i P_(i mod m)
-    n_c = 1 << 20
+    # (c) BASELINE config 4: 2^22-point G1 MSM, 255-bit scalars (and the 2^20 size of config 3).  Closed-form check on the tiled
+    # points: sum_i k_(i mod 4096) sk_(i mod m).  Single GPU: all windows on this rank, with the device time of each phase.
+    # Under torchrun the bucket space is sharded over the ranks (rank g owns the windows w = g mod G), one all-gather of
+    # 144-byte partials + a fold on every rank; the speed-up is against the single-rank time measured in the same run.
     K, kvals = hg.splitmix_scalars(99, 1 << 12)
-    dKs = up(np.resize(K, (n_c, 4)))
-    dOut = torch.empty(144, dtype=torch.uint8, device=dev)
-    t_msm = timed(lambda: ctx.dev("b381_g1_msm_dev", dK.data_ptr(), dKs.data_ptr(), ctypes.c_size_t(n_c), dOut.data_ptr()))
-    ctx.call("b381_d2h", ctypes.c_void_p(hostPk.ctypes.data), ctypes.c_void_p(dOut.data_ptr()), ctypes.c_size_t(144))
-    S = sum(kvals[i % 4096] * (s0 + (i % m) * d0) for i in range(n_c)) % L.R_ORDER
-    agg["x"] = hostPk["x"]; agg["y"] = hostPk["y"]
-    assert agg.tobytes() == hg.g1_mul(S).tobytes(), "MSM result differs from the closed form"
-    out["g1_msm_2^20_255bit"] = {"ms": t_msm, "points_per_s": n_c / (t_msm * 1e-3)}
-    if world > 1:
-        dParts = torch.empty(world * 144, dtype=torch.uint8, device=dev)
-        t_sh = timed(lambda: bd.msm_bucket_sharded_dev(ctx, dK, dKs, n_c, dParts, dOut))
-        ts = torch.tensor([t_sh], dtype=torch.float64, device=dev)
-        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-        ctx.call("b381_d2h", ctypes.c_void_p(hostPk.ctypes.data), ctypes.c_void_p(dOut.data_ptr()), ctypes.c_size_t(144))
-        agg["x"] = hostPk["x"]; agg["y"] = hostPk["y"]
-        assert agg.tobytes() == hg.g1_mul(S).tobytes(), "bucket-sharded MSM differs from the closed form"
-        out["g1_msm_2^20_bucket_sharded"] = {"ms": float(ts.item()), "ranks": world, "exchange": "all_gather of %d x 144 B + fold" % world}
+    hostPk2 = np.zeros(1, dtype=L.G1_JAC)
+    PH = ("sort", "chunk_sums", "chunk_tree", "bucket_reduce", "combine")
+    for lg in (20, 22):
+        n_c = 1 << lg
+        dKp = dK if lg == 20 else up(np.resize(keys, n_c))
+        dKs = up(np.resize(K, (n_c, 4)))
+        dOut = torch.empty(144, dtype=torch.uint8, device=dev)
+        S = (n_c // m) * sum(kvals[i % 4096] * (s0 + i * d0) for i in range(m)) % L.R_ORDER
+        want = hg.g1_mul(S).tobytes()
+
+        def check(what):
+            ctx.call("b381_d2h", ctypes.c_void_p(hostPk2.ctypes.data), ctypes.c_void_p(dOut.data_ptr()), ctypes.c_size_t(144))
+            agg["x"] = hostPk2["x"]; agg["y"] = hostPk2["y"]
+            assert agg.tobytes() == want, what + " differs from the closed form"
+        t_msm = timed(lambda: ctx.dev("b381_g1_msm_dev", dKp.data_ptr(), dKs.data_ptr(), ctypes.c_size_t(n_c), dOut.data_ptr()))
+        check("MSM result")
+        ph = (ctypes.c_float * 5)()
+        ctx.dev("b381_g1_msm_shard_phases_dev", dKp.data_ptr(), dKs.data_ptr(), ctypes.c_size_t(n_c), 0, 1, dOut.data_ptr(), ph)
+        c_bits = max(4, min(16, lg - 5)); W = (255 + c_bits - 1) // c_bits
+        macs = n_c * W * 10 * MACS_PER_FQ_MUL          # XYZZ mixed addition: 8 M + 2 S per point and window
+        blk = {"n": n_c, "scalar_bits": 255, "window_bits": c_bits, "windows": W, "ms": t_msm, "points_per_s": n_c / (t_msm * 1e-3),
+               "phases_ms": {k: float(v) for k, v in zip(PH, ph)},
+               "roofline": {"kernel": "k_msm_chunk_sum", "bound": "int32-imad", "fq_mul_per_point": W * 10,
+                            "achieved": macs / (ph[1] * 1e-3) / 1e12, "peak": imad_peak / 1e12, "unit": "T wide-MAC/s",
+                            "frac": macs / (ph[1] * 1e-3) / imad_peak,
+                            "hbm_gbs_sanity": n_c * W * (4 + 104) / (ph[1] * 1e-3) / 1e9}}
+        if world > 1:
+            dParts = torch.empty(world * 144, dtype=torch.uint8, device=dev)
+            t_sh = timed(lambda: bd.msm_bucket_sharded_dev(ctx, dKp, dKs, n_c, dParts, dOut))
+            ts = torch.tensor([t_sh], dtype=torch.float64, device=dev)
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            check("bucket-sharded MSM")
+            ph2 = (ctypes.c_float * 5)()
+            ctx.dev("b381_g1_msm_shard_phases_dev", dKp.data_ptr(), dKs.data_ptr(), ctypes.c_size_t(n_c), rank, world, dOut.data_ptr(), ph2)
+            blk["bucket_sharded"] = {"ranks": world, "ms": float(ts.item()), "speedup_vs_one_gpu": t_msm / float(ts.item()),
+                                     "exchange": "one all_gather of %d x 144 B (NCCL) + fold on every rank" % world,
+                                     "phases_ms_this_rank": {k: float(v) for k, v in zip(PH, ph2)}}
+        out["g1_msm_2^%d_255bit" % lg] = blk
+        del dKs
+        if lg == 22:
+            del dKp
+    # BASELINE config 3 as one number: AggregateVerify of 2^20 signatures = 2^20-point MSM (random weights) + one 2-pair check
+    t3 = out["g1_msm_2^20_255bit"]["ms"] + t_chk
+    out["aggregate_verify_2^20_weighted"] = {"msm_ms": out["g1_msm_2^20_255bit"]["ms"], "pairing_check_ms": t_chk, "verifies_per_s": 1e3 / t3}
     return out
 
 
@@ -402,7 +458,7 @@ def run_engine(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / float(te.item())
 
-    extras = aggregate_extras(ctx, stream, dev, rank, world, torch, np) if not args.no_aggregate else None
+    extras = aggregate_extras(ctx, stream, dev, rank, world, torch, np, imad_peak) if not args.no_aggregate else None
     # ---- result check (sample vs the oracle) + CPU baseline on rank 0 ---------------------------
     if rank == 0:
         from oracle import pyoracle as orc
@@ -438,7 +494,7 @@ def run_engine(args):
                 "peak_source": "measured in this run on this GPU: max of k_fpmul_probe (dependent Fq-multiplication chain, "
                                "%.2f T/s) and k_imad_probe (independent mad.wide chains, %.2f T/s); MEASURED_PEAKS.json has no "
                                "integer peak" % (imad_peak_chain / 1e12, imad_peak_plain / 1e12),
-                "traffic": traffic_from_profiles(dom),
+                "traffic": traffic_from_profiles(dom)[0], "traffic_source": traffic_from_profiles(dom)[1],
                 "kernels_ms": kt,
                 "fq_mul_per_pairing": {"impl_miller": W_IMPL_MILLER, "impl_final_exp": W_IMPL_FINAL_EXP, "reference": W_REF},
                 "ref_equivalent_frac": (n * W_REF * MACS_PER_FQ_MUL / ((kt["k_miller_loop"] + kt["k_final_exp"]) * 1e-3)) / imad_peak,

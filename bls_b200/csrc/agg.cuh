@@ -21,6 +21,7 @@ namespace b381 {
 
 #define MSM_CHUNK 64u       // points per chunk partial sum
 #define MSM_SEG 16u         // buckets per running-sum segment
+#define MSM_INLINE_CHUNKS 4u // up to this many chunks per bucket (uniform scalars: 2-3) are added where the bucket sum is consumed
 
 // ---- block tree over shared memory: the sum of every thread's acc ends up in thread 0 -------------
 template <class F, int BLOCK> __device__ void block_reduce_xyzz(xyzz<F> &acc, xyzz<F> *sm) {
@@ -103,36 +104,53 @@ __global__ void k_msm_hist(const uint64_t *__restrict__ k, msm_geom g, uint32_t 
     }
 }
 
-// per window (one block): bucket_off = exclusive scan of count, chunk_off = exclusive scan of
-// ceil(count / MSM_CHUNK); both get a closing total at [nb].  maxch = largest chunk count of a bucket.
+// per window (one block): bucket_off = exclusive scan of count; the sorted index list of the window is cut into RUNS of
+// MSM_CHUNK consecutive positions (one per thread of k_msm_chunk_sum, whatever buckets they fall in), so bucket d owns
+// one chunk partial sum per run it touches: nch(d) = last run - first run + 1.  chunk_off = exclusive scan of nch; both get a
+// closing total at [nb].  maxch = largest chunk count of a bucket.
 __global__ void __launch_bounds__(1024) k_msm_scan(const uint32_t *__restrict__ count, msm_geom g, uint32_t *__restrict__ bucket_off,
                                                    uint32_t *__restrict__ chunk_off, uint32_t *__restrict__ maxch) {
-    __shared__ uint32_t sa[1024], sb[1024];
+    __shared__ uint32_t sa[1024];
     int j = blockIdx.x, t = threadIdx.x;
     const uint32_t *cnt = count + (size_t)j * g.nb;
     uint32_t *bo = bucket_off + (size_t)j * (g.nb + 1), *co = chunk_off + (size_t)j * (g.nb + 1);
     uint32_t per = (g.nb + 1023u) / 1024u;
     uint32_t lo = t * per, hi = lo + per < g.nb ? lo + per : g.nb;
+    if (lo > g.nb) lo = g.nb;
     uint32_t a = 0, b = 0, mx = 0;
-    for (uint32_t d = lo; d < hi; d++) {
-        uint32_t c = cnt[d], ch = (c + MSM_CHUNK - 1) / MSM_CHUNK;
-        a += c; b += ch; mx = ch > mx ? ch : mx;
-    }
-    sa[t] = a; sb[t] = b;
+    for (uint32_t d = lo; d < hi; d++) a += cnt[d];
+    sa[t] = a;
     __syncthreads();
     for (int s = 1; s < 1024; s <<= 1) {          // inclusive Hillis-Steele scan
-        uint32_t va = t >= s ? sa[t - s] : 0, vb = t >= s ? sb[t - s] : 0;
+        uint32_t va = t >= s ? sa[t - s] : 0;
         __syncthreads();
-        sa[t] += va; sb[t] += vb;
+        sa[t] += va;
         __syncthreads();
     }
-    uint32_t ea = sa[t] - a, eb = sb[t] - b;       // exclusive prefix of this thread's range
+    uint32_t ea = sa[t] - a, tot = sa[1023];
+    __syncthreads();
     for (uint32_t d = lo; d < hi; d++) {
         uint32_t c = cnt[d];
-        bo[d] = ea; co[d] = eb;
-        ea += c; eb += (c + MSM_CHUNK - 1) / MSM_CHUNK;
+        bo[d] = ea;
+        uint32_t ch = c ? ((ea + c - 1) / MSM_CHUNK - ea / MSM_CHUNK + 1) : 0;
+        b += ch; mx = ch > mx ? ch : mx;
+        ea += c;
     }
-    if (t == 1023) { bo[g.nb] = sa[t]; co[g.nb] = sb[t]; }
+    sa[t] = b;
+    __syncthreads();
+    for (int s = 1; s < 1024; s <<= 1) {
+        uint32_t vb = t >= s ? sa[t - s] : 0;
+        __syncthreads();
+        sa[t] += vb;
+        __syncthreads();
+    }
+    uint32_t eb = sa[t] - b;
+    for (uint32_t d = lo; d < hi; d++) {
+        uint32_t c = cnt[d], e0 = bo[d];
+        co[d] = eb;
+        eb += c ? ((e0 + c - 1) / MSM_CHUNK - e0 / MSM_CHUNK + 1) : 0;
+    }
+    if (t == 1023) { bo[g.nb] = tot; co[g.nb] = sa[t]; }
     if (mx) atomicMax(maxch, mx);
 }
 
@@ -150,45 +168,65 @@ __global__ void k_msm_scatter(const uint64_t *__restrict__ k, msm_geom g, const 
     }
 }
 
-// one thread per chunk: partial sum of <= MSM_CHUNK points of one bucket
+// one thread per RUN of MSM_CHUNK consecutive positions of the window's sorted index list: every lane of a warp performs the
+// same number of mixed additions whatever the bucket sizes are (with one thread per bucket-aligned chunk a third of the lanes
+// idled on the short tail chunks of buckets holding a little more than MSM_CHUNK points: ncu, profiles/r02_experiments.md).
+// At a bucket boundary the accumulator is flushed as that bucket's chunk number (run - first run of the bucket).
 template <class F, class APOD> __global__ void __launch_bounds__(128) k_msm_chunk_sum(const APOD *__restrict__ pts, const uint32_t *__restrict__ idx, msm_geom g,
                                                        const uint32_t *__restrict__ bucket_off, const uint32_t *__restrict__ chunk_off,
                                                        xyzz<F> *__restrict__ chunks, uint32_t *__restrict__ chunk_bucket) {
     int j = blockIdx.y;
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t *co = chunk_off + (size_t)j * (g.nb + 1), *bo = bucket_off + (size_t)j * (g.nb + 1);
-    if (q >= co[g.nb]) return;
-    uint32_t lo = 0, hi = g.nb;                    // largest b with co[b] <= q (and a non-empty bucket)
-    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (co[mid] <= q) lo = mid; else hi = mid; }
-    uint32_t b = lo, l = q - co[b];
-    uint32_t first = bo[b] + l * MSM_CHUNK, last = first + MSM_CHUNK < bo[b + 1] ? first + MSM_CHUNK : bo[b + 1];
+    const uint32_t total = bo[g.nb];
+    if ((uint64_t)q * MSM_CHUNK >= total) return;
+    const uint32_t first = q * MSM_CHUNK, last = first + MSM_CHUNK < total ? first + MSM_CHUNK : total;
+    const uint32_t *ix = idx + (size_t)j * g.n;
+    xyzz<F> *cbase = chunks + (size_t)j * g.maxchunks;
+    uint32_t *bbase = chunk_bucket + (size_t)j * g.maxchunks;
+    uint32_t b = 0, bend = 0;
     xyzz<F> acc;
-    msm_bucket_sum(acc, pts, idx + (size_t)j * g.n, first, last);
-    chunks[(size_t)j * g.maxchunks + q] = acc;
-    chunk_bucket[(size_t)j * g.maxchunks + q] = b;
+    xyzz_set_inf(acc);
+#pragma unroll 1
+    for (uint32_t pos = first; pos < last; pos++) {
+        if (pos == bend || pos == first) {
+            if (pos != first) { uint32_t ci = co[b] + (q - bo[b] / MSM_CHUNK); cbase[ci] = acc; bbase[ci] = b; xyzz_set_inf(acc); }
+            uint32_t lo = 0, hi = g.nb;            // the bucket of position pos: largest b with bo[b] <= pos (it is non-empty)
+            while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (bo[mid] <= pos) lo = mid; else hi = mid; }
+            b = lo; bend = bo[b + 1];
+        }
+        typename F::T x, y; bool inf;
+        load_affine(x, y, inf, pts + ix[pos]);
+        if (!inf) xyzz_madd(acc, x, y);
+    }
+    uint32_t ci = co[b] + (q - bo[b] / MSM_CHUNK);
+    cbase[ci] = acc; bbase[ci] = b;
 }
 
-// round r of the in-bucket tree: chunk l of a bucket absorbs chunk l + 2^r when l % 2^(r+1) == 0
+// round r of the in-bucket tree: chunk l of a bucket absorbs chunk l + 2^r when l % 2^(r+1) == 0.  Grid-stride over the chunks:
+// uniform scalars need two rounds, the launches of the remaining ones (a single bucket may hold every point) exit at once.
 template <class F> __global__ void __launch_bounds__(128) k_msm_chunk_tree(xyzz<F> *__restrict__ chunks, const uint32_t *__restrict__ chunk_bucket,
                                                         const uint32_t *__restrict__ chunk_off, msm_geom g, int r,
                                                         const uint32_t *__restrict__ maxch) {
-    if ((1u << r) >= *maxch) return;
+    if ((1u << r) >= *maxch || *maxch <= MSM_INLINE_CHUNKS) return;      // few chunks per bucket: k_msm_segment_reduce adds them itself
     int j = blockIdx.y;
-    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t *co = chunk_off + (size_t)j * (g.nb + 1);
-    if (q >= co[g.nb]) return;
-    uint32_t b = chunk_bucket[(size_t)j * g.maxchunks + q];
-    uint32_t l = q - co[b], nch = co[b + 1] - co[b];
-    if ((l & ((2u << r) - 1)) || l + (1u << r) >= nch) return;
+    const uint32_t nchunks = co[g.nb];
     xyzz<F> *base = chunks + (size_t)j * g.maxchunks;
-    xyzz<F> a = base[q];
-    xyzz_add(a, base[q + (1u << r)]);
-    base[q] = a;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nchunks; q += gridDim.x * blockDim.x) {
+        uint32_t b = chunk_bucket[(size_t)j * g.maxchunks + q];
+        uint32_t l = q - co[b], nch = co[b + 1] - co[b];
+        if ((l & ((2u << r) - 1)) || l + (1u << r) >= nch) continue;
+        xyzz<F> a = base[q];
+        xyzz_add(a, base[q + (1u << r)]);
+        base[q] = a;
+    }
 }
 
 // one thread per (window, segment of MSM_SEG buckets): sum_{d in segment} d * B[d]
 template <class F> __global__ void __launch_bounds__(128) k_msm_segment_reduce(const xyzz<F> *__restrict__ chunks, const uint32_t *__restrict__ chunk_off,
-                                                            msm_geom g, xyzz<F> *__restrict__ segsum) {
+                                                            msm_geom g, xyzz<F> *__restrict__ segsum, const uint32_t *__restrict__ maxch) {
+    const bool folded = *maxch > MSM_INLINE_CHUNKS;     // the chunk tree ran: chunk 0 of a bucket holds its sum
     int j = blockIdx.y;
     uint32_t nseg = g.nb / MSM_SEG;
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -200,7 +238,8 @@ template <class F> __global__ void __launch_bounds__(128) k_msm_segment_reduce(c
     xyzz<F> running, acc;
     xyzz_set_inf(running); xyzz_set_inf(acc);
     for (uint32_t d = hi; d-- > lo;) {
-        if (co[d + 1] > co[d]) { xyzz<F> bsum = base[co[d]]; xyzz_add(running, bsum); }
+        const uint32_t c0 = co[d], c1 = folded && co[d + 1] > c0 ? c0 + 1 : co[d + 1];
+        for (uint32_t q = c0; q < c1; q++) { xyzz<F> bsum = base[q]; xyzz_add(running, bsum); }
         xyzz_add(acc, running);
     }
     if (lo > 1 && !xyzz_is_inf(running)) { xyzz_mul_small(running, lo - 1); xyzz_add(acc, running); }

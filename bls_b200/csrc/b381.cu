@@ -348,7 +348,9 @@ static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n
 #define VM_MAX_UNITS 12288      // measured crossover on B200 (tools/small_bench.py): 8192 pairings 11.8 ms (VM) vs 24.1 ms; 16384: 23.2 vs 24.2
 static inline bool vm_for(const b381_ctx *ctx, size_t n) { return ctx->path < 0 ? n <= VM_MAX_UNITS : ctx->path == 1; }
 static inline bool quad_for(const b381_ctx *ctx, size_t n) { (void)n; return ctx->path == 2; }
-static inline bool duo_for(const b381_ctx *ctx, size_t n) { return ctx->path < 0 ? n > VM_MAX_UNITS : ctx->path == 3; }
+// (measured on B200, 2^16 pairings: thread 46.9 ms, duo 51.0 ms, quad 73.2 ms -- profiles/r02_experiments.md: large batches stay on the
+// one-pairing-per-thread kernels; the lane-cooperative schedules are selected explicitly)
+static inline bool duo_for(const b381_ctx *ctx, size_t n) { (void)n; return ctx->path == 3; }
 // persistent grid: the block-rounds of the batch spread evenly over the fewest rounds of sms x min_blocks resident blocks
 static inline unsigned lane_grid(const b381_ctx *ctx, size_t n, size_t per_block, size_t min_blocks) {
     size_t want = (n + per_block - 1) / per_block, cap = (size_t)ctx->sms * min_blocks;
@@ -1027,17 +1029,23 @@ static inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 }   // extern "C"
 // Pippenger over G1 (F = FpInl) or G2 (F = Fp2Out); nbits = scalar bits that can be non-zero (255 for field scalars, 64 for the
 // weights of the random-linear-combination check): only ceil(nbits / c) windows are formed
+// phase_ms (optional, host, 5 floats): sort (histogram + scan + scatter), chunk sums, chunk tree, bucket reduction (segments +
+// window sums), window combine -- CUDA events on the stream; asking for them synchronises the stream at the end
 template <class F, class APOD, class JPOD>
-static int msm_shard_dev(b381_ctx *ctx, const APOD *d_p, const b381_scalar *d_k, size_t n, int nbits, int rank, int nranks, JPOD *d_partial) {
+static int msm_shard_dev(b381_ctx *ctx, const APOD *d_p, const b381_scalar *d_k, size_t n, int nbits, int rank, int nranks, JPOD *d_partial,
+                         float *phase_ms = nullptr) {
     if (!ctx || !d_partial || (n && (!d_p || !d_k)) || nranks < 1 || rank < 0 || rank >= nranks || n > 0xFFFFFFF0u || nbits < 1 || nbits > 255)
         return B381_ERR_ARG;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (phase_ms) for (int i = 0; i < 6; i++) CK(cudaEventCreate(&ev[i]));
+#define MSM_MARK(i) do { if (phase_ms) CK(cudaEventRecord(ev[i], ctx->stream)); } while (0)
     bool whole = nranks == 1;
     msm_geom g;
     g.c = msm_window_bits(n);
     int W = (nbits + g.c - 1) / g.c;
     g.w0 = rank; g.wstep = nranks; g.nw = rank < W ? (W - rank + nranks - 1) / nranks : 0;
     g.nb = 1u << g.c; g.n = n;
-    g.maxchunks = (uint32_t)(n / MSM_CHUNK) + g.nb + 1;
+    g.maxchunks = (uint32_t)(n / MSM_CHUNK) + g.nb + 2;      // runs of the sorted list + one more chunk per bucket boundary
     uint32_t nseg = g.nb / MSM_SEG;
     int nw = g.nw > 0 ? g.nw : 1;
     // carve one scratch block
@@ -1052,34 +1060,53 @@ static int msm_shard_dev(b381_ctx *ctx, const APOD *d_p, const b381_scalar *d_k,
     uint32_t *maxch = (uint32_t *)(base + o_max), *idx = (uint32_t *)(base + o_idx), *cb = (uint32_t *)(base + o_cb);
     xyzz<F> *chunks = (xyzz<F> *)(base + o_chunks), *seg = (xyzz<F> *)(base + o_seg), *win = (xyzz<F> *)(base + o_win);
     if (g.nw > 0 && n > 0) {
+        MSM_MARK(0);
         CK(cudaMemsetAsync(base, 0, o_idx, ctx->stream));        // count, offsets, maxch
         unsigned pg = grid_for(n, 256);
         k_msm_hist<<<pg, 256, 0, ctx->stream>>>((const uint64_t *)d_k, g, count);
         k_msm_scan<<<g.nw, 1024, 0, ctx->stream>>>(count, g, boff, coff, maxch);
         k_msm_scatter<<<pg, 256, 0, ctx->stream>>>((const uint64_t *)d_k, g, boff, count, idx);
         dim3 cg(grid_for(g.maxchunks, 128), g.nw);
+        MSM_MARK(1);
         k_msm_chunk_sum<F><<<cg, 128, 0, ctx->stream>>>(d_p, idx, g, boff, coff, chunks, cb);
         ctx->launches += 4;
-        for (int r = 0; ((size_t)MSM_CHUNK << r) < n; r++) {
-            k_msm_chunk_tree<F><<<cg, 128, 0, ctx->stream>>>(chunks, cb, coff, g, r, maxch);
+        MSM_MARK(2);
+        dim3 tg((unsigned)ctx->sms * 8u < cg.x ? (unsigned)ctx->sms * 8u : cg.x, g.nw);
+        for (int r = 0; ((size_t)MSM_CHUNK << r) < n + MSM_CHUNK; r++) {
+            k_msm_chunk_tree<F><<<tg, 128, 0, ctx->stream>>>(chunks, cb, coff, g, r, maxch);
             ctx->launches++;
         }
         dim3 sg(grid_for(nseg, 128), g.nw);
-        k_msm_segment_reduce<F><<<sg, 128, 0, ctx->stream>>>(chunks, coff, g, seg);
+        MSM_MARK(3);
+        k_msm_segment_reduce<F><<<sg, 128, 0, ctx->stream>>>(chunks, coff, g, seg, maxch);
         k_msm_window_sum<F><<<g.nw, 128, 0, ctx->stream>>>(seg, nseg, win);
         ctx->launches += 2;
+        MSM_MARK(4);
     } else {
         g.nw = 0;
+        for (int i = 0; i < 5; i++) MSM_MARK(i);
     }
     k_msm_combine<F><<<1, 64, 0, ctx->stream>>>(win, g, whole ? 1 : 0, d_partial);
     ctx->launches++;
+    MSM_MARK(5);
     CK(cudaGetLastError());
+    if (phase_ms) {
+        CK(cudaEventSynchronize(ev[5]));
+        for (int i = 0; i < 5; i++) { CK(cudaEventElapsedTime(&phase_ms[i], ev[i], ev[i + 1])); }
+        for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
+    }
+#undef MSM_MARK
     return B381_OK;
 }
 extern "C" {
 int b381_g1_msm_shard_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_scalar *d_k, size_t n, int rank, int nranks,
                           b381_g1_jac *d_partial) {
     return msm_shard_dev<FpInl>(ctx, (const g1_affine_pod *)d_p, d_k, n, 255, rank, nranks, (g1_jac_pod *)d_partial);
+}
+int b381_g1_msm_shard_phases_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_scalar *d_k, size_t n, int rank, int nranks,
+                                 b381_g1_jac *d_partial, float *phase_ms) {
+    if (!phase_ms) return B381_ERR_ARG;
+    return msm_shard_dev<FpInl>(ctx, (const g1_affine_pod *)d_p, d_k, n, 255, rank, nranks, (g1_jac_pod *)d_partial, phase_ms);
 }
 int b381_g1_msm_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_scalar *d_k, size_t n, b381_g1_jac *d_out) {
     return b381_g1_msm_shard_dev(ctx, d_p, d_k, n, 0, 1, d_out);

@@ -63,6 +63,15 @@ HD bool fp_eq(const fp &a, const fp &b) {
 // ---------------------------------------------------------------------------------------------
 #if !defined(__CUDA_ARCH__)
 namespace hostimpl {
+// Fq multiplications executed by the host build (tests/emu pins the per-pairing counts bench.py's roofline uses)
+#if defined(B381_HOST_COUNT)
+static thread_local unsigned long long g_mul_count = 0, g_dot2_count = 0;
+#define B381_COUNT_MUL(k) (hostimpl::g_mul_count += (k))
+#define B381_COUNT_DOT2(k) (hostimpl::g_dot2_count += (k))
+#else
+#define B381_COUNT_MUL(k) ((void)0)
+#define B381_COUNT_DOT2(k) ((void)0)
+#endif
 static inline void cond_sub_q(uint32_t x[12], uint32_t top) {
     const uint32_t q[12] = {B381_Q_LIMBS};
     uint32_t d[12];
@@ -76,6 +85,7 @@ static inline void cond_sub_q(uint32_t x[12], uint32_t top) {
         for (int i = 0; i < 12; i++) x[i] = d[i];
 }
 static inline void mul(uint32_t r[12], const uint32_t a[12], const uint32_t b[12]) {
+    B381_COUNT_MUL(1);
     const uint32_t q[12] = {B381_Q_LIMBS};
     uint32_t t[14] = {0};
     for (int i = 0; i < 12; i++) {
@@ -297,6 +307,7 @@ HDN fp fp_dot2_v(fp a, fp b, fp c, fp d) {
     fp_dot2_inl(r, a, b, c, d);
 #else
     uint32_t t[12], u[12];
+    B381_COUNT_DOT2(1);                                // (the device runs ONE 444-MAC body; the two host products below are counted too)
     hostimpl::mul(t, a.l, b.l);
     hostimpl::mul(u, c.l, d.l);
     fp x, y;

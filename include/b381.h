@@ -64,10 +64,10 @@ int b381_set_stream(b381_ctx *ctx, void *cuda_stream);
 int b381_use_own_stream(b381_ctx *ctx);
 int b381_sync(b381_ctx *ctx);
 /* Which of the three schedules of the SAME arithmetic (bit-identical results) the pairing entry points launch:
- * AUTO picks by batch size (small batches: the warp-cooperative VM, low latency; large batches: two lanes per pairing,
- * k_duo_*, half the tower state per lane); THREAD is one pairing per thread (k_miller_loop / k_final_exp, the round-1
- * throughput path) and QUAD four lanes per pairing (k_quad_*): both kept for A/B measurements and as further
- * implementations the parity tests run.  The reference has one
+ * AUTO picks by batch size (small batches: the warp-cooperative VM, low latency; large batches: one pairing per thread,
+ * k_miller_loop / k_final_exp, the fastest at 2^16 on B200).  DUO (two lanes per pairing, k_duo_*: half the tower state per
+ * lane, a third of the DRAM traffic, 9 % slower) and QUAD (four lanes, k_quad_*) are complete alternative schedules kept
+ * for A/B measurements and as further implementations the parity tests run (profiles/r02_experiments.md).  The reference has one
  * schedule (pairing.go:16-129); this call has no reference counterpart.  Env B381_PATH=auto|thread|vm|quad|duo sets the
  * initial value. */
 enum { B381_PATH_AUTO = -1, B381_PATH_THREAD = 0, B381_PATH_VM = 1, B381_PATH_QUAD = 2, B381_PATH_DUO = 3 };
@@ -134,6 +134,11 @@ int b381_g2_msm_dev(b381_ctx *ctx, const b381_g2_affine *d_p, const b381_scalar 
  * *d_partial.  The caller all-gathers the nranks partials and folds them with b381_g1_fold_dev.  */
 int b381_g1_msm_shard_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_scalar *d_k, size_t n,
                           int rank, int nranks, b381_g1_jac *d_partial);
+/* The same call with the device time of its phases (measurement; synchronises the stream): phase_ms[0..4] = sort of the point
+ * indices by bucket (histogram, scan, scatter), chunk partial sums, in-bucket chunk tree, bucket reduction (running-sum
+ * segments + window sums), window combine.  phase_ms is HOST memory, 5 floats. */
+int b381_g1_msm_shard_phases_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_scalar *d_k, size_t n,
+                                 int rank, int nranks, b381_g1_jac *d_partial, float *phase_ms);
 /* out = normalised sum of n Jacobian points (G1Projective.Add fold, g1.go:400-482) */
 int b381_g1_fold_dev(b381_ctx *ctx, const b381_g1_jac *d_parts, size_t n, b381_g1_jac *d_out);
 

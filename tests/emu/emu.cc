@@ -2,6 +2,7 @@
 // C++ with the portable limb bodies).  It lets the CPU test suite exercise the exact tower /
 // pairing / group-law logic the kernels run, against the oracle, without a GPU.  The product
 // library (libb381.so) never contains or calls this path.
+#define B381_HOST_COUNT 1
 #include "pairing.cuh"
 #include "curve.cuh"
 #include <cstring>
@@ -69,3 +70,17 @@ extern "C" void emu_miller_loop2(const g1_affine_pod *p, const g2_affine_pod *q,
 }
 #include "emu_quad.inc"
 #include "emu_duo.inc"
+
+// Fq multiplications (hostimpl::mul calls: products and squarings, one each; a two-product dot product counts two)
+// executed on this thread since the last reset
+extern "C" unsigned long long emu_mul_count(int reset) {
+    unsigned long long v = hostimpl::g_mul_count;
+    if (reset) hostimpl::g_mul_count = 0;
+    return v;
+}
+// two-product dot products (fp_dot2_v: one 444-MAC body on the device) among them; each also added 2 to emu_mul_count
+extern "C" unsigned long long emu_dot2_count(int reset) {
+    unsigned long long v = hostimpl::g_dot2_count;
+    if (reset) hostimpl::g_dot2_count = 0;
+    return v;
+}

@@ -152,3 +152,28 @@ def test_msm_building_blocks(emu, orc, rank, nranks):
         tot = np.zeros(1, dtype=L.G1_JAC)
         emu.emu_g1_fold(_p(np.concatenate([out, other])), ctypes.c_size_t(2), _p(tot))
         assert orc.g1.to_affine(tot).tobytes() == orc.g1.to_affine(orc.g1_msm_naive(P, K, threads=4)).tobytes()
+
+
+def test_op_counts(emu):
+    """The multiplier work bench.py's roofline numerator uses, pinned by the instrumented host build of the device code: Fq
+    products (300 wide MACs: 144 product + 144 reduction + 12 quotient words) and two-product dot products with one reduction
+    (444 wide MACs) executed per pairing by the one-pairing-per-thread kernels.  The two-lane form executes the same
+    operations (the host emulation runs two copies of the lane pair); the four-lane form trades a few more for balance."""
+    import bench
+    emu.emu_mul_count.restype = ctypes.c_ulonglong; emu.emu_dot2_count.restype = ctypes.c_ulonglong
+    P = hg.g1_progression(3, 1, 1); Q = hg.g2_progression(4, 1, 1)
+    ml = np.zeros(1, dtype=L.FP12); fe = np.zeros(1, dtype=L.FP12); ok = np.zeros(1, np.uint8)
+
+    def macs():
+        m = emu.emu_mul_count(1); d = emu.emu_dot2_count(1)
+        return 300 * (m - 2 * d) + 444 * d
+    macs()
+    emu.emu_miller_loop(_p(P), _p(Q), ctypes.c_size_t(1), _p(ml)); a = macs()
+    emu.emu_final_exp(_p(ml), ctypes.c_size_t(1), _p(fe), _p(ok)); b = macs()
+    assert (a, b) == (bench.MACS_IMPL_MILLER, bench.MACS_IMPL_FINAL_EXP) == (2052576, 1895976)
+    emu.emu_duo_miller_loop(_p(P), _p(Q), ctypes.c_size_t(1), _p(ml)); a2 = macs()
+    emu.emu_duo_final_exp(_p(ml), ctypes.c_size_t(1), _p(fe), _p(ok)); b2 = macs()
+    assert a2 == 2 * a and b2 == 2 * 1899576       # + 12 products: both lanes of a pair run the six norm inversions
+    P2 = hg.g1_progression(3, 1, 2); Q2 = hg.g2_progression(4, 1, 2)
+    emu.emu_miller_loop2(_p(P2), _p(Q2), ctypes.c_size_t(1), _p(ml)); c = macs()
+    assert c == bench.MACS_IMPL_MILLER2

@@ -1,0 +1,31 @@
+#!/usr/bin/env python3
+"""One bucket-sharded G1 MSM call per (rank, nranks) given on the command line, on tiled points and splitmix scalars
+(timing only): python tools/msm_phases.py LOG2N rank:nranks ...   Run under `ncu --metrics gpu__time_duration.sum` for the
+per-kernel times of each call, or plain for CUDA-event totals."""
+import ctypes, os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from bls_b200 import capi, hostgen as hg, layout as L
+lg = int(sys.argv[1]); n = 1 << lg
+ctx = capi.Ctx(0); st = torch.cuda.current_stream(); ctx.set_stream(st.cuda_stream)
+dev = torch.device("cuda", 0)
+m = 1 << 12
+P = np.resize(hg.g1_progression(3, 5, m), n)
+rng = np.random.RandomState(7)
+K = rng.randint(0, 1 << 63, size=(n, 4), dtype=np.int64).astype(np.uint64)
+K[:, 3] &= np.uint64((1 << 62) - 1)                      # < 2^254 < r: canonical
+up = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).to(dev)
+dP, dK = up(P), up(K)
+dO = torch.empty(144, dtype=torch.uint8, device=dev)
+res = {}
+for spec in sys.argv[2:]:
+    r, nr = map(int, spec.split(":"))
+    best = None
+    for rep in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        ctx.dev("b381_g1_msm_shard_dev", dP.data_ptr(), dK.data_ptr(), ctypes.c_size_t(n), ctypes.c_int(r), ctypes.c_int(nr), dO.data_ptr())
+        e1.record(st); torch.cuda.synchronize()
+        t = e0.elapsed_time(e1); best = t if best is None else min(best, t)
+    res[spec] = best
+print(json.dumps({"log2n": lg, "ms": res}))

@@ -138,6 +138,21 @@ class Ctx:
         self.call("b381_final_exp_batch", _hp(f), ctypes.c_size_t(f.shape[0]), _hp(out), _hp(ok))
         return out, ok
 
+    def g2_prepare_batch(self, q):
+        """n x G2AffineToPrepared (g2.go:650-801) -- b381_g2_prepare_batch"""
+        q = np.ascontiguousarray(q, dtype=L.G2_AFFINE)
+        out = np.zeros(q.size, dtype=L.G2_PREPARED)
+        self.call("b381_g2_prepare_batch", _hp(q), ctypes.c_size_t(q.size), _hp(out))
+        return out
+
+    def miller_loop_prepared_batch(self, p, prep, prep_idx=None):
+        """MillerLoop of one item per pair with a prepared Q (pairing.go:4-7,16-75) -- b381_miller_loop_prepared_batch"""
+        p = np.ascontiguousarray(p, dtype=L.G1_AFFINE); prep = np.ascontiguousarray(prep, dtype=L.G2_PREPARED)
+        idx = None if prep_idx is None else np.ascontiguousarray(prep_idx, dtype=np.uint32)
+        out = np.empty(p.size, dtype=L.FP12)
+        self.call("b381_miller_loop_prepared_batch", _hp(p), _hp(prep), ctypes.c_size_t(prep.size), _hp(idx), ctypes.c_size_t(p.size), _hp(out))
+        return out
+
     def pairing_product_is_one(self, p, q, group_off):
         p = np.ascontiguousarray(p, dtype=L.G1_AFFINE); q = np.ascontiguousarray(q, dtype=L.G2_AFFINE)
         off = np.ascontiguousarray(group_off, dtype=np.uint32)

@@ -26,6 +26,7 @@ using namespace b381;
 static_assert(sizeof(b381_g1_affine) == sizeof(g1_affine_pod) && sizeof(b381_g1_affine) == 104, "layout");
 static_assert(sizeof(b381_g2_affine) == sizeof(g2_affine_pod) && sizeof(b381_g2_affine) == 200, "layout");
 static_assert(sizeof(b381_fp12) == 576 && sizeof(fp12) == 576, "layout");
+static_assert(sizeof(b381_g2_prepared) == sizeof(g2_prepared_pod) && sizeof(b381_g2_prepared) == 68 * 288 + 8, "layout");
 static_assert(sizeof(b381_g1_jac) == 144 && sizeof(b381_g2_jac) == 288, "layout");
 
 // ---------------------------------------------------------------------------------------------
@@ -59,6 +60,37 @@ __global__ void __launch_bounds__(PAIRING_BLOCK, PAIRING_MIN_BLOCKS) k_miller_lo
     if (g >= ngroups) return;
     fp12 f;
     miller_loop_two(&f, p + 2 * g, q + 2 * g);
+    fp12_store_u64(out + 72 * g, &f);
+}
+
+// prep[i] = G2AffineToPrepared(q[i])   (g2.go:650-801)
+__global__ void __launch_bounds__(PAIRING_BLOCK, PAIRING_MIN_BLOCKS) k_g2_prepare(const g2_affine_pod *__restrict__ q, size_t n,
+                                                                                  g2_prepared_pod *__restrict__ prep) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    g2_prepare_one(prep + i, q + i);
+}
+// out[i] = MillerLoop({p[i], prep[idx ? idx[i] : i]})   (pairing.go:16-75 on a MillerLoopItem whose Q was prepared before)
+__global__ void __launch_bounds__(PAIRING_BLOCK, PAIRING_MIN_BLOCKS) k_miller_loop_prepared(const g1_affine_pod *__restrict__ p,
+                                                                                            const g2_prepared_pod *__restrict__ prep,
+                                                                                            const uint32_t *__restrict__ idx, size_t n,
+                                                                                            uint64_t *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fp12 f;
+    miller_loop_prepared_one(&f, p + i, prep + (idx ? idx[i] : i));
+    fp12_store_u64(out + 72 * i, &f);
+}
+// prod[g] = MillerLoop of (p[2g], q[2g]) computed and (p[2g+1], prep[idx[g]]) read from its prepared coefficients, shared accumulator
+__global__ void __launch_bounds__(PAIRING_BLOCK, PAIRING_MIN_BLOCKS) k_miller_loop_fused_prepared(const g1_affine_pod *__restrict__ p,
+                                                                                                  const g2_affine_pod *__restrict__ q,
+                                                                                                  const g2_prepared_pod *__restrict__ prep,
+                                                                                                  const uint32_t *__restrict__ idx, size_t ngroups,
+                                                                                                  uint64_t *__restrict__ out) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    fp12 f;
+    miller_loop_fused_prepared(&f, p + 2 * g, q + 2 * g, prep + idx[g]);
     fp12_store_u64(out + 72 * g, &f);
 }
 
@@ -130,6 +162,9 @@ __global__ void __launch_bounds__(PAIRING_BLOCK, PAIRING_MIN_BLOCKS) k_final_exp
     bool good = final_exp_one(&f, &f);
     ok[i] = (good && fp12_is_one(&f)) ? 1 : 0;
 }
+
+// group offsets of ONE group of n values, written on the device (no host staging, nothing to wait for)
+__global__ void k_one_group(uint32_t *off, uint32_t n) { off[0] = 0; off[1] = n; }
 
 // ok[i] &= (fe[i] == 1)   (the Equals(FQ12One) of pairing.go:146 after a separate final-exponentiation pass)
 __global__ void k_fp12_is_one(const uint64_t *__restrict__ fe, size_t n, uint8_t *__restrict__ ok) {
@@ -309,6 +344,7 @@ struct b381_ctx {
     struct { uint4 *code, *consts; int lanes, nsteps, nslots, spill_fq; } vm[3];
     int path;                // -1 by batch size, 0 one pairing per thread, 1 warp-cooperative VM, 2 four lanes per pairing
     int vm_split;
+    int prepared_attest;     // attestation batches prepare repeated message points (B381_PREPARED=0 disables: A/B measurements)
 };
 enum { VM_ML1 = 0, VM_FE_A = 1, VM_FE_C = 2 };
 
@@ -329,7 +365,7 @@ enum { VM_ML1 = 0, VM_FE_A = 1, VM_FE_C = 2 };
 //   15-18  wire-level verify: decoded keys, decoded signatures, message points, status + validity bytes
 //   19, 20  wire-level verify host staging (inputs, verdicts)                       21  largest group size (tree product)
 //   22  group offsets of the random-linear-combination check                        23  its G2 sum + "any invalid" flag
-//   24  validity bytes of an attestation batch                                      25-27  prepared G2 line coefficients / staging
+//   24  validity bytes of an attestation batch        25, 26  group offsets / verdicts of b381_pairing_product_is_one        27-31  prepared G2 points
 static int scratch_get(b381_ctx *ctx, int slot, size_t bytes, void **out) {
     if (ctx->scratch_bytes[slot] < bytes) {
         if (ctx->scratch[slot]) {
@@ -345,12 +381,25 @@ static int scratch_get(b381_ctx *ctx, int slot, size_t bytes, void **out) {
 }
 
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
-#define VM_MAX_UNITS 12288      // measured crossover on B200 (tools/small_bench.py): 8192 pairings 11.8 ms (VM) vs 24.1 ms; 16384: 23.2 vs 24.2
-static inline bool vm_for(const b381_ctx *ctx, size_t n) { return ctx->path < 0 ? n <= VM_MAX_UNITS : ctx->path == 1; }
-static inline bool quad_for(const b381_ctx *ctx, size_t n) { (void)n; return ctx->path == 2; }
-// (measured on B200, 2^16 pairings: thread 46.9 ms, duo 51.0 ms, quad 73.2 ms -- profiles/r02_experiments.md: large batches stay on the
-// one-pairing-per-thread kernels; the lane-cooperative schedules are selected explicitly)
-static inline bool duo_for(const b381_ctx *ctx, size_t n) { (void)n; return ctx->path == 3; }
+// Which schedule runs a batch of n units when the caller did not force one (measured on B200, tools/path_sweep.py,
+// profiles/r02_path_sweep.json: ms per b381_pairing_batch_dev call)
+//      n      VM    thread    duo    quad
+//     64     7.3    18.6    10.2     7.3        few units: only latency counts -- four lanes per pairing (and the VM's
+//   4096     9.4    18.7    10.3     7.7        eight-lane split form up to 592 units) finish first
+//   8192    11.3    18.7    10.4    10.2
+//  16384    22.7    20.2    13.8    17.8        half a wave of threads: two lanes per pairing fill the SMs
+//  32768    45.3    27.2    25.1    36.1
+//  49152      -     37.2    39.8    54.5        a full wave of threads: one pairing per thread executes the fewest instructions
+//  65536      -     46.6    50.8    72.8
+#define QUAD_MAX_UNITS 10240
+#define DUO_MAX_UNITS 40960
+static inline int path_for(const b381_ctx *ctx, size_t n) {
+    if (ctx->path >= 0) return ctx->path;
+    return n <= QUAD_MAX_UNITS ? B381_PATH_QUAD : n <= DUO_MAX_UNITS ? B381_PATH_DUO : B381_PATH_THREAD;
+}
+static inline bool vm_for(const b381_ctx *ctx, size_t n) { return path_for(ctx, n) == B381_PATH_VM; }
+static inline bool quad_for(const b381_ctx *ctx, size_t n) { return path_for(ctx, n) == B381_PATH_QUAD; }
+static inline bool duo_for(const b381_ctx *ctx, size_t n) { return path_for(ctx, n) == B381_PATH_DUO; }
 // persistent grid: the block-rounds of the batch spread evenly over the fewest rounds of sms x min_blocks resident blocks
 static inline unsigned lane_grid(const b381_ctx *ctx, size_t n, size_t per_block, size_t min_blocks) {
     size_t want = (n + per_block - 1) / per_block, cap = (size_t)ctx->sms * min_blocks;
@@ -397,10 +446,14 @@ int b381_init(int device, b381_ctx **out) {
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B381_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
     // the tower state of a pairing lives in local memory: prefer L1 over shared memory
-    cudaFuncSetAttribute(k_miller_loop, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(k_final_exp, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(k_final_exp_is_one, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(k_group_product, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    if (cudaFuncSetAttribute(k_miller_loop, cudaFuncAttributePreferredSharedMemoryCarveout, 0) != cudaSuccess ||
+        cudaFuncSetAttribute(k_miller_loop2, cudaFuncAttributePreferredSharedMemoryCarveout, 0) != cudaSuccess ||
+        cudaFuncSetAttribute(k_final_exp, cudaFuncAttributePreferredSharedMemoryCarveout, 0) != cudaSuccess ||
+        cudaFuncSetAttribute(k_final_exp_is_one, cudaFuncAttributePreferredSharedMemoryCarveout, 0) != cudaSuccess ||
+        cudaFuncSetAttribute(k_group_product, cudaFuncAttributePreferredSharedMemoryCarveout, 0) != cudaSuccess) {
+        b381_free(ctx);
+        return B381_ERR_CUDA;
+    }
     // upload the VM programs and opt in to the shared memory they need
     static_assert(sizeof(vm_program_images) / sizeof(vm_program_images[0]) == 3, "ml1, fe_a, fe_c");
     size_t max_smem = 0;
@@ -421,6 +474,8 @@ int b381_init(int device, b381_ctx **out) {
     // throughput once ~65 k threads are resident).  Default: by batch size; B381_VM=0/1 forces one of them for A/B measurements.
     const char *ev = getenv("B381_VM");
     ctx->path = ev ? (ev[0] == '0' ? 0 : 1) : -1;
+    const char *epr = getenv("B381_PREPARED");
+    ctx->prepared_attest = epr ? (epr[0] != '0') : 1;
     const char *ep = getenv("B381_PATH");          // thread | vm | quad | auto (same as b381_set_kernel_path)
     if (ep) ctx->path = ep[0] == 't' ? 0 : ep[0] == 'v' ? 1 : ep[0] == 'q' ? 2 : ep[0] == 'd' ? 3 : -1;
     const char *es = getenv("B381_VM_SPLIT");       // 0 disables the two-lanes-per-operation latency form (A/B measurements)
@@ -443,11 +498,15 @@ const char *b381_last_error(const b381_ctx *ctx) { return ctx ? ctx->err : "null
 
 int b381_set_stream(b381_ctx *ctx, void *cuda_stream) {
     if (!ctx) return B381_ERR_ARG;
+    // work queued on the stream being left may still use the grow-only scratch (scratch_get frees after synchronising the
+    // CURRENT stream only): drain it before switching
+    if ((cudaStream_t)cuda_stream != ctx->stream) CK(cudaStreamSynchronize(ctx->stream));
     ctx->stream = (cudaStream_t)cuda_stream;   // NULL is the legacy default stream, as everywhere in CUDA
     return B381_OK;
 }
 int b381_use_own_stream(b381_ctx *ctx) {
     if (!ctx) return B381_ERR_ARG;
+    if (ctx->stream != ctx->own_stream) CK(cudaStreamSynchronize(ctx->stream));
     ctx->stream = ctx->own_stream;
     return B381_OK;
 }
@@ -511,9 +570,13 @@ int b381_vm_exec_dev(b381_ctx *ctx, const void *code, int lanes, int nsteps, int
     uint4 *dcode = nullptr, *dconst = nullptr;
     size_t cb = (size_t)nsteps * lanes * 64, kb = (size_t)(nconsts > 0 ? nconsts : 1) * 96;
     CK(cudaMalloc(&dcode, cb));
-    CK(cudaMalloc(&dconst, kb));
-    CK(cudaMemcpy(dcode, code, cb, cudaMemcpyHostToDevice));
-    if (nconsts > 0) CK(cudaMemcpy(dconst, consts, kb, cudaMemcpyHostToDevice));
+    if (cudaMalloc(&dconst, kb) != cudaSuccess) { cudaFree(dcode); return B381_ERR_NOMEM; }
+    if (cudaMemcpy(dcode, code, cb, cudaMemcpyHostToDevice) != cudaSuccess ||
+        (nconsts > 0 && cudaMemcpy(dconst, consts, kb, cudaMemcpyHostToDevice) != cudaSuccess)) {
+        cudaFree(dcode); cudaFree(dconst);
+        snprintf(ctx->err, sizeof ctx->err, "vm_exec: upload failed");
+        return B381_ERR_CUDA;
+    }
     vm2_args A;
     for (int i = 0; i < 4; i++) { A.seg[i].base = (unsigned char *)d_seg[i]; A.seg[i].stride = stride[i]; }
     A.seg[4].base = (unsigned char *)dconst; A.seg[4].stride = 0;
@@ -521,7 +584,10 @@ int b381_vm_exec_dev(b381_ctx *ctx, const void *code, int lanes, int nsteps, int
     A.flag_a = A.flag_b = nullptr; A.flag_stride_a = A.flag_stride_b = 0; A.ok = nullptr;
     size_t sm = vm_smem_bytes(lanes, nslots);
     if (sm > 200 * 1024) { cudaFree(dcode); cudaFree(dconst); return B381_ERR_ARG; }
-    CK(cudaFuncSetAttribute(k_vm2<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (cudaFuncSetAttribute(k_vm2<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+        cudaFree(dcode); cudaFree(dconst);
+        return B381_ERR_CUDA;
+    }
     k_vm2<4, 1><<<grid_for(n, VM2_WARPS * (32 / lanes)), VM2_WARPS * 32, sm, ctx->stream>>>(A);
     ctx->launches++;
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -791,6 +857,60 @@ int b381_pairing_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_
     if (rc) return rc;
     return b381_final_exp_batch_dev(ctx, d_out, n, d_out, nullptr);
 }
+// ---- prepared G2 points: G2AffineToPrepared once, MillerLoop from the coefficients (g2.go:639-801, pairing.go:4-75) ---------------
+int b381_g2_prepare_batch_dev(b381_ctx *ctx, const b381_g2_affine *d_q, size_t n, b381_g2_prepared *d_prep) {
+    if (!ctx || (n && (!d_q || !d_prep))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    k_g2_prepare<<<grid_for(n, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>((const g2_affine_pod *)d_q, n, (g2_prepared_pod *)d_prep);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+int b381_miller_loop_prepared_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_prepared *d_prep, const uint32_t *d_prep_idx,
+                                        size_t n, b381_fp12 *d_out) {
+    if (!ctx || (n && (!d_p || !d_prep || !d_out))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    k_miller_loop_prepared<<<grid_for(n, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>((const g1_affine_pod *)d_p, (const g2_prepared_pod *)d_prep,
+                                                                                        d_prep_idx, n, (uint64_t *)d_out);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+int b381_g2_prepare_batch(b381_ctx *ctx, const b381_g2_affine *q, size_t n, b381_g2_prepared *prep) {
+    if (!ctx || (n && (!q || !prep))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    CK(cudaSetDevice(ctx->device));
+    void *dq, *dp;
+    int rc = scratch_get(ctx, 3, n * sizeof(b381_g2_affine), &dq); if (rc) return rc;
+    rc = scratch_get(ctx, 27, n * sizeof(b381_g2_prepared), &dp); if (rc) return rc;
+    CK(cudaMemcpyAsync(dq, q, n * sizeof(b381_g2_affine), cudaMemcpyHostToDevice, ctx->stream));
+    rc = b381_g2_prepare_batch_dev(ctx, (const b381_g2_affine *)dq, n, (b381_g2_prepared *)dp); if (rc) return rc;
+    CK(cudaMemcpyAsync(prep, dp, n * sizeof(b381_g2_prepared), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B381_OK;
+}
+// out[i] = MillerLoop({p[i], prep[prep_idx ? prep_idx[i] : i]}); nprep = number of prepared points behind `prep`
+int b381_miller_loop_prepared_batch(b381_ctx *ctx, const b381_g1_affine *p, const b381_g2_prepared *prep, size_t nprep, const uint32_t *prep_idx,
+                                    size_t n, b381_fp12 *out) {
+    if (!ctx || (n && (!p || !prep || !out || !nprep)) || (!prep_idx && nprep < n)) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    if (prep_idx) for (size_t i = 0; i < n; i++) if (prep_idx[i] >= nprep) return B381_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    void *dp, *dprep, *didx = nullptr, *dout;
+    int rc = scratch_get(ctx, 2, n * sizeof(b381_g1_affine), &dp); if (rc) return rc;
+    rc = scratch_get(ctx, 27, nprep * sizeof(b381_g2_prepared), &dprep); if (rc) return rc;
+    rc = scratch_get(ctx, 0, n * sizeof(b381_fp12), &dout); if (rc) return rc;
+    if (prep_idx) { rc = scratch_get(ctx, 28, n * sizeof(uint32_t), &didx); if (rc) return rc; }
+    CK(cudaMemcpyAsync(dp, p, n * sizeof(b381_g1_affine), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dprep, prep, nprep * sizeof(b381_g2_prepared), cudaMemcpyHostToDevice, ctx->stream));
+    if (prep_idx) CK(cudaMemcpyAsync(didx, prep_idx, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    rc = b381_miller_loop_prepared_batch_dev(ctx, (const b381_g1_affine *)dp, (const b381_g2_prepared *)dprep, (const uint32_t *)didx, n, (b381_fp12 *)dout);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, dout, n * sizeof(b381_fp12), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B381_OK;
+}
+
 // prod[g] = product of the Fq12 values ml[group_off[g] .. group_off[g+1]) (ml is overwritten when groups are folded as trees)
 static int group_products(b381_ctx *ctx, void *ml, size_t nvals, const uint32_t *d_group_off, size_t ngroups, void *prod) {
     int tree = nvals > 2 * ngroups;               // some group has more than two factors: fold groups as trees
@@ -854,7 +974,10 @@ int b381_pairing_product_is_one_dev(b381_ctx *ctx, const b381_g1_affine *d_p, co
 static int pairs2_product_is_one(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_affine *d_q, size_t ngroups,
                                  const uint32_t *d_group_off, uint8_t *d_ok) {
     if (!ngroups) return B381_OK;
-    if (vm_for(ctx, 2 * ngroups)) return b381_pairing_product_is_one_dev(ctx, d_p, d_q, 2 * ngroups, d_group_off, ngroups, d_ok);
+    // few checks: one unit per PAIR, so that the two Miller loops of a check run side by side (latency), then the group products
+    // and one final exponentiation per check; many checks: the shared-accumulator Miller loop (throughput)
+    if (vm_for(ctx, 2 * ngroups) || (ctx->path < 0 && 2 * ngroups <= QUAD_MAX_UNITS))
+        return b381_pairing_product_is_one_dev(ctx, d_p, d_q, 2 * ngroups, d_group_off, ngroups, d_ok);
     void *prod;
     int rc = scratch_get(ctx, 1, ngroups * sizeof(b381_fp12), &prod);
     if (rc) return rc;
@@ -880,9 +1003,8 @@ int b381_miller_product_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381
     if (rc) return rc;
     rc = scratch_get(ctx, 6, 2 * sizeof(uint32_t), &off);
     if (rc) return rc;
-    uint32_t h_off[2] = {0, (uint32_t)npairs};
-    CK(cudaMemcpyAsync(off, h_off, sizeof h_off, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));        // h_off lives on this stack frame
+    k_one_group<<<1, 1, 0, ctx->stream>>>((uint32_t *)off, (uint32_t)npairs);
+    ctx->launches++;
     rc = b381_miller_loop_batch_dev(ctx, d_p, d_q, npairs, (b381_fp12 *)ml);
     if (rc) return rc;
     return group_products(ctx, ml, npairs, (const uint32_t *)off, 1, d_out);
@@ -897,10 +1019,9 @@ int b381_fp12_product_final_exp_is_one_dev(b381_ctx *ctx, const b381_fp12 *d_par
     if (rc) return rc;
     rc = scratch_get(ctx, 6, 2 * sizeof(uint32_t), &off);
     if (rc) return rc;
-    uint32_t h_off[2] = {0, (uint32_t)n};
-    CK(cudaMemcpyAsync(off, h_off, sizeof h_off, cudaMemcpyHostToDevice, ctx->stream));
+    k_one_group<<<1, 1, 0, ctx->stream>>>((uint32_t *)off, (uint32_t)n);
+    ctx->launches++;
     if (n) CK(cudaMemcpyAsync(ml, d_parts, n * sizeof(b381_fp12), cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
     rc = group_products(ctx, ml, n, (const uint32_t *)off, 1, prod);
     if (rc) return rc;
     return final_exp_is_one(ctx, prod, 1, d_ok);
@@ -966,22 +1087,19 @@ int b381_pairing_product_is_one(b381_ctx *ctx, const b381_g1_affine *p, const b3
     void *dp = nullptr, *dq = nullptr;
     int rc = staged_pq(ctx, p, q, npairs ? npairs : 1, &dp, &dq);
     if (rc) return rc;
-    // offsets and result flags live behind the product scratch (slot 1 is sized by the _dev call)
-    uint32_t *doff = nullptr; uint8_t *dok = nullptr;
-    CK(cudaMalloc(&doff, (ngroups + 1) * sizeof(uint32_t)));
-    cudaError_t e = cudaMalloc(&dok, ngroups);
-    if (e != cudaSuccess) { cudaFree(doff); snprintf(ctx->err, sizeof ctx->err, "cudaMalloc: %s", cudaGetErrorString(e)); return B381_ERR_NOMEM; }
-    rc = B381_OK;
-    do {
-        if (cudaMemcpyAsync(doff, group_off, (ngroups + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = B381_ERR_CUDA; break; }
-        rc = b381_pairing_product_is_one_dev(ctx, (b381_g1_affine *)dp, (b381_g2_affine *)dq, npairs, doff, ngroups, dok);
-        if (rc) break;
-        if (cudaMemcpyAsync(ok, dok, ngroups, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { rc = B381_ERR_CUDA; break; }
-        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = B381_ERR_CUDA; break; }
-    } while (0);
-    if (rc == B381_ERR_CUDA) snprintf(ctx->err, sizeof ctx->err, "pairing_product_is_one: %s", cudaGetErrorString(cudaGetLastError()));
-    cudaFree(doff); cudaFree(dok);
-    return rc;
+    // offsets and result flags in grow-only scratch (a cudaMalloc / cudaFree pair per call would synchronise the device on
+    // what is the latency path of a single Verify)
+    void *doff = nullptr, *dok = nullptr;
+    rc = scratch_get(ctx, 25, (ngroups + 1) * sizeof(uint32_t), &doff);
+    if (rc) return rc;
+    rc = scratch_get(ctx, 26, ngroups, &dok);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(doff, group_off, (ngroups + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    rc = b381_pairing_product_is_one_dev(ctx, (b381_g1_affine *)dp, (b381_g2_affine *)dq, npairs, (const uint32_t *)doff, ngroups, (uint8_t *)dok);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ok, dok, ngroups, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B381_OK;
 }
 
 // ---- aggregation, device-resident ----------------------------------------------------------------
@@ -1137,7 +1255,21 @@ int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *
                                                                     (uint32_t *)off, (uint8_t *)valid);
     ctx->launches++;
     CK(cudaGetLastError());
-    rc = pairs2_product_is_one(ctx, (b381_g1_affine *)P, (b381_g2_affine *)Q, nattest, (uint32_t *)off, d_ok);
+    if (path_for(ctx, nattest) == B381_PATH_THREAD && 2 * nmsg <= nattest && ctx->prepared_attest) {
+        // every message point serves many attestations: G2AffineToPrepared once per message, and the pair (-pk, H(m)) of each check
+        // reads the 68 coefficient triples instead of recomputing them (1 760 of the 11 600 Fq multiplications of a check)
+        void *prep, *prod;
+        rc = scratch_get(ctx, 27, nmsg * sizeof(b381_g2_prepared), &prep); if (rc) return rc;
+        rc = scratch_get(ctx, 1, nattest * sizeof(b381_fp12), &prod); if (rc) return rc;
+        rc = b381_g2_prepare_batch_dev(ctx, d_msg_hash, nmsg, (b381_g2_prepared *)prep); if (rc) return rc;
+        k_miller_loop_fused_prepared<<<grid_for(nattest, PAIRING_BLOCK), PAIRING_BLOCK, 0, ctx->stream>>>(
+            (const g1_affine_pod *)P, (const g2_affine_pod *)Q, (const g2_prepared_pod *)prep, d_msg_idx, nattest, (uint64_t *)prod);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        rc = final_exp_is_one(ctx, prod, nattest, d_ok);
+    } else {
+        rc = pairs2_product_is_one(ctx, (b381_g1_affine *)P, (b381_g2_affine *)Q, nattest, (uint32_t *)off, d_ok);
+    }
     if (rc) return rc;
     k_and_bytes2<<<grid_for(nattest, 256), 256, 0, ctx->stream>>>(d_ok, (const uint8_t *)valid, nattest);
     ctx->launches++;

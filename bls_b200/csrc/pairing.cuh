@@ -171,6 +171,109 @@ HD void miller_loop_two(fp12 *f, const g1_affine_pod *P, const g2_affine_pod *Q)
     fp12_conj(f, f);
 }
 
+// ---- prepared G2 points (G2Prepared g2.go:639-642, G2AffineToPrepared g2.go:650-801, MillerLoopItem pairing.go:4-7) -----------
+// The 68 line-coefficient triples of a G2 point in the reference's order (63 doubling steps, 5 addition steps; coefficient k of a
+// step is an Fq2 = 12 x u64, Montgomery form): 19 584 bytes + the infinity flag.  A point that repeats over many pairs -- the
+// hash of a message signed by many committees, the generator in g2pubs -- is prepared once and its Miller loops read the
+// coefficients instead of recomputing them (1 760 of the 6 916 Fq multiplications of a pair).
+#define B381_PREP_STEPS 68
+struct g2_prepared_pod { uint64_t coeffs[B381_PREP_STEPS][3][12]; uint8_t inf; uint8_t pad[7]; };
+HD void prep_store(g2_prepared_pod *out, int k, const fp2 &c0, const fp2 &c1, const fp2 &c2) {
+    fp_store_u64(out->coeffs[k][0], c0.c0); fp_store_u64(out->coeffs[k][0] + 6, c0.c1);
+    fp_store_u64(out->coeffs[k][1], c1.c0); fp_store_u64(out->coeffs[k][1] + 6, c1.c1);
+    fp_store_u64(out->coeffs[k][2], c2.c0); fp_store_u64(out->coeffs[k][2] + 6, c2.c1);
+}
+HD void prep_load(fp2 &c0, fp2 &c1, fp2 &c2, const g2_prepared_pod *in, int k) {
+    fp_load_u64(c0.c0, in->coeffs[k][0]); fp_load_u64(c0.c1, in->coeffs[k][0] + 6);
+    fp_load_u64(c1.c0, in->coeffs[k][1]); fp_load_u64(c1.c1, in->coeffs[k][1] + 6);
+    fp_load_u64(c2.c0, in->coeffs[k][2]); fp_load_u64(c2.c1, in->coeffs[k][2] + 6);
+}
+// G2AffineToPrepared (g2.go:650-801): infinity gives the flag and all-zero coefficients (the reference leaves the slice empty)
+HD void g2_prepare_one(g2_prepared_pod *out, const g2_affine_pod *Q) {
+    out->inf = Q->inf ? 1 : 0;
+    for (int i = 0; i < 7; i++) out->pad[i] = 0;
+    fp2 c0, c1, c2;
+    if (Q->inf) {
+        fp2_set_zero(c0);
+#pragma unroll 1
+        for (int k = 0; k < B381_PREP_STEPS; k++) prep_store(out, k, c0, c0, c0);
+        return;
+    }
+    fp2 qx, qy;
+    g2_jac r;
+    fp_load_u64(qx.c0, Q->x); fp_load_u64(qx.c1, Q->x + 6);
+    fp_load_u64(qy.c0, Q->y); fp_load_u64(qy.c1, Q->y + 6);
+    r.x = qx; r.y = qy; fp2_set_one(r.z);
+    const uint64_t xr = 0xd201000000010000ULL >> 1;
+    int k = 0;
+#pragma unroll 1
+    for (int bit = 61; bit >= -1; bit--) {
+        line_double(&r, &c0, &c1, &c2);
+        prep_store(out, k++, c0, c1, c2);
+        if (bit < 0) break;
+        if ((xr >> bit) & 1) {
+            line_add(&r, &qx, &qy, &c0, &c1, &c2);
+            prep_store(out, k++, c0, c1, c2);
+        }
+    }
+}
+// MillerLoop of one item (P, prepared Q)   (pairing.go:16-75): the same value as miller_loop_one(P, Q)
+HD void miller_loop_prepared_one(fp12 *f, const g1_affine_pod *P, const g2_prepared_pod *Qp) {
+    fp12_set_one(f);
+    if (P->inf || Qp->inf) return;
+    fp px, py;
+    fp_load_u64(px, P->x); fp_load_u64(py, P->y);
+    fp2 c0, c1, c2;
+    const uint64_t xr = 0xd201000000010000ULL >> 1;
+    int k = 0;
+#pragma unroll 1
+    for (int bit = 61; bit >= -1; bit--) {
+        prep_load(c0, c1, c2, Qp, k++);
+        ell(f, &c0, &c1, &c2, &px, &py);
+        if (bit < 0) break;
+        if ((xr >> bit) & 1) {
+            prep_load(c0, c1, c2, Qp, k++);
+            ell(f, &c0, &c1, &c2, &px, &py);
+        }
+        fp12_sqr(f, f);
+    }
+    fp12_conj(f, f);
+}
+// Two pairs sharing the accumulator, the FIRST computed (its G2 point is new: a signature), the SECOND read from a prepared
+// point (a message hash shared by many checks): the shape of the attestation batch.  Same value as miller_loop_two.
+HD void miller_loop_fused_prepared(fp12 *f, const g1_affine_pod *P, const g2_affine_pod *Q0, const g2_prepared_pod *Q1p) {
+    fp12_set_one(f);
+    const bool live0 = !(P[0].inf || Q0->inf), live1 = !(P[1].inf || Q1p->inf);
+    if (!live0 && !live1) return;
+    fp px[2], py[2];
+    fp2 qx, qy;
+    g2_jac r;
+    for (int k = 0; k < 2; k++) { fp_load_u64(px[k], P[k].x); fp_load_u64(py[k], P[k].y); }
+    fp_load_u64(qx.c0, Q0->x); fp_load_u64(qx.c1, Q0->x + 6);
+    fp_load_u64(qy.c0, Q0->y); fp_load_u64(qy.c1, Q0->y + 6);
+    r.x = qx; r.y = qy; fp2_set_one(r.z);
+    fp2 c0, c1, c2;
+    const uint64_t xr = 0xd201000000010000ULL >> 1;
+    int k = 0;
+#pragma unroll 1
+    for (int bit = 61; bit >= -1; bit--) {
+        const bool add = bit >= 0 && ((xr >> bit) & 1);
+        if (live0) {
+            line_double(&r, &c0, &c1, &c2);
+            ell(f, &c0, &c1, &c2, &px[0], &py[0]);
+            if (add) { line_add(&r, &qx, &qy, &c0, &c1, &c2); ell(f, &c0, &c1, &c2, &px[0], &py[0]); }
+        }
+        if (live1) {
+            prep_load(c0, c1, c2, Q1p, k);
+            ell(f, &c0, &c1, &c2, &px[1], &py[1]);
+            if (add) { prep_load(c0, c1, c2, Q1p, k + 1); ell(f, &c0, &c1, &c2, &px[1], &py[1]); }
+        }
+        k += add ? 2 : 1;
+        if (bit >= 0) fp12_sqr(f, f);
+    }
+    fp12_conj(f, f);
+}
+
 // conj(f^x) for f in the cyclotomic subgroup   (ExpByX, pairing.go:92-98): MSB-first square and multiply with
 // Granger-Scott squarings.  The form the reference's loop has; exp_by_x below falls back to it for degenerate values.
 HDN void exp_by_x_gs(fp12 *r, const fp12 *f, uint64_t x) {

@@ -24,6 +24,8 @@ G1_JAC = np.dtype([("x", U64, (6,)), ("y", U64, (6,)), ("z", U64, (6,))])
 G2_JAC = np.dtype([("x", U64, (2, 6)), ("y", U64, (2, 6)), ("z", U64, (2, 6))])
 #: FQ12 flattened c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2, each FQ2 = c0 || c1 (fq12.go:9-12): 576 bytes
 FP12 = np.dtype((U64, (2, 3, 2, 6)))
+# G2Prepared (g2.go:639-642): 68 coefficient triples (c0 || c1 each), infinity flag + padding = b381_g2_prepared
+G2_PREPARED = np.dtype([("coeffs", U64, (68, 3, 2, 6)), ("inf", np.uint8), ("pad", np.uint8, (7,))])
 #: canonical scalar < r, 4 x u64 LS limb first (frrepr.go:11)
 SCALAR = np.dtype((U64, (4,)))
 

@@ -44,6 +44,11 @@ typedef struct { b381_fp x, y, z; } b381_g1_jac;
 typedef struct { b381_fp2 x, y, z; } b381_g2_jac;
 typedef struct { uint64_t l[4]; } b381_scalar;
 
+/* G2Prepared (g2.go:639-642): the 68 line-coefficient triples G2AffineToPrepared (g2.go:650-801) computes for a G2 point, in
+ * the reference's order (63 doubling steps and 5 addition steps interleaved as the bits of blsX >> 1 dictate), then the
+ * infinity flag + padding.  An infinite point has all-zero coefficients (the reference leaves the slice empty). */
+typedef struct { b381_fp2 coeffs[68][3]; uint8_t infinity; uint8_t pad[7]; } b381_g2_prepared;
+
 typedef struct b381_ctx b381_ctx;
 
 enum {
@@ -97,6 +102,18 @@ int b381_miller_loop_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b
 int b381_final_exp_batch(b381_ctx *ctx, const b381_fp12 *in, size_t n, b381_fp12 *out, uint8_t *ok);
 int b381_final_exp_batch_dev(b381_ctx *ctx, const b381_fp12 *d_in, size_t n, b381_fp12 *d_out,
                              uint8_t *d_ok);
+/* Prepared G2 points.  b381_g2_prepare_batch = n x G2AffineToPrepared (g2.go:650-801); b381_miller_loop_prepared_batch:
+ * out[i] = MillerLoop([]MillerLoopItem{{p[i], prep[prep_idx ? prep_idx[i] : i]}}) (pairing.go:4-7,16-75): the same Fq12 as
+ * b381_miller_loop_batch on the unprepared point, 1 760 Fq multiplications cheaper per pair.  A MillerLoop over several items is
+ * the product of the one-item values (the shared accumulator of pairing.go:40-69 computes exactly that product).  prep_idx
+ * lets many pairs share one prepared point (the hash of a message many committees signed; the generator in g2pubs); nprep is
+ * the number of prepared points behind `prep`. */
+int b381_g2_prepare_batch(b381_ctx *ctx, const b381_g2_affine *q, size_t n, b381_g2_prepared *prep);
+int b381_g2_prepare_batch_dev(b381_ctx *ctx, const b381_g2_affine *d_q, size_t n, b381_g2_prepared *d_prep);
+int b381_miller_loop_prepared_batch(b381_ctx *ctx, const b381_g1_affine *p, const b381_g2_prepared *prep, size_t nprep,
+                                    const uint32_t *prep_idx, size_t n, b381_fp12 *out);
+int b381_miller_loop_prepared_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_prepared *d_prep,
+                                        const uint32_t *d_prep_idx, size_t n, b381_fp12 *d_out);
 /* Generalised bls.CompareTwoPairings (pairing.go:140-147): for every group g,
  *   ok[g] = FinalExponentiation(prod_{i in [group_off[g], group_off[g+1])} MillerLoop(p[i], q[i])) == 1.
  * group_off has ngroups+1 non-decreasing entries, group_off[0] == 0, group_off[ngroups] == npairs.

@@ -84,3 +84,15 @@ extern "C" unsigned long long emu_dot2_count(int reset) {
     if (reset) hostimpl::g_dot2_count = 0;
     return v;
 }
+
+// prepared G2 points (pairing.cuh): coefficients, Miller loop from them, the fused + prepared two-pair loop
+extern "C" void emu_g2_prepare(const g2_affine_pod *q, size_t n, g2_prepared_pod *out) {
+    for (size_t i = 0; i < n; i++) g2_prepare_one(out + i, q + i);
+}
+extern "C" void emu_miller_loop_prepared(const g1_affine_pod *p, const g2_prepared_pod *prep, const uint32_t *idx, size_t n, uint64_t *out) {
+    for (size_t i = 0; i < n; i++) { fp12 f; miller_loop_prepared_one(&f, p + i, prep + (idx ? idx[i] : i)); fp12_store_u64(out + 72 * i, &f); }
+}
+extern "C" void emu_miller_loop_fused_prepared(const g1_affine_pod *p, const g2_affine_pod *q0, const g2_prepared_pod *prep, const uint32_t *idx,
+                                               size_t ngroups, uint64_t *out) {
+    for (size_t i = 0; i < ngroups; i++) { fp12 f; miller_loop_fused_prepared(&f, p + 2 * i, q0 + i, prep + idx[i]); fp12_store_u64(out + 72 * i, &f); }
+}

@@ -177,3 +177,34 @@ def test_op_counts(emu):
     P2 = hg.g1_progression(3, 1, 2); Q2 = hg.g2_progression(4, 1, 2)
     emu.emu_miller_loop2(_p(P2), _p(Q2), ctypes.c_size_t(1), _p(ml)); c = macs()
     assert c == bench.MACS_IMPL_MILLER2
+
+
+def test_prepared_g2(emu, orc):
+    """g2_prepare_one == the oracle's G2AffineToPrepared coefficients (g2.go:650-801: 68 triples in the reference's order),
+    miller_loop_prepared_one == MillerLoop on the unprepared point, the fused + prepared two-pair loop == miller_loop_two"""
+    n = 4
+    P = hg.g1_progression(0x71, 3, 2 * n); Q = hg.g2_progression(0x33, 5, n)
+    Q["inf"][3] = 1
+    prep = np.zeros(n, dtype=L.G2_PREPARED)
+    emu.emu_g2_prepare(_p(Q), ctypes.c_size_t(n), _p(prep))
+    for i in range(3):
+        want = orc.g2_prepare(Q[i:i + 1])
+        assert want.shape[0] == 68 and (prep["coeffs"][i] == want).all(), i
+    assert prep["inf"].tolist() == [0, 0, 0, 1] and not prep["coeffs"][3].any()
+    idx = np.array([0, 1, 2, 3, 0, 0, 2, 1], np.uint32)
+    out = np.zeros(2 * n, dtype=L.FP12)
+    emu.emu_miller_loop_prepared(_p(P), _p(prep), _p(idx), ctypes.c_size_t(2 * n), _p(out))
+    ref = np.zeros(2 * n, dtype=L.FP12)
+    Qi = Q[idx]
+    emu.emu_miller_loop(_p(P), _p(Qi), ctypes.c_size_t(2 * n), _p(ref))
+    assert out.tobytes() == ref.tobytes()
+    for i in (0, 1, 2):
+        assert (out[i] == orc.miller_loop(P[i:i + 1], Qi[i:i + 1])).all()
+    # groups of two pairs: (P[2g], Q0[g]) computed, (P[2g+1], prep[gidx[g]]) from coefficients
+    gidx = np.array([1, 0, 3, 2], np.uint32)
+    Q0 = hg.g2_progression(0x99, 7, n); Q0["inf"][1] = 1
+    QQ = np.zeros(2 * n, dtype=L.G2_AFFINE); QQ[0::2] = Q0; QQ[1::2] = Q[gidx]
+    got = np.zeros(n, dtype=L.FP12); want2 = np.zeros(n, dtype=L.FP12)
+    emu.emu_miller_loop_fused_prepared(_p(P), _p(Q0), _p(prep), _p(gidx), ctypes.c_size_t(n), _p(got))
+    emu.emu_miller_loop2(_p(P), _p(QQ), ctypes.c_size_t(n), _p(want2))
+    assert got.tobytes() == want2.tobytes()

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 # the verification tests below run on the VM kernels ("auto" at these sizes), on the one-pairing-per-thread kernels incl. the
 # shared-accumulator k_miller_loop2, and on the two-lane kernels (k_duo_miller_loop<2>): b381_set_kernel_path
-@pytest.fixture(scope="module", params=["auto", "thread", "duo"])
+@pytest.fixture(scope="module", params=["auto", "vm", "thread", "duo"])
 def ctx(request):
     from bls_b200 import capi
     c = capi.Ctx(0, path=request.param)

@@ -8,10 +8,10 @@ from bls_b200 import hostgen as hg, layout as L
 pytestmark = pytest.mark.gpu
 
 
-# every test of this module runs once per schedule of the pairing arithmetic (b381_set_kernel_path): "auto" takes the
-# warp-cooperative VM for these batch sizes, the others force the one-pairing-per-thread kernels of the 2^16 benchmark
-# (k_miller_loop / k_final_exp / k_group_product), the two-lane kernels (k_duo_*) and the four-lane kernels (k_quad_*)
-@pytest.fixture(scope="module", params=["auto", "thread", "duo", "quad"])
+# every test of this module runs once per schedule of the pairing arithmetic (b381_set_kernel_path): "auto" picks by batch size
+# (four lanes per pairing at these sizes), the others force the warp-cooperative VM, the one-pairing-per-thread kernels of the
+# 2^16 benchmark (k_miller_loop / k_final_exp / k_group_product), the two-lane kernels (k_duo_*), the four-lane kernels (k_quad_*)
+@pytest.fixture(scope="module", params=["auto", "vm", "thread", "duo", "quad"])
 def ctx(request):
     from bls_b200 import capi
     c = capi.Ctx(0, path=request.param)
@@ -166,3 +166,27 @@ def test_full_size_bilinearity_checksum(ctx, orc):
     out = ctx.pairing_batch(P, Q)
     idx = np.arange(0, n, 1024)
     assert out[idx].tobytes() == orc.pairing_batch(P[idx], Q[idx], threads=8).tobytes()
+
+
+def test_prepared_g2_points(ctx, orc):
+    """b381_g2_prepare_batch == G2AffineToPrepared (g2.go:650-801: the oracle's 68 coefficient triples, bit for bit) and
+    b381_miller_loop_prepared_batch == MillerLoop on a MillerLoopItem (pairing.go:4-7,16-75) == the fused Miller loop;
+    several pairs share one prepared point through prep_idx; an infinite Q or P gives the factor 1"""
+    n = 37
+    Q = hg.g2_progression(0x5151, 0x77, 5)
+    Q["inf"][4] = 1
+    prep = ctx.g2_prepare_batch(Q)
+    for i in range(4):
+        assert (prep["coeffs"][i] == orc.g2_prepare(Q[i:i + 1])).all(), i
+    assert prep["inf"].tolist() == [0, 0, 0, 0, 1]
+    P = hg.g1_progression(0x1717, 0x3, n)
+    P["inf"][9] = 1
+    idx = (np.arange(n) % 5).astype(np.uint32)
+    got = ctx.miller_loop_prepared_batch(P, prep, idx)
+    want = ctx.miller_loop_batch(P, Q[idx])
+    assert got.tobytes() == want.tobytes()
+    for i in (0, 6, 13):
+        assert (got[i] == orc.miller_loop(P[i:i + 1], Q[idx[i]:idx[i] + 1])).all(), i
+    # without an index: pair i uses prepared point i
+    got2 = ctx.miller_loop_prepared_batch(P[:5], prep)
+    assert got2.tobytes() == ctx.miller_loop_batch(P[:5], Q).tobytes()

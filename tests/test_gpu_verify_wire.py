@@ -16,7 +16,7 @@ from bls_b200 import hostgen as hg, layout as L
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["auto", "thread", "duo"])
+@pytest.fixture(scope="module", params=["auto", "vm", "thread", "duo"])
 def ctx(request):
     from bls_b200 import capi
     return capi.Ctx(0, path=request.param)

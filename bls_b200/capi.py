@@ -325,12 +325,27 @@ class Ctx:
         """ok[i] = g2pubs.Verify(msgs[i], pub_i, sig_i) from wire bytes -- b381_g2pubs_verify_batch"""
         return self._verify_wire("b381_g2pubs_verify_batch", pubs96, 96, msgs, sigs48, 48)
 
-    def verify_with_domain_rlc_batch(self, pubs48, msgs32, domain8, sigs96, weights):
-        """one boolean for the whole batch (random linear combination) -- b381_verify_with_domain_rlc_batch"""
+    @staticmethod
+    def rlc_weights(n):
+        """n fresh non-zero 64-bit weights from the operating system's generator (the verifier's randomness)"""
+        w = np.frombuffer(os.urandom(8 * n), dtype=np.uint64).copy()
+        w[w == 0] = 1
+        return w
+
+    def set_rlc_weight_bits(self, bits):
+        self.call("b381_set_rlc_weight_bits", ctypes.c_int(bits))
+
+    def verify_with_domain_rlc_batch(self, pubs48, msgs32, domain8, sigs96, weights=None):
+        """one boolean for the whole batch (random linear combination) -- b381_verify_with_domain_rlc_batch.  weights: one
+        non-zero 64-bit value per triple; None draws them here (a zero weight is rejected by the engine: the check is false)"""
         p = np.ascontiguousarray(pubs48, np.uint8).reshape(-1); m = np.ascontiguousarray(msgs32, np.uint8).reshape(-1)
         s = np.ascontiguousarray(sigs96, np.uint8).reshape(-1); d = np.frombuffer(bytes(domain8), np.uint8).copy()
         n = p.size // 48
-        r = np.zeros((n, 4), np.uint64); r[:, 0] = np.asarray(weights, np.uint64)
+        assert p.size == 48 * n and s.size == 96 * n and m.size == 32 * n and d.size == 8, "buffer sizes do not match the triple count"
+        weights = self.rlc_weights(n) if weights is None else np.asarray(weights, np.uint64)
+        assert weights.size == n
+        self.set_rlc_weight_bits(64)
+        r = np.zeros((n, 4), np.uint64); r[:, 0] = weights
         ok = np.zeros(1, np.uint8)
         self.call("b381_verify_with_domain_rlc_batch", _hp(p), _hp(m), _hp(d), ctypes.c_size_t(0), _hp(s), _hp(r), ctypes.c_size_t(n), _hp(ok))
         return bool(ok[0])
@@ -341,6 +356,8 @@ class Ctx:
         pub = np.ascontiguousarray(pub, dtype=L.G1_AFFINE); h = np.ascontiguousarray(msg_point, dtype=L.G2_AFFINE)
         sig = np.ascontiguousarray(sig, dtype=L.G2_AFFINE)
         n = pub.size
+        assert h.size == n and sig.size == n and np.asarray(weights).size == n
+        self.set_rlc_weight_bits(64)
         r = np.zeros((n, 4), np.uint64); r[:, 0] = np.asarray(weights, np.uint64)
         bufs = [self.to_device(a) for a in (pub, h, sig, r)]
         dpart, dval = self.dev_empty(576), self.dev_empty(8)

@@ -344,6 +344,7 @@ struct b381_ctx {
     struct { uint4 *code, *consts; int lanes, nsteps, nslots, spill_fq; } vm[3];
     int path;                // -1 by batch size, 0 one pairing per thread, 1 warp-cooperative VM, 2 four lanes per pairing
     int vm_split;
+    int rlc_bits;            // bit length the caller promises for the weights of the random-linear-combination checks
     int prepared_attest;     // attestation batches prepare repeated message points (B381_PREPARED=0 disables: A/B measurements)
 };
 enum { VM_ML1 = 0, VM_FE_A = 1, VM_FE_C = 2 };
@@ -474,6 +475,7 @@ int b381_init(int device, b381_ctx **out) {
     // throughput once ~65 k threads are resident).  Default: by batch size; B381_VM=0/1 forces one of them for A/B measurements.
     const char *ev = getenv("B381_VM");
     ctx->path = ev ? (ev[0] == '0' ? 0 : 1) : -1;
+    ctx->rlc_bits = 255;
     const char *epr = getenv("B381_PREPARED");
     ctx->prepared_attest = epr ? (epr[0] != '0') : 1;
     const char *ep = getenv("B381_PATH");          // thread | vm | quad | auto (same as b381_set_kernel_path)
@@ -513,6 +515,11 @@ int b381_use_own_stream(b381_ctx *ctx) {
 int b381_set_kernel_path(b381_ctx *ctx, int path) {
     if (!ctx || path < B381_PATH_AUTO || path > B381_PATH_DUO) return B381_ERR_ARG;
     ctx->path = path;
+    return B381_OK;
+}
+int b381_set_rlc_weight_bits(b381_ctx *ctx, int bits) {
+    if (!ctx || bits < 8 || bits > 255) return B381_ERR_ARG;
+    ctx->rlc_bits = bits;
     return B381_OK;
 }
 int b381_sync(b381_ctx *ctx) {
@@ -1366,8 +1373,8 @@ static int verify_wire_dev(b381_ctx *ctx, int mode, const uint8_t *d_pub, const 
 static int verify_rlc_core(b381_ctx *ctx, const b381_g1_affine *d_pub, const b381_g2_affine *d_h, const b381_g2_affine *d_sig,
                            const uint8_t *d_pub_status, const uint8_t *d_sig_status, const b381_scalar *d_r, size_t n, uint8_t *d_ok,
                            b381_fp12 *d_partial = nullptr) {
-    const int rlc_bits = 255;          // weights are full scalars; callers that use 64-bit weights only pay for empty windows' scans
     if (!ctx || n > 0x7FFFFFF0u || !d_ok || (n && (!d_pub || !d_h || !d_sig || !d_r))) return B381_ERR_ARG;
+    const int rlc_bits = ctx->rlc_bits;     // the weights' bit length (b381_set_rlc_weight_bits): MSM windows and ladder length follow it
     void *P, *Q, *S, *off, *bad;
     int rc = scratch_get(ctx, 2, (n + 1) * sizeof(b381_g1_affine), &P); if (rc) return rc;
     rc = scratch_get(ctx, 3, (n + 1) * sizeof(b381_g2_affine), &Q); if (rc) return rc;
@@ -1377,7 +1384,7 @@ static int verify_rlc_core(b381_ctx *ctx, const b381_g1_affine *d_pub, const b38
     CK(cudaMemsetAsync(bad, 0, sizeof(uint32_t), ctx->stream));
     if (n) {
         k_rlc_valid<<<grid_for(n, 256), 256, 0, ctx->stream>>>((const g1_affine_pod *)d_pub, (const g2_affine_pod *)d_sig, d_pub_status,
-                                                               d_sig_status, n, (uint32_t *)bad);
+                                                               d_sig_status, (const uint64_t *)d_r, rlc_bits, n, (uint32_t *)bad);
         ctx->launches++;
         rc = b381_g1_mul_batch_dev(ctx, d_pub, 1, d_r, 1, n, (b381_g1_affine *)P); if (rc) return rc;
         CK(cudaMemcpyAsync(Q, d_h, n * sizeof(b381_g2_affine), cudaMemcpyDeviceToDevice, ctx->stream));

@@ -141,7 +141,7 @@ template <class F> HDN void field_pow(typename F::T *r, const typename F::T *a, 
 // FQ.Sqrt (fq.go:203-217): q = 3 mod 4
 HDN bool fp_sqrt(fp *out, const fp *a) {
     fp a1, a0, m1;
-    field_pow<FpInl>(&a1, a, B381_TAB(qm3o4));
+    field_pow<FpSqr>(&a1, a, B381_TAB(qm3o4));
     fp_sqr(a0, a1);
     fp_mul(a0, a0, *a);
     fp_load_tab(m1, B381_TAB(neg_one));
@@ -265,7 +265,7 @@ HDN void fp2_sqrt_from_norm_root(fp2 *out, const fp2 *a, const fp *sp) {
     fp t, w, x, c, one;
     fp_add(t, a->c0, *sp);
     fp_half(t, t);
-    field_pow<FpInl>(&w, &t, B381_TAB(qm3o4));
+    field_pow<FpSqr>(&w, &t, B381_TAB(qm3o4));
     fp_mul(x, w, t);
     fp_mul(c, w, x);                           // t^((Q-1)/2)
     fp_mul(w, w, a->c1);

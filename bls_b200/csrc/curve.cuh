@@ -35,6 +35,16 @@ struct FpIlp : FpInl {
 };
 template <class F> struct shift_policy { typedef F type; };
 template <> struct shift_policy<FpInl> { typedef FpIlp type; };
+// the dedicated squaring body (fp_sqr_v) for long squaring chains: square-root exponentiations
+struct FpSqr : FpInl {
+    static HD void sqr(T &r, const T &a) {
+#if defined(B381_NO_FP_SQR)
+        fp_sqr(r, a);
+#else
+        r = fp_sqr_v(a);
+#endif
+    }
+};
 struct FpOut : FpInl {
     static HD void mul(T &r, const T &a, const T &b) { fp_mul_n(&r, &a, &b); }
     static HD void sqr(T &r, const T &a) { fp_sqr_n(&r, &a); }

@@ -328,6 +328,22 @@ HDN void fp_dot2_p(fp *r, const fp *a, const fp *b, const fp *c, const fp *d) {
 #endif
 }
 HD void fp_mul(fp &r, const fp &a, const fp &b) { r = fp_mul_v(a, b); }
-HD void fp_sqr(fp &r, const fp &a) { r = fp_mul_v(a, a); }   // fq.go:151-198
+HD void fp_sqr(fp &r, const fp &a) { r = fp_mul_v(a, a); }   // fq.go:151-198 through the multiplier (the pairing kernels: no second body)
+// FQ.SquareAssign (fq.go:151-198) with its own body: the 66 cross products once, doubled, and the 12 diagonal products -- 228 wide
+// MACs instead of 300 (78 products + 144 reduction + 12 quotient words; FP_SQR_PTX, tools/gen_fp_asm.py).  Used by the long
+// squaring chains: square roots (380 squarings each) in decompression and hashing.  Out of line, by value.
+HDN fp fp_sqr_v(fp a) {
+#if defined(__CUDA_ARCH__)
+    fp r;
+    asm(FP_SQR_PTX
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]),
+          "=r"(r.l[7]), "=r"(r.l[8]), "=r"(r.l[9]), "=r"(r.l[10]), "=r"(r.l[11])
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+          "r"(a.l[8]), "r"(a.l[9]), "r"(a.l[10]), "r"(a.l[11]));
+    return r;
+#else
+    return fp_mul_v(a, a);
+#endif
+}
 
 }  // namespace b381

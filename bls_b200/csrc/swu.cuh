@@ -326,11 +326,22 @@ __global__ void __launch_bounds__(128) k_rlc_close(const g2_jac_pod *__restrict_
     for (int k = 0; k < 7; k++) q.pad[k] = 0;
     *Q_last = q;
 }
+// a weight of zero would drop its triple from the combination (r pk = infinity contributes the factor 1), and a weight of more
+// than `bits` bits would be truncated by the short ladder / the window count: both make the whole check false
 __global__ void k_rlc_valid(const g1_affine_pod *__restrict__ pub, const g2_affine_pod *__restrict__ sig, const uint8_t *__restrict__ pub_status,
-                            const uint8_t *__restrict__ sig_status, size_t n, uint32_t *__restrict__ any_bad) {
+                            const uint8_t *__restrict__ sig_status, const uint64_t *__restrict__ r, int bits, size_t n,
+                            uint32_t *__restrict__ any_bad) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     bool bad = pub[i].inf || sig[i].inf || (pub_status && pub_status[i]) || (sig_status && sig_status[i]);
+    uint64_t any = 0, over = 0;
+    for (int l = 0; l < 4; l++) {
+        uint64_t w = r[4 * i + l];
+        any |= w;
+        int lo = 64 * l;
+        if (bits <= lo) over |= w; else if (bits < lo + 64) over |= w >> (bits - lo);
+    }
+    bad = bad || any == 0 || over != 0;
     if (bad) atomicOr(any_bad, 1u);
 }
 __global__ void k_rlc_finish(uint8_t *__restrict__ ok, const uint32_t *__restrict__ any_bad) {

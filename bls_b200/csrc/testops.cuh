@@ -12,6 +12,7 @@ namespace b381 {
 #if defined(__CUDACC__)
 
 // family 0: Fq (6 x u64 per element).  op: 0 mul 1 add 2 sub 3 sqr 4 neg 5 dbl 6 inv 8 inv by the Fermat chain 9 a*b + a*b as one dot product
+// 10 the multiplication body inlined 11 the dedicated squaring body (FQ.SquareAssign, fq.go:151-198)
 __global__ void k_test_fp(int op, const uint64_t *a, const uint64_t *b, uint64_t *o, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -28,6 +29,7 @@ __global__ void k_test_fp(int op, const uint64_t *a, const uint64_t *b, uint64_t
         case 8: fp_inv_fermat(&r, &x); break;
         case 9: r = fp_dot2_v(x, y, y, x); break;
         case 10: fp_mul_inl(r, x, y); break;
+        case 11: r = fp_sqr_v(x); break;
         default: r = x;
     }
     fp_store_u64(o + 6 * i, r);

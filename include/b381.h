@@ -77,6 +77,10 @@ int b381_sync(b381_ctx *ctx);
  * initial value. */
 enum { B381_PATH_AUTO = -1, B381_PATH_THREAD = 0, B381_PATH_VM = 1, B381_PATH_QUAD = 2, B381_PATH_DUO = 3 };
 int b381_set_kernel_path(b381_ctx *ctx, int path);
+/* Bit length of the weights r_i of the random-linear-combination checks (b381_verify_rlc_dev, b381_verify_with_domain_rlc_batch,
+ * b381_verify_rlc_partial_dev): default 255 (any canonical scalar); 64 or 128 is what a verifier needs (soundness error
+ * 2^-bits) and shortens the weighted sums accordingly.  A weight of zero or of more than `bits` bits makes the check false. */
+int b381_set_rlc_weight_bits(b381_ctx *ctx, int bits);
 /* number of kernels this ctx has launched so far */
 uint64_t b381_launch_count(const b381_ctx *ctx);
 

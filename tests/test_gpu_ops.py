@@ -39,12 +39,12 @@ def _edge_fq(orc, seed, n):
 def test_fq_ops_edges_and_random(ctx, orc):
     n = 1 << 12
     a = _edge_fq(orc, 1001, n); b = np.roll(_edge_fq(orc, 1002, n), 3, axis=0)
-    for op, name in [(0, "mul"), (1, "add"), (2, "sub"), (3, "square"), (4, "neg"), (5, "double"), (10, "mul")]:
+    for op, name in [(0, "mul"), (1, "add"), (2, "sub"), (3, "square"), (4, "neg"), (5, "double"), (10, "mul"), (11, "square")]:
         out, _, _ = ctx.test_op(0, op, a, b)
         assert (out == orc.fq(name, a, b)).all(), name
     # every pairing of the edge operands with each other (7 x 7)
     ea = np.repeat(a[:7], 7, axis=0); eb = np.tile(a[:7], (7, 1))
-    for op, name in [(0, "mul"), (1, "add"), (2, "sub")]:
+    for op, name in [(0, "mul"), (1, "add"), (2, "sub"), (11, "square")]:
         out, _, _ = ctx.test_op(0, op, ea, eb)
         assert (out == orc.fq(name, ea, eb)).all(), name
     # the two-product dot product with one reduction (the rows of every Fq2 product): a b + b a = 2 a b

@@ -141,6 +141,31 @@ def test_rlc_batch_verification(ctx):
     assert ok.sum() == n - 1 and ok[777] == 0
 
 
+def test_rlc_weights_zero_or_too_wide_are_rejected(ctx):
+    """a zero weight would silently drop its triple (r pk = infinity is the factor 1), so a batch whose only bad
+    signature carries weight 0 would pass; weights wider than the declared bit length would be truncated.  Both make the check
+    false; weights drawn by the wrapper (None) are non-zero 64-bit values."""
+    _, msgs, domain, pubs, sigs = make_batch(ctx, 8, 31)
+    assert ctx.verify_with_domain_rlc_batch(pubs, msgs, domain, sigs) is True                 # wrapper-generated weights
+    w = np.arange(1, 9, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    assert ctx.verify_with_domain_rlc_batch(pubs, msgs, domain, sigs, w) is True
+    s2 = sigs.copy(); s2[3] = sigs[4]                                                          # a wrong signature ...
+    w0 = w.copy(); w0[3] = 0                                                                   # ... hidden behind a zero weight
+    assert ctx.verify_with_domain_rlc_batch(pubs, msgs, domain, s2, w) is False
+    assert ctx.verify_with_domain_rlc_batch(pubs, msgs, domain, s2, w0) is False
+    assert ctx.verify_with_domain_rlc_batch(pubs, msgs, domain, sigs, w0) is False             # zero weight on a valid batch too
+    ctx.set_rlc_weight_bits(32)                                                                # declared 32 bits, weights are 64 bits wide
+    r = np.zeros((8, 4), np.uint64); r[:, 0] = w
+    import ctypes
+    from bls_b200.capi import _hp
+    ok = np.ones(1, np.uint8)
+    p = np.ascontiguousarray(pubs, np.uint8).reshape(-1); m = np.ascontiguousarray(msgs, np.uint8).reshape(-1)
+    sg = np.ascontiguousarray(sigs, np.uint8).reshape(-1); d = np.frombuffer(bytes(domain), np.uint8).copy()
+    ctx.call("b381_verify_with_domain_rlc_batch", _hp(p), _hp(m), _hp(d), ctypes.c_size_t(0), _hp(sg), _hp(r), ctypes.c_size_t(8), _hp(ok))
+    assert ok[0] == 0
+    ctx.set_rlc_weight_bits(255)
+
+
 def test_rlc_partials_combine_like_the_unsharded_check(ctx):
     """the multi-GPU form on one device: three 'ranks' form partial Miller products of their tiles; the product of the
     partials passes the final exponentiation iff the unsharded batch does (b381_verify_rlc_partial_dev +

@@ -425,6 +425,8 @@ def main():
     txt += to_ptx(gen_mul(), "FP_MUL_PTX", 2)
     txt += "// FP_DOT2_PTX: %0..%11 = r (out), %12..%23 = a, %24..%35 = b, %36..%47 = c, %48..%59 = d;  r = (a*b + c*d) * 2^-384 mod Q\n"
     txt += to_ptx(gen_dot2(), "FP_DOT2_PTX", 4)
+    txt += "// FP_SQR_PTX: %0..%11 = r (out), %12..%23 = a;  r = a*a * 2^-384 mod Q -- FQ.SquareAssign (fq.go:151-198): 66 cross products once, doubled, 12 diagonal products\n"
+    txt += to_ptx(gen_sqr(), "FP_SQR_PTX", 1)
     txt += "// FP_MUL_NR_PTX / FP_DOT2_NR_PTX: the same without the final conditional subtraction: result in [0, 2Q)\n"
     txt += to_ptx(gen_mul(False), "FP_MUL_NR_PTX", 2)
     txt += to_ptx(gen_dot2(False), "FP_DOT2_NR_PTX", 4)

@@ -31,6 +31,8 @@ var decodeErrors = []error{
 // DecompressG1Batch is DecompressG1 (g1.go:185-195) over many 48-byte encodings; errs[i] is nil or the
 // reference's error.  checked = false gives DecompressG1Unchecked (g1.go:199-227).
 func DecompressG1Batch(in [][48]byte, checked bool) ([]G1Affine, []error) {
+	c, leave := enter()
+	defer leave()
 	n := len(in)
 	out := make([]G1Affine, n)
 	st := make([]uint8, n)
@@ -42,7 +44,7 @@ func DecompressG1Batch(in [][48]byte, checked bool) ([]G1Affine, []error) {
 	if checked {
 		chk = 1
 	}
-	rc := C.b381_g1_decompress_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&in[0])), C.size_t(n), chk,
+	rc := C.b381_g1_decompress_batch(c, (*C.uint8_t)(unsafe.Pointer(&in[0])), C.size_t(n), chk,
 		(*C.b381_g1_affine)(unsafe.Pointer(&out[0])), (*C.uint8_t)(unsafe.Pointer(&st[0])))
 	must(rc)
 	for i, s := range st {
@@ -53,6 +55,8 @@ func DecompressG1Batch(in [][48]byte, checked bool) ([]G1Affine, []error) {
 
 // DecompressG2Batch is DecompressG2 (g2.go:219-229) / DecompressG2Unchecked (g2.go:232-265) over 96-byte encodings.
 func DecompressG2Batch(in [][96]byte, checked bool) ([]G2Affine, []error) {
+	c, leave := enter()
+	defer leave()
 	n := len(in)
 	out := make([]G2Affine, n)
 	st := make([]uint8, n)
@@ -64,7 +68,7 @@ func DecompressG2Batch(in [][96]byte, checked bool) ([]G2Affine, []error) {
 	if checked {
 		chk = 1
 	}
-	rc := C.b381_g2_decompress_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&in[0])), C.size_t(n), chk,
+	rc := C.b381_g2_decompress_batch(c, (*C.uint8_t)(unsafe.Pointer(&in[0])), C.size_t(n), chk,
 		(*C.b381_g2_affine)(unsafe.Pointer(&out[0])), (*C.uint8_t)(unsafe.Pointer(&st[0])))
 	must(rc)
 	for i, s := range st {
@@ -75,18 +79,22 @@ func DecompressG2Batch(in [][96]byte, checked bool) ([]G2Affine, []error) {
 
 // CompressG1Batch / CompressG2Batch: CompressG1 (g1.go:230-249) / CompressG2 (g2.go:268-289).
 func CompressG1Batch(p []G1Affine) [][48]byte {
+	c, leave := enter()
+	defer leave()
 	out := make([][48]byte, len(p))
 	if len(p) > 0 {
-		must(C.b381_g1_compress_batch(ctx(), (*C.b381_g1_affine)(unsafe.Pointer(&p[0])), C.size_t(len(p)),
+		must(C.b381_g1_compress_batch(c, (*C.b381_g1_affine)(unsafe.Pointer(&p[0])), C.size_t(len(p)),
 			(*C.uint8_t)(unsafe.Pointer(&out[0]))))
 	}
 	return out
 }
 
 func CompressG2Batch(p []G2Affine) [][96]byte {
+	c, leave := enter()
+	defer leave()
 	out := make([][96]byte, len(p))
 	if len(p) > 0 {
-		must(C.b381_g2_compress_batch(ctx(), (*C.b381_g2_affine)(unsafe.Pointer(&p[0])), C.size_t(len(p)),
+		must(C.b381_g2_compress_batch(c, (*C.b381_g2_affine)(unsafe.Pointer(&p[0])), C.size_t(len(p)),
 			(*C.uint8_t)(unsafe.Pointer(&out[0]))))
 	}
 	return out
@@ -104,6 +112,11 @@ func scalars(k []*FR) []FRRepr {
 // MulG1Batch: out[i] = p[i].MulFR(k[i]).ToAffine() (g1.go:80-90,322-340).  len(p) == 1 broadcasts the base
 // (PrivToPub, g1pubs/bls.go:144-146); len(k) == 1 broadcasts the scalar.
 func MulG1Batch(p []G1Affine, k []*FR) []G1Affine {
+	if len(p) == 0 || len(k) == 0 {
+		return []G1Affine{}
+	}
+	c, leave := enter()
+	defer leave()
 	n := len(p)
 	if len(k) > n {
 		n = len(k)
@@ -117,13 +130,18 @@ func MulG1Batch(p []G1Affine, k []*FR) []G1Affine {
 	if len(k) == 1 && n > 1 {
 		kst = 0
 	}
-	must(C.b381_g1_mul_batch(ctx(), (*C.b381_g1_affine)(unsafe.Pointer(&p[0])), ps,
+	must(C.b381_g1_mul_batch(c, (*C.b381_g1_affine)(unsafe.Pointer(&p[0])), ps,
 		(*C.b381_scalar)(unsafe.Pointer(&ks[0])), kst, C.size_t(n), (*C.b381_g1_affine)(unsafe.Pointer(&out[0]))))
 	return out
 }
 
 // MulG2Batch: out[i] = p[i].MulFR(k[i]).ToAffine() (g2.go:92-102,365-386): Sign of many hashed messages.
 func MulG2Batch(p []G2Affine, k []*FR) []G2Affine {
+	if len(p) == 0 || len(k) == 0 {
+		return []G2Affine{}
+	}
+	c, leave := enter()
+	defer leave()
 	n := len(p)
 	if len(k) > n {
 		n = len(k)
@@ -137,7 +155,7 @@ func MulG2Batch(p []G2Affine, k []*FR) []G2Affine {
 	if len(k) == 1 && n > 1 {
 		kst = 0
 	}
-	must(C.b381_g2_mul_batch(ctx(), (*C.b381_g2_affine)(unsafe.Pointer(&p[0])), ps,
+	must(C.b381_g2_mul_batch(c, (*C.b381_g2_affine)(unsafe.Pointer(&p[0])), ps,
 		(*C.b381_scalar)(unsafe.Pointer(&ks[0])), kst, C.size_t(n), (*C.b381_g2_affine)(unsafe.Pointer(&out[0]))))
 	return out
 }
@@ -162,29 +180,41 @@ func mulStrides(np, nk int) (n int, ps, ks C.size_t) {
 // the engine takes the endomorphism ladder (1.5x / 1.9x faster), same result.  PrivToPub (g2pubs keys live in G2,
 // g1pubs keys in G1) and Sign use these.
 func MulG1SubgroupBatch(p []G1Affine, k []*FR) []G1Affine {
+	if len(p) == 0 || len(k) == 0 {
+		return []G1Affine{}
+	}
+	c, leave := enter()
+	defer leave()
 	n, ps, kst := mulStrides(len(p), len(k))
 	out := make([]G1Affine, n)
 	ks := scalars(k)
-	must(C.b381_g1_mul_subgroup_batch(ctx(), (*C.b381_g1_affine)(unsafe.Pointer(&p[0])), ps,
+	must(C.b381_g1_mul_subgroup_batch(c, (*C.b381_g1_affine)(unsafe.Pointer(&p[0])), ps,
 		(*C.b381_scalar)(unsafe.Pointer(&ks[0])), kst, C.size_t(n), (*C.b381_g1_affine)(unsafe.Pointer(&out[0]))))
 	return out
 }
 
 // MulG2SubgroupBatch: see MulG1SubgroupBatch.
 func MulG2SubgroupBatch(p []G2Affine, k []*FR) []G2Affine {
+	if len(p) == 0 || len(k) == 0 {
+		return []G2Affine{}
+	}
+	c, leave := enter()
+	defer leave()
 	n, ps, kst := mulStrides(len(p), len(k))
 	out := make([]G2Affine, n)
 	ks := scalars(k)
-	must(C.b381_g2_mul_subgroup_batch(ctx(), (*C.b381_g2_affine)(unsafe.Pointer(&p[0])), ps,
+	must(C.b381_g2_mul_subgroup_batch(c, (*C.b381_g2_affine)(unsafe.Pointer(&p[0])), ps,
 		(*C.b381_scalar)(unsafe.Pointer(&ks[0])), kst, C.size_t(n), (*C.b381_g2_affine)(unsafe.Pointer(&out[0]))))
 	return out
 }
 
 // HashG2WithDomainBatch: out[i] = HashG2WithDomain(msgs[i], domain).ToAffine() (g2.go:1041-1085).
 func HashG2WithDomainBatch(msgs [][32]byte, domain [8]byte) []G2Affine {
+	c, leave := enter()
+	defer leave()
 	out := make([]G2Affine, len(msgs))
 	if len(msgs) > 0 {
-		must(C.b381_hash_g2_with_domain_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&msgs[0])),
+		must(C.b381_hash_g2_with_domain_batch(c, (*C.uint8_t)(unsafe.Pointer(&msgs[0])),
 			(*C.uint8_t)(unsafe.Pointer(&domain[0])), 0, C.size_t(len(msgs)), (*C.b381_g2_affine)(unsafe.Pointer(&out[0]))))
 	}
 	return out
@@ -194,13 +224,15 @@ func HashG2WithDomainBatch(msgs [][32]byte, domain [8]byte) []G2Affine {
 // g1pubs.VerifyWithDomain(msgs[i], DeserializePublicKey(pubs[i]), DeserializeSignature(sigs[i]), domain)
 // (g1pubs/bls.go:38-58,91-111,171-174), false when either deserialisation fails.
 func VerifyWithDomainWire(pubs [][48]byte, msgs [][32]byte, domain [8]byte, sigs [][96]byte) []bool {
+	c, leave := enter()
+	defer leave()
 	n := len(pubs)
 	ok8 := make([]uint8, n)
 	out := make([]bool, n)
 	if n == 0 {
 		return out
 	}
-	must(C.b381_verify_with_domain_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&pubs[0])), (*C.uint8_t)(unsafe.Pointer(&msgs[0])),
+	must(C.b381_verify_with_domain_batch(c, (*C.uint8_t)(unsafe.Pointer(&pubs[0])), (*C.uint8_t)(unsafe.Pointer(&msgs[0])),
 		(*C.uint8_t)(unsafe.Pointer(&domain[0])), 0, (*C.uint8_t)(unsafe.Pointer(&sigs[0])), C.size_t(n),
 		(*C.uint8_t)(unsafe.Pointer(&ok8[0]))))
 	for i, v := range ok8 {
@@ -226,20 +258,24 @@ func packMessages(msgs [][]byte) ([]byte, []uint64) {
 
 // HashG1Batch / HashG2Batch: HashG1 (hash.go:320-331) / HashG2 (hash.go:404-411) of every message.
 func HashG1Batch(msgs [][]byte) []G1Affine {
+	c, leave := enter()
+	defer leave()
 	out := make([]G1Affine, len(msgs))
 	if len(msgs) > 0 {
 		buf, off := packMessages(msgs)
-		must(C.b381_hash_g1_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&buf[0])), (*C.uint64_t)(unsafe.Pointer(&off[0])),
+		must(C.b381_hash_g1_batch(c, (*C.uint8_t)(unsafe.Pointer(&buf[0])), (*C.uint64_t)(unsafe.Pointer(&off[0])),
 			C.size_t(len(msgs)), (*C.b381_g1_affine)(unsafe.Pointer(&out[0]))))
 	}
 	return out
 }
 
 func HashG2Batch(msgs [][]byte) []G2Affine {
+	c, leave := enter()
+	defer leave()
 	out := make([]G2Affine, len(msgs))
 	if len(msgs) > 0 {
 		buf, off := packMessages(msgs)
-		must(C.b381_hash_g2_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&buf[0])), (*C.uint64_t)(unsafe.Pointer(&off[0])),
+		must(C.b381_hash_g2_batch(c, (*C.uint8_t)(unsafe.Pointer(&buf[0])), (*C.uint64_t)(unsafe.Pointer(&off[0])),
 			C.size_t(len(msgs)), (*C.b381_g2_affine)(unsafe.Pointer(&out[0]))))
 	}
 	return out
@@ -248,6 +284,8 @@ func HashG2Batch(msgs [][]byte) []G2Affine {
 // VerifyWire: g1pubs.Verify (g2pubs = false: 48-byte keys, 96-byte signatures, g1pubs/bls.go:165-168) or g2pubs.Verify
 // (g2pubs = true: 96-byte keys, 48-byte signatures, g2pubs/bls.go:159-162) for n wire-format triples on the device.
 func VerifyWire(g2pubs bool, pubs []byte, msgs [][]byte, sigs []byte) []bool {
+	c, leave := enter()
+	defer leave()
 	n := len(msgs)
 	ok8 := make([]uint8, n)
 	out := make([]bool, n)
@@ -256,10 +294,10 @@ func VerifyWire(g2pubs bool, pubs []byte, msgs [][]byte, sigs []byte) []bool {
 	}
 	buf, off := packMessages(msgs)
 	if g2pubs {
-		must(C.b381_g2pubs_verify_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&pubs[0])), (*C.uint8_t)(unsafe.Pointer(&buf[0])),
+		must(C.b381_g2pubs_verify_batch(c, (*C.uint8_t)(unsafe.Pointer(&pubs[0])), (*C.uint8_t)(unsafe.Pointer(&buf[0])),
 			(*C.uint64_t)(unsafe.Pointer(&off[0])), (*C.uint8_t)(unsafe.Pointer(&sigs[0])), C.size_t(n), (*C.uint8_t)(unsafe.Pointer(&ok8[0]))))
 	} else {
-		must(C.b381_g1pubs_verify_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&pubs[0])), (*C.uint8_t)(unsafe.Pointer(&buf[0])),
+		must(C.b381_g1pubs_verify_batch(c, (*C.uint8_t)(unsafe.Pointer(&pubs[0])), (*C.uint8_t)(unsafe.Pointer(&buf[0])),
 			(*C.uint64_t)(unsafe.Pointer(&off[0])), (*C.uint8_t)(unsafe.Pointer(&sigs[0])), C.size_t(n), (*C.uint8_t)(unsafe.Pointer(&ok8[0]))))
 	}
 	for i, v := range ok8 {
@@ -268,16 +306,27 @@ func VerifyWire(g2pubs bool, pubs []byte, msgs [][]byte, sigs []byte) []bool {
 	return out
 }
 
+// must is called with the engine locked (enter): the error text belongs to the call that just failed.
 func must(rc C.int) {
 	if rc != C.B381_OK {
-		panic(C.GoString(C.b381_last_error(ctx())))
+		panic(C.GoString(C.b381_last_error(engine.ctx)))
 	}
+}
+
+// enter locks the engine for one cgo call and returns the context with the unlock function.  A b381_ctx serves one OS
+// thread at a time (include/b381.h): every entry point shares its stream and its grow-only device scratch, so concurrent
+// goroutines -- the normal case for a Go verifier -- are serialised here, exactly as the functions of pairing_b200.go do.
+func enter() (*C.b381_ctx, func()) {
+	engine.mu.Lock()
+	return ctx(), engine.mu.Unlock
 }
 
 // VerifyWithDomainRLC checks n wire-format triples with ONE final exponentiation (random linear combination):
 // true iff every VerifyWithDomain equation holds, up to a false-accept probability of 2^-64.  The weights must be
 // drawn after the signatures are fixed, from a cryptographic source.
 func VerifyWithDomainRLC(pubs [][48]byte, msgs [][32]byte, domain [8]byte, sigs [][96]byte, rnd io.Reader) bool {
+	c, leave := enter()
+	defer leave()
 	n := len(pubs)
 	if n == 0 {
 		return true
@@ -291,7 +340,8 @@ func VerifyWithDomainRLC(pubs [][48]byte, msgs [][32]byte, domain [8]byte, sigs 
 		w[i][0] = binary.LittleEndian.Uint64(b[:]) | 1
 	}
 	var ok C.uint8_t
-	must(C.b381_verify_with_domain_rlc_batch(ctx(), (*C.uint8_t)(unsafe.Pointer(&pubs[0])), (*C.uint8_t)(unsafe.Pointer(&msgs[0])),
+	must(C.b381_set_rlc_weight_bits(c, 64))
+	must(C.b381_verify_with_domain_rlc_batch(c, (*C.uint8_t)(unsafe.Pointer(&pubs[0])), (*C.uint8_t)(unsafe.Pointer(&msgs[0])),
 		(*C.uint8_t)(unsafe.Pointer(&domain[0])), 0, (*C.uint8_t)(unsafe.Pointer(&sigs[0])),
 		(*C.b381_scalar)(unsafe.Pointer(&w[0])), C.size_t(n), &ok))
 	return ok != 0

@@ -60,21 +60,107 @@ func packFQ12(f *FQ12) (out C.b381_fp12) {
 	return
 }
 
-// MillerLoop replaces pairing.go:16-75.  The reference takes prepared G2 points; the engine fuses
-// G2AffineToPrepared (g2.go:650-801) into the loop, so items carry the affine Q (see MillerLoopItemB200).
-func MillerLoopAffine(ps []G1Affine, qs []G2Affine) *FQ12 {
-	n := len(ps)
+// MillerLoopItem is pairing.go:4-7 (the file this one replaces under -tags b200): a G1 point and a prepared G2 point.
+// G2Prepared and G2AffineToPrepared stay the reference's (g2.go:639-801, not replaced); G2AffineToPreparedBatch below
+// prepares many points in one launch.
+type MillerLoopItem struct {
+	P *G1Affine
+	Q *G2Prepared
+}
+
+// packPrepared copies a G2Prepared (coeffs [][3]FQ2, 68 entries, g2.go:639-642) into the engine's flat form.  An infinite
+// point has no coefficients in the reference; the engine reads none of them.
+func packPrepared(dst *C.b381_g2_prepared, q *G2Prepared) {
+	if q.infinity {
+		dst.infinity = 1
+		return
+	}
+	if len(q.coeffs) != 68 {
+		panic("bls/b200: G2Prepared with an unexpected number of coefficient triples")
+	}
+	v := (*[68][3]FQ2)(unsafe.Pointer(&dst.coeffs[0]))
+	copy(v[:], q.coeffs)
+}
+
+// MillerLoop replaces pairing.go:16-75: the product over the items of f_{|x|,Q}(P), conjugated.  Each item's Miller value
+// is computed from the prepared coefficients on the device (b381_miller_loop_prepared_batch); the reference's shared
+// accumulator (pairing.go:40-69) computes exactly the product of the per-item values, formed here with FQ12.MulAssign.
+// An item with P or Q at infinity contributes the factor 1 (the reference panics there, indexing an empty slice).
+func MillerLoop(items []MillerLoopItem) *FQ12 {
+	f := FQ12One.Copy()
+	n := len(items)
+	if n == 0 {
+		return f
+	}
+	ps := make([]G1Affine, n)
+	prep := make([]C.b381_g2_prepared, n)
+	for i, it := range items {
+		ps[i] = *it.P
+		packPrepared(&prep[i], it.Q)
+	}
 	ml := make([]C.b381_fp12, n)
 	engine.mu.Lock()
-	defer engine.mu.Unlock()
+	rc := C.b381_miller_loop_prepared_batch(ctx(), (*C.b381_g1_affine)(unsafe.Pointer(&ps[0])), &prep[0], C.size_t(n), nil,
+		C.size_t(n), &ml[0])
+	engine.mu.Unlock()
+	if rc != C.B381_OK {
+		panic(C.GoString(C.b381_last_error(ctx())))
+	}
+	runtime.KeepAlive(ps)
+	for i := range ml {
+		f.MulAssign(flatFQ12(&ml[i]))
+	}
+	return f
+}
+
+// G2AffineToPreparedBatch is G2AffineToPrepared (g2.go:650-801) for many points in one launch.
+func G2AffineToPreparedBatch(qs []G2Affine) []*G2Prepared {
+	n := len(qs)
+	out := make([]*G2Prepared, n)
+	if n == 0 {
+		return out
+	}
+	prep := make([]C.b381_g2_prepared, n)
+	engine.mu.Lock()
+	rc := C.b381_g2_prepare_batch(ctx(), (*C.b381_g2_affine)(unsafe.Pointer(&qs[0])), C.size_t(n), &prep[0])
+	engine.mu.Unlock()
+	if rc != C.B381_OK {
+		panic(C.GoString(C.b381_last_error(ctx())))
+	}
+	for i := range prep {
+		if prep[i].infinity != 0 {
+			out[i] = &G2Prepared{infinity: true}
+			continue
+		}
+		v := (*[68][3]FQ2)(unsafe.Pointer(&prep[i].coeffs[0]))
+		c := make([][3]FQ2, 68)
+		copy(c, v[:])
+		out[i] = &G2Prepared{coeffs: c}
+	}
+	return out
+}
+
+// MillerLoopAffine is the batched form on unprepared points: the engine fuses G2AffineToPrepared into the loop
+// (no 19.6 KB coefficient table per point); the product of the Miller values is returned.
+func MillerLoopAffine(ps []G1Affine, qs []G2Affine) *FQ12 {
+	f := FQ12One.Copy()
+	n := len(ps)
+	if n == 0 {
+		return f
+	}
+	if len(qs) != n {
+		panic("bls/b200: MillerLoopAffine needs as many G2 points as G1 points")
+	}
+	ml := make([]C.b381_fp12, n)
+	engine.mu.Lock()
 	rc := C.b381_miller_loop_batch(ctx(), (*C.b381_g1_affine)(unsafe.Pointer(&ps[0])),
 		(*C.b381_g2_affine)(unsafe.Pointer(&qs[0])), C.size_t(n), &ml[0])
+	engine.mu.Unlock()
 	if rc != C.B381_OK {
 		panic(C.GoString(C.b381_last_error(ctx())))
 	}
 	runtime.KeepAlive(ps)
 	runtime.KeepAlive(qs)
-	f := FQ12One.Copy()
 	for i := range ml {
 		f.MulAssign(flatFQ12(&ml[i])) // shared accumulator of pairing.go:40-69
 	}
@@ -105,6 +191,9 @@ func Pairing(p *G1Projective, q *G2Projective) *FQ12 {
 // PairingBatch is the batched form the reference lacks: out[i] = Pairing(ps[i], qs[i]).
 func PairingBatch(ps []*G1Affine, qs []*G2Affine) []*FQ12 {
 	n := len(ps)
+	if n == 0 {
+		return []*FQ12{}
+	}
 	p := make([]G1Affine, n)
 	q := make([]G2Affine, n)
 	for i := range ps {
@@ -126,7 +215,12 @@ func PairingBatch(ps []*G1Affine, qs []*G2Affine) []*FQ12 {
 }
 
 // CompareTwoPairings replaces pairing.go:140-147: e(P1,Q1) == e(P2,Q2) as one 2-pair group.
+// A point at infinity on either side makes the comparison false: the engine's Miller loop treats such a pair as the factor 1
+// (the reference panics there, pairing.go:17-26), and Verify(m, infinity, infinity) must not hold for every m.
 func CompareTwoPairings(P1 *G1Projective, Q1 *G2Projective, P2 *G1Projective, Q2 *G2Projective) bool {
+	if P1.IsZero() || Q1.IsZero() || P2.IsZero() || Q2.IsZero() {
+		return false
+	}
 	negP2 := P2.ToAffine()
 	negP2.NegAssign()
 	return PairingProductsAreOne(
@@ -139,6 +233,16 @@ func CompareTwoPairings(P1 *G1Projective, Q1 *G2Projective, P2 *G1Projective, Q2
 // over i in [off[g], off[g+1]).  One launch verifies any number of signatures.
 func PairingProductsAreOne(p []G1Affine, q []G2Affine, off []uint32) []bool {
 	ng := len(off) - 1
+	if ng <= 0 {
+		return []bool{}
+	}
+	if len(p) == 0 { // every group is empty: the empty product is 1
+		res := make([]bool, ng)
+		for i := range res {
+			res[i] = true
+		}
+		return res
+	}
 	ok := make([]C.uint8_t, ng)
 	engine.mu.Lock()
 	defer engine.mu.Unlock()
@@ -190,6 +294,12 @@ func SumG2(qs []G2Affine) *G2Projective {
 // the reference would compute as a fold of G1Affine.MulFR (g1.go:80-90).
 func MSMG1(ps []G1Affine, ks []FRRepr) *G1Projective {
 	var out G1Projective
+	if len(ps) == 0 {
+		return G1ProjectiveZero.Copy()
+	}
+	if len(ks) != len(ps) {
+		panic("bls/b200: MSMG1 needs one scalar per point")
+	}
 	engine.mu.Lock()
 	defer engine.mu.Unlock()
 	rc := C.b381_g1_msm(ctx(), (*C.b381_g1_affine)(unsafe.Pointer(&ps[0])),

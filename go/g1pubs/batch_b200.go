@@ -1,18 +1,20 @@
 // +build b200
 
-// batch_b200.go -- additions to package g1pubs (pubkeys in G1, signatures in G2).  The exported
-// API of g1pubs/bls.go is unchanged: Verify / VerifyWithDomain / VerifyAggregateCommon* keep calling
-// bls.CompareTwoPairings, which `-tags b200` routes to the GPU engine (go/bls/pairing_b200.go).
-// Two replacements and two batch entry points live here.
+// batch_b200.go -- package g1pubs (pubkeys in G1, signatures in G2) under `-tags b200`.  The exported API of
+// g1pubs/bls.go is unchanged: Verify / VerifyWithDomain / VerifyAggregateCommon* keep calling bls.CompareTwoPairings,
+// which the tag routes to the GPU engine (go/bls/pairing_b200.go).  Three functions of bls.go are REPLACED here under the
+// tag -- AggregatePublicKeys, AggregateSignatures, (*Signature).VerifyAggregate: the maintainer moves those three, unchanged,
+// from bls.go into a file `aggregate_ref.go` that starts with `// +build !b200` (INTEGRATION.md section 2) -- and the batch
+// entry points the reference lacks are added.
 package g1pubs
 
 import (
 	"github.com/phoreproject/bls"
 )
 
-// AggregatePublicKeys replaces g1pubs/bls.go:192-198 (serial fold of G1Projective.Add) with one
-// device reduction.  Put `// +build !b200` on the original or rename it.
-func AggregatePublicKeysB200(p []*PublicKey) *PublicKey {
+// AggregatePublicKeys replaces g1pubs/bls.go:192-198 (serial fold of G1Projective.Add) with one device reduction; the
+// result is normalised and Equal()s the fold.
+func AggregatePublicKeys(p []*PublicKey) *PublicKey {
 	aff := make([]bls.G1Affine, len(p))
 	for i, pk := range p {
 		aff[i] = *pk.p.ToAffine()
@@ -20,8 +22,8 @@ func AggregatePublicKeysB200(p []*PublicKey) *PublicKey {
 	return &PublicKey{p: bls.SumG1(aff)}
 }
 
-// AggregateSignaturesB200 replaces g1pubs/bls.go:177-183.
-func AggregateSignaturesB200(s []*Signature) *Signature {
+// AggregateSignatures replaces g1pubs/bls.go:177-183.
+func AggregateSignatures(s []*Signature) *Signature {
 	aff := make([]bls.G2Affine, len(s))
 	for i, sig := range s {
 		aff[i] = *sig.s.ToAffine()
@@ -33,9 +35,18 @@ func AggregateSignaturesB200(s []*Signature) *Signature {
 // empty message is rejected), but ONE product of n+1 Miller loops and one final exponentiation
 // instead of n+1 full pairings.  e(G1, sig) == prod e(pk_i, H(m_i))  <=>
 // FE(ML(-G1, sig) * prod ML(pk_i, H(m_i))) == 1.
-func (s *Signature) VerifyAggregateB200(pubKeys []*PublicKey, msgs [][]byte) bool {
+// An infinite signature or key makes the check false (the reference panics in MillerLoop, pairing.go:17-26).
+func (s *Signature) VerifyAggregate(pubKeys []*PublicKey, msgs [][]byte) bool {
 	if len(pubKeys) != len(msgs) {
 		return false
+	}
+	if s.s.IsZero() {
+		return false
+	}
+	for _, pk := range pubKeys {
+		if pk.p.IsZero() {
+			return false
+		}
 	}
 	if hasDuplicates(msgs) { // the sort + dedupe of bls.go:257-273, unchanged
 		return false
@@ -56,20 +67,31 @@ func (s *Signature) VerifyAggregateB200(pubKeys []*PublicKey, msgs [][]byte) boo
 // VerifyBatchCommonWithDomain verifies many (aggregate signature, committee, message) triples in one
 // launch: the Ethereum-beacon shape of BASELINE config 5.  ok[i] ==
 // sigs[i].VerifyAggregateCommonWithDomain(committees[i], msgs[i], domain)  (g1pubs/bls.go:294-297).
+// An empty committee, keys that cancel to infinity or an infinite signature give false.
 func VerifyBatchCommonWithDomain(sigs []*Signature, committees [][]*PublicKey, msgs [][32]byte, domain [8]byte) []bool {
 	n := len(sigs)
+	if n == 0 {
+		return []bool{}
+	}
+	valid := make([]bool, n)
 	p := make([]bls.G1Affine, 0, 2*n)
 	q := make([]bls.G2Affine, 0, 2*n)
 	off := make([]uint32, 1, n+1)
 	hs := bls.HashG2WithDomainBatch(msgs, domain) // one launch for all message points
 	for i := range sigs {
-		agg := AggregatePublicKeysB200(committees[i]).p.ToAffine()
+		aggp := AggregatePublicKeys(committees[i]).p
+		valid[i] = len(committees[i]) > 0 && !aggp.IsZero() && !sigs[i].s.IsZero()
+		agg := aggp.ToAffine()
 		agg.NegAssign()
 		p = append(p, *bls.G1AffineOne, *agg)
 		q = append(q, *sigs[i].s.ToAffine(), hs[i])
 		off = append(off, uint32(len(p)))
 	}
-	return bls.PairingProductsAreOne(p, q, off)
+	ok := bls.PairingProductsAreOne(p, q, off)
+	for i := range ok {
+		ok[i] = ok[i] && valid[i]
+	}
+	return ok
 }
 
 // VerifyWithDomainBatch verifies n independent wire-format (public key, message hash, signature) triples with one

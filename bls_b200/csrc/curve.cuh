@@ -70,8 +70,53 @@ template <class F> HD void xyzz_set_inf(xyzz<F> &p) {
 }
 template <class F> HD bool xyzz_is_inf(const xyzz<F> &p) { return F::is_zero(p.zz); }
 
-// p = 2 * (x, y) for a finite affine point (mdbl-2008-s-1, a = 0)
+// EXPERIMENT, off by default (-DB381_GROUP_LAW_OOL): the group law out of line for the policies whose multiplications are calls
+// already (FpOut, Fp2Out: codec, hashing, scalar multiplication, G2 sum / MSM).  Inlined at every use those kernels carry
+// 0.1-0.6 MB of SASS and stall on instruction fetch (profiles/r01_v6_ncu_summary_hash.md).  Measured in round 2
+// (profiles/r02_experiments.md): doubling / mixed addition out of line are correct and gain 1-2 % (HashG2WithDomain 27.5 ->
+// 26.9 ms); the full addition out of line still gives WRONG G2 MSM results on the device (host build of the same source
+// correct; cicc infers the address space of the callee's first pointer from its callers) -- so the inlined form ships.
+#ifndef B381_OOL_DBLA
+#define B381_OOL_DBLA 1
+#endif
+#ifndef B381_OOL_DBL
+#define B381_OOL_DBL 1
+#endif
+#ifndef B381_OOL_MADD
+#define B381_OOL_MADD 1
+#endif
+#ifndef B381_OOL_ADD
+#define B381_OOL_ADD 0
+#endif
+template <class F> struct group_law_ool { static const bool value = false; };
+struct FpOut; struct Fp2Out;
+#if defined(B381_GROUP_LAW_OOL)
+template <> struct group_law_ool<FpOut> { static const bool value = true; };
+template <> struct group_law_ool<Fp2Out> { static const bool value = true; };
+#endif
+template <class F> HD void xyzz_dbl_affine_body(xyzz<F> &p, const typename F::T &x, const typename F::T &y);
+template <class F> HD void xyzz_dbl_body(xyzz<F> &p);
+template <class F> HD void xyzz_madd_body(xyzz<F> &p, const typename F::T &x2, const typename F::T &y2);
+template <class F> HD void xyzz_add_body(xyzz<F> &p, const xyzz<F> &q);
+template <class F> HDN void xyzz_dbl_affine_ool(xyzz<F> *p, const typename F::T *x, const typename F::T *y) { xyzz_dbl_affine_body<F>(*p, *x, *y); }
+template <class F> HDN void xyzz_dbl_ool(xyzz<F> *p) { xyzz_dbl_body<F>(*p); }
+template <class F> HDN void xyzz_madd_ool(xyzz<F> *p, const typename F::T *x2, const typename F::T *y2) { xyzz_madd_body<F>(*p, *x2, *y2); }
+template <class F> HDN void xyzz_add_ool(xyzz<F> *p, const xyzz<F> *q) { xyzz_add_body<F>(*p, *q); }
 template <class F> HD void xyzz_dbl_affine(xyzz<F> &p, const typename F::T &x, const typename F::T &y) {
+    if constexpr (group_law_ool<F>::value && B381_OOL_DBLA) xyzz_dbl_affine_ool<F>(&p, &x, &y); else xyzz_dbl_affine_body<F>(p, x, y);
+}
+template <class F> HD void xyzz_dbl(xyzz<F> &p) {
+    if constexpr (group_law_ool<F>::value && B381_OOL_DBL) xyzz_dbl_ool<F>(&p); else xyzz_dbl_body<F>(p);
+}
+template <class F> HD void xyzz_madd(xyzz<F> &p, const typename F::T &x2, const typename F::T &y2) {
+    if constexpr (group_law_ool<F>::value && B381_OOL_MADD) xyzz_madd_ool<F>(&p, &x2, &y2); else xyzz_madd_body<F>(p, x2, y2);
+}
+template <class F> HD void xyzz_add(xyzz<F> &p, const xyzz<F> &q) {
+    if constexpr (group_law_ool<F>::value && B381_OOL_ADD) xyzz_add_ool<F>(&p, &q); else xyzz_add_body<F>(p, q);
+}
+
+// p = 2 * (x, y) for a finite affine point (mdbl-2008-s-1, a = 0)
+template <class F> HD void xyzz_dbl_affine_body(xyzz<F> &p, const typename F::T &x, const typename F::T &y) {
     typename F::T u, v, w, s, m, t;
     F::dbl(u, y);
     if (F::is_zero(u)) { xyzz_set_inf(p); return; }   // 2-torsion: not on these curves, kept for totality
@@ -89,7 +134,7 @@ template <class F> HD void xyzz_dbl_affine(xyzz<F> &p, const typename F::T &x, c
     p.zz = v; p.zzz = w;
 }
 // p = 2p (dbl-2008-s-1, a = 0); same case split as G1Projective.Double (g1.go:343-397)
-template <class F> HD void xyzz_dbl(xyzz<F> &p) {
+template <class F> HD void xyzz_dbl_body(xyzz<F> &p) {
     if (xyzz_is_inf(p)) return;
     typename F::T u, v, w, s, m, t;
     F::dbl(u, p.y);
@@ -108,7 +153,7 @@ template <class F> HD void xyzz_dbl(xyzz<F> &p) {
     F::mul(p.zzz, w, p.zzz);
 }
 // p += (x2, y2), a finite affine point (madd-2008-s); case split of G1Projective.AddAffine (g1.go:485-559)
-template <class F> HD void xyzz_madd(xyzz<F> &p, const typename F::T &x2, const typename F::T &y2) {
+template <class F> HD void xyzz_madd_body(xyzz<F> &p, const typename F::T &x2, const typename F::T &y2) {
     if (xyzz_is_inf(p)) { p.x = x2; p.y = y2; F::set_one(p.zz); F::set_one(p.zzz); return; }
     typename F::T u2, s2, pp, ppp, q, t;
     F::mul(u2, x2, p.zz);
@@ -135,7 +180,7 @@ template <class F> HD void xyzz_madd(xyzz<F> &p, const typename F::T &x2, const 
     F::mul(p.zzz, p.zzz, ppp);
 }
 // p += q (add-2008-s); case split of G1Projective.Add (g1.go:400-482)
-template <class F> HD void xyzz_add(xyzz<F> &p, const xyzz<F> &q) {
+template <class F> HD void xyzz_add_body(xyzz<F> &p, const xyzz<F> &q) {
     if (xyzz_is_inf(q)) return;
     if (xyzz_is_inf(p)) { p = q; return; }
     typename F::T u1, u2, s1, s2, pp, ppp, qq, t;

@@ -27,6 +27,7 @@ namespace duo {
 
 using quad::qfp;
 using quad::q6;
+using quad::qa;
 typedef qfp d2;                            // an Fq2 value: this lane's coefficient
 struct d12 { q6 c0, c1; };                 // Fq12 = c0 + c1 w, six Fq per lane
 struct dg2 { d2 x, y, z; };                // the running point of the Miller loop (Jacobian)
@@ -95,9 +96,9 @@ HD void d_both(dflag &r, const dflag &p) {
 }
 
 // ---- Fq6 (fq6.go): q6_mul, q6_mul_by_01, q6_inv, q6_mul_v of quad.cuh are lane-pair code already -------------------------
-HD void d6_add(q6 *r, const q6 *a, const q6 *b) { dv_addsub(&r->c0, &a->c0, &b->c0, 3, 0); }
-HD void d6_sub(q6 *r, const q6 *a, const q6 *b) { dv_addsub(&r->c0, &a->c0, &b->c0, 3, 1); }
-HD void d6_neg(q6 *r, const q6 *a) { quad::qv_neg(&r->c0, &a->c0, 3, 0); }
+HD void d6_add(q6 *r, const q6 *a, const q6 *b) { dv_addsub(qa(r), qa(a), qa(b), 3, 0); }
+HD void d6_sub(q6 *r, const q6 *a, const q6 *b) { dv_addsub(qa(r), qa(a), qa(b), 3, 1); }
+HD void d6_neg(q6 *r, const q6 *a) { quad::qv_neg(qa(r), qa(a), 3, 0); }
 // r = a * b   (fq6.go:255-292; fp6_mul of tower.cuh: outputs double as temporaries)
 HDN void d6_mul(q6 *r, const q6 *a, const q6 *b) {
     d2 v0, v1, v2, s, t, x, y;
@@ -160,7 +161,7 @@ HDN void d6_mul_by_1(q6 *r, const q6 *a, const d2 *b1) {
 HDN void d6_frobenius(q6 *r, const q6 *a, int power) {
     q6 t = *a;
     d2 k;
-    if (power & 1) quad::qv_neg(&t.c0, &t.c0, 3, 1);
+    if (power & 1) quad::qv_neg(qa(&t), qa(&t), 3, 1);
     quad::q2_load_tab(k, B381_TAB(frob6_c1) + power * 24);
     d2_mul(&t.c1, &t.c1, &k);
     quad::q2_load_tab(k, B381_TAB(frob6_c2) + power * 24);
@@ -172,13 +173,13 @@ HD void d6_add_vmul(q6 *r, const q6 *a, const q6 *b) {
     d2 x;
     d2_mul_nr(x, b->c2);
     d2_add(r->c0, a->c0, x);
-    dv_addsub(&r->c1, &a->c1, &b->c0, 2, 0);
+    dv_addsub(qa(r, 1), qa(a, 1), qa(b, 0), 2, 0);
 }
 HD void d6_sub_vmul(q6 *r, const q6 *a, const q6 *b) {
     d2 x;
     d2_mul_nr(x, b->c2);
     d2_sub(r->c0, a->c0, x);
-    dv_addsub(&r->c1, &a->c1, &b->c0, 2, 1);
+    dv_addsub(qa(r, 1), qa(a, 1), qa(b, 0), 2, 1);
 }
 
 // ---- Fq12 (fq12.go) ------------------------------------------------------------------------------------------------
@@ -230,7 +231,7 @@ HDN void d12_mul_by_014(d12 *f, const d2 *d0, const d2 *d1, const d2 *d4) {
 // per lane: the own pair's Fq12 value is zero / one
 HD void d12_is_zero(dflag &r, const d12 *a) {
     dflag p;
-    const d2 *c = &a->c0.c0;
+    const d2 *c = qa(a);
     QFOR { bool z = true; for (int i = 0; i < 6; i++) z = z && fp_is_zero(c[i].v[l_]); p.on[l_] = z; }
     d_both(r, p);
 }
@@ -238,7 +239,7 @@ HD void d12_is_one(dflag &r, const d12 *a) {
     dflag p;
     d2 one;
     d2_set_one(one);
-    const d2 *c = &a->c0.c0;
+    const d2 *c = qa(a);
     QFOR { bool z = fp_eq(c[0].v[l_], one.v[l_]); for (int i = 1; i < 6; i++) z = z && fp_is_zero(c[i].v[l_]); p.on[l_] = z; }
     d_both(r, p);
 }
@@ -296,11 +297,11 @@ HDN void d12_cyc_sqr(d12 *r, const d12 *a) {
 
 // ---- global memory <-> lanes ---------------------------------------------------------------------------------------
 HD void d12_load(d12 *F, const uint64_t *src) {
-    d2 *c = &F->c0.c0;
+    d2 *c = qa(F);
     for (int i = 0; i < 6; i++) quad::q_load(c[i], src, 2 * i, 1, 0);
 }
 HD void d12_store(uint64_t *dst, const d12 *F) {
-    const d2 *c = &F->c0.c0;
+    const d2 *c = qa(F);
     for (int i = 0; i < 6; i++) quad::q_store(dst, c[i], 2 * i, 1, 0);
 }
 
@@ -396,7 +397,7 @@ HD void dpair_load(dpair *S, const g1_affine_pod *P, const g2_affine_pod *Q) {
     QFOR S->live.on[l_] = !(P->inf || Q->inf);
 }
 HD void d12_keep_if(d12 *F, const d12 *G, const dflag &keep) {       // F <- keep ? F : G
-    d2 *f = &F->c0.c0; const d2 *g = &G->c0.c0;
+    d2 *f = qa(F); const d2 *g = qa(G);
     QFOR { if (!keep.on[l_]) for (int i = 0; i < 6; i++) f[i].v[l_] = g[i].v[l_]; }
 }
 // Miller loop of NP pairs sharing the accumulator, conjugated; a pair with P or Q at infinity contributes the factor 1

@@ -421,12 +421,12 @@ HD bool final_exp_one(fp12 *out, const fp12 *in) {
 }
 
 HD void fp12_store_u64(uint64_t *dst, const fp12 *a) {
-    const fp *p = &a->c0.c0.c0;
+    const fp *p = fp_array(a);
 #pragma unroll 1
     for (int i = 0; i < 12; i++) { fp x = p[i]; fp_store_u64(dst + 6 * i, x); }
 }
 HD void fp12_load_u64(fp12 *a, const uint64_t *src) {
-    fp *p = &a->c0.c0.c0;
+    fp *p = fp_array(a);
 #pragma unroll 1
     for (int i = 0; i < 12; i++) { fp x; fp_load_u64(x, src + 6 * i); p[i] = x; }
 }

@@ -46,6 +46,11 @@ namespace quad {
 
 struct qfp { fp v[QL]; };                 // one Fq per lane
 struct q6 { qfp c0, c1, c2; };            // an Fq6 value (coefficient j of each Fq2 coefficient), or half of an Fq12
+// Coefficient k of a q6 (or the first of a run of coefficients) as a pointer into the WHOLE object.  `qa(&x, 0)` followed by
+// indexing past that member is undefined behaviour which cicc 12.9 exploits (a callee given `qa(&x, 0)` is assumed to touch that
+// member only; tower.cuh:fp_array, profiles/r02_experiments.md); every multi-coefficient call below goes through this.
+template <class T> HD qfp *qa(T *x, int k = 0) { return reinterpret_cast<qfp *>(x) + k; }
+template <class T> HD const qfp *qa(const T *x, int k = 0) { return reinterpret_cast<const qfp *>(x) + k; }
 
 // ---- lane exchange ---------------------------------------------------------------------------------------------
 HD void q_shfl(qfp &r, const qfp &a, int mask) {
@@ -234,28 +239,28 @@ HD void q2_is_zero(bool z[QL], const qfp &a) {
 // r = a * b   (fq6.go:255-292; six Fq2 products)
 HDN void q6_mul(q6 *r, const q6 *a, const q6 *b) {
     qfp v0, v1, v2, s, t, x, y, z;
-    q2_mul(&v0, &a->c0, &b->c0);
-    q2_mul(&v1, &a->c1, &b->c1);
-    q2_mul(&v2, &a->c2, &b->c2);
+    q2_mul(&v0, qa(a, 0), qa(b, 0));
+    q2_mul(&v1, qa(a, 1), qa(b, 1));
+    q2_mul(&v2, qa(a, 2), qa(b, 2));
     // c0 = v0 + xi ((a1 + a2)(b1 + b2) - v1 - v2)
-    qv_add(&s, &a->c1, &a->c2, 1);
-    qv_add(&t, &b->c1, &b->c2, 1);
+    qv_add(&s, qa(a, 1), qa(a, 2), 1);
+    qv_add(&t, qa(b, 1), qa(b, 2), 1);
     q2_mul(&x, &s, &t);
     qv_sub(&x, &x, &v1, 1);
     qv_sub(&x, &x, &v2, 1);
     q2_mul_nr(&x, &x);
     qv_add(&x, &x, &v0, 1);
     // c1 = (a0 + a1)(b0 + b1) - v0 - v1 + xi v2
-    qv_add(&s, &a->c0, &a->c1, 1);
-    qv_add(&t, &b->c0, &b->c1, 1);
+    qv_add(&s, qa(a, 0), qa(a, 1), 1);
+    qv_add(&t, qa(b, 0), qa(b, 1), 1);
     q2_mul(&y, &s, &t);
     qv_sub(&y, &y, &v0, 1);
     qv_sub(&y, &y, &v1, 1);
     q2_mul_nr(&s, &v2);
     qv_add(&y, &y, &s, 1);
     // c2 = (a0 + a2)(b0 + b2) - v0 - v2 + v1
-    qv_add(&s, &a->c0, &a->c2, 1);
-    qv_add(&t, &b->c0, &b->c2, 1);
+    qv_add(&s, qa(a, 0), qa(a, 2), 1);
+    qv_add(&t, qa(b, 0), qa(b, 2), 1);
     q2_mul(&z, &s, &t);
     qv_sub(&z, &z, &v0, 1);
     qv_sub(&z, &z, &v2, 1);
@@ -265,19 +270,19 @@ HDN void q6_mul(q6 *r, const q6 *a, const q6 *b) {
 // r = a * (b0 + b1 v)   (fq6.go:60-90; five Fq2 products)
 HDN void q6_mul_by_01(q6 *r, const q6 *a, const qfp *b0, const qfp *b1) {
     qfp v0, v1, s, t, x, y, z;
-    q2_mul(&v0, &a->c0, b0);
-    q2_mul(&v1, &a->c1, b1);
-    qv_add(&s, &a->c1, &a->c2, 1);
+    q2_mul(&v0, qa(a, 0), b0);
+    q2_mul(&v1, qa(a, 1), b1);
+    qv_add(&s, qa(a, 1), qa(a, 2), 1);
     q2_mul(&x, &s, b1);
     qv_sub(&x, &x, &v1, 1);
     q2_mul_nr(&x, &x);
     qv_add(&x, &x, &v0, 1);
-    qv_add(&s, &a->c0, &a->c1, 1);
+    qv_add(&s, qa(a, 0), qa(a, 1), 1);
     qv_add(&t, b0, b1, 1);
     q2_mul(&y, &s, &t);
     qv_sub(&y, &y, &v0, 1);
     qv_sub(&y, &y, &v1, 1);
-    qv_add(&s, &a->c0, &a->c2, 1);
+    qv_add(&s, qa(a, 0), qa(a, 2), 1);
     q2_mul(&z, &s, b0);
     qv_sub(&z, &z, &v0, 1);
     qv_add(&z, &z, &v1, 1);
@@ -286,33 +291,33 @@ HDN void q6_mul_by_01(q6 *r, const q6 *a, const qfp *b0, const qfp *b1) {
 // r = a * v = (xi a2, a0, a1)   (fq6.go:34-37)
 HD void q6_mul_v(q6 *r, const q6 *a) {
     qfp t, c0 = a->c0, c1 = a->c1;
-    q2_mul_nr(&t, &a->c2);
+    q2_mul_nr(&t, qa(a, 2));
     r->c0 = t; r->c1 = c0; r->c2 = c1;
 }
 // r = a^-1, 0 -> 0   (fq6.go:295-336); run by both halves on the same value (one per final exponentiation)
 HDN void q6_inv(q6 *r, const q6 *a) {
     qfp k0, k1, k2, t, u;
-    q2_sqr(&k0, &a->c0);
-    q2_mul(&t, &a->c1, &a->c2);
+    q2_sqr(&k0, qa(a, 0));
+    q2_mul(&t, qa(a, 1), qa(a, 2));
     q2_mul_nr(&t, &t);
     qv_sub(&k0, &k0, &t, 1);
-    q2_sqr(&k1, &a->c2);
+    q2_sqr(&k1, qa(a, 2));
     q2_mul_nr(&k1, &k1);
-    q2_mul(&t, &a->c0, &a->c1);
+    q2_mul(&t, qa(a, 0), qa(a, 1));
     qv_sub(&k1, &k1, &t, 1);
-    q2_sqr(&k2, &a->c1);
-    q2_mul(&t, &a->c0, &a->c2);
+    q2_sqr(&k2, qa(a, 1));
+    q2_mul(&t, qa(a, 0), qa(a, 2));
     qv_sub(&k2, &k2, &t, 1);
-    q2_mul(&t, &a->c2, &k1);
-    q2_mul(&u, &a->c1, &k2);
+    q2_mul(&t, qa(a, 2), &k1);
+    q2_mul(&u, qa(a, 1), &k2);
     qv_add(&t, &t, &u, 1);
     q2_mul_nr(&t, &t);
-    q2_mul(&u, &a->c0, &k0);
+    q2_mul(&u, qa(a, 0), &k0);
     qv_add(&t, &t, &u, 1);
     q2_inv(&t, &t);
-    q2_mul(&r->c0, &k0, &t);
-    q2_mul(&r->c1, &k1, &t);
-    q2_mul(&r->c2, &k2, &t);
+    q2_mul(qa(r, 0), &k0, &t);
+    q2_mul(qa(r, 1), &k1, &t);
+    q2_mul(qa(r, 2), &k2, &t);
 }
 
 // ---- Fq12 split over the halves (fq12.go): F = the own half's Fq6 coefficient ----------------------------------------
@@ -320,43 +325,43 @@ HDN void q6_inv(q6 *r, const q6 *a) {
 HDN void q12_sqr(q6 *F) {
     q6 O, S, T, Pr;
     qfp x;
-    qv_xh(&O.c0, &F->c0, 3);
-    qv_add(&S.c0, &F->c0, &O.c0, 3);
+    qv_xh(qa(&O, 0), qa(F, 0), 3);
+    qv_add(qa(&S, 0), qa(F, 0), qa(&O, 0), 3);
     // on half 1 (F = c1, O = c0): c0 + v c1 = (O0 + xi F2, O1 + F0, O2 + F1)
-    q2_mul_nr(&x, &F->c2);
-    qv_add(&T.c0, &O.c0, &x, 1);
-    qv_add(&T.c1, &O.c1, &F->c0, 2);
-    qv_selh(&S.c0, &F->c0, &S.c0, 3);              // X = c0      | c0 + c1
-    qv_selh(&T.c0, &O.c0, &T.c0, 3);               // Y = c1      | c0 + v c1
+    q2_mul_nr(&x, qa(F, 2));
+    qv_add(qa(&T, 0), qa(&O, 0), &x, 1);
+    qv_add(qa(&T, 1), qa(&O, 1), qa(F, 0), 2);
+    qv_selh(qa(&S, 0), qa(F, 0), qa(&S, 0), 3);              // X = c0      | c0 + c1
+    qv_selh(qa(&T, 0), qa(&O, 0), qa(&T, 0), 3);               // Y = c1      | c0 + v c1
     q6_mul(&Pr, &S, &T);
-    qv_xh(&O.c0, &Pr.c0, 3);
-    qv_selh(&S.c0, &Pr.c0, &O.c0, 3);              // ab on all lanes
-    qv_selh(&T.c0, &O.c0, &Pr.c0, 3);              // (c0 + c1)(c0 + v c1) on all lanes
+    qv_xh(qa(&O, 0), qa(&Pr, 0), 3);
+    qv_selh(qa(&S, 0), qa(&Pr, 0), qa(&O, 0), 3);              // ab on all lanes
+    qv_selh(qa(&T, 0), qa(&O, 0), qa(&Pr, 0), 3);              // (c0 + c1)(c0 + v c1) on all lanes
     // c0' = T - ab - v ab   (half 0)        c1' = 2 ab   (half 1)
-    qv_sub(&T.c0, &T.c0, &S.c0, 3);
-    q2_mul_nr(&x, &S.c2);
-    qv_sub(&T.c0, &T.c0, &x, 1);
-    qv_sub(&T.c1, &T.c1, &S.c0, 2);
-    qv_dbl(&S.c0, &S.c0, 3);
-    qv_selh(&F->c0, &T.c0, &S.c0, 3);
+    qv_sub(qa(&T, 0), qa(&T, 0), qa(&S, 0), 3);
+    q2_mul_nr(&x, qa(&S, 2));
+    qv_sub(qa(&T, 0), qa(&T, 0), &x, 1);
+    qv_sub(qa(&T, 1), qa(&T, 1), qa(&S, 0), 2);
+    qv_dbl(qa(&S, 0), qa(&S, 0), 3);
+    qv_selh(qa(F, 0), qa(&T, 0), qa(&S, 0), 3);
 }
 // f <- f * ((d0 + d1 v) + (d4 v) w)   (fq12.go:32-47; 13 Fq2 products) and, in the free slot of the seventh round,
 // *eout = ea * eb (the y coordinate of the line step that produced d: its last product has no partner there)
 HDN void q12_mul_by_014(q6 *F, const qfp *d0, const qfp *d1, const qfp *d4, const qfp *ea, const qfp *eb, qfp *eout) {
     q6 O, X, Pr, U;
     qfp D1, ia, ib, own, b0, b1, b2;
-    qv_xh(&O.c0, &F->c0, 3);
-    qv_add(&X.c0, &F->c0, &O.c0, 3);
-    qv_selh(&X.c0, &F->c0, &X.c0, 3);              // c0 | c0 + c1
+    qv_xh(qa(&O, 0), qa(F, 0), 3);
+    qv_add(qa(&X, 0), qa(F, 0), qa(&O, 0), 3);
+    qv_selh(qa(&X, 0), qa(F, 0), qa(&X, 0), 3);              // c0 | c0 + c1
     qv_add(&D1, d1, d4, 1);
     qv_selh(&D1, d1, &D1, 1);                      // d1 | d1 + d4
     q6_mul_by_01(&Pr, &X, d0, &D1);                // aa = c0 (d0, d1) | (c0 + c1)(d0, d1 + d4)
     // bb = c1 * (d4 v) = (xi c1_2 d4, c1_0 d4, c1_1 d4): three products + the extra one
-    qv_selh(&X.c0, &O.c0, &F->c0, 3);              // c1 on all lanes
-    qv_selh(&ia, &X.c0, &X.c1, 1);
+    qv_selh(qa(&X, 0), qa(&O, 0), qa(F, 0), 3);              // c1 on all lanes
+    qv_selh(&ia, qa(&X, 0), qa(&X, 1), 1);
     q2_mul(&own, &ia, d4);
     q_bcast(&b0, &b1, &own);
-    qv_selh(&ia, &X.c2, ea, 1);
+    qv_selh(&ia, qa(&X, 2), ea, 1);
     qv_selh(&ib, d4, eb, 1);
     q2_mul(&own, &ia, &ib);
     q_bcast(&b2, eout, &own);
@@ -364,13 +369,13 @@ HDN void q12_mul_by_014(q6 *F, const qfp *d0, const qfp *d1, const qfp *d4, cons
     // c0' = aa + v bb = (aa0 + xi b1, aa1 + b2, aa2 + b0)   (half 0)
     // c1' = cc - aa - bb                                      (half 1)
     q2_mul_nr(&own, &b1);
-    qv_xh(&O.c0, &Pr.c0, 3);                       // half 1 receives aa
+    qv_xh(qa(&O, 0), qa(&Pr, 0), 3);                       // half 1 receives aa
     U.c0 = own; U.c1 = b2; U.c2 = b0;
     X.c0 = b2; X.c1 = b0; X.c2 = b1;
-    qv_selh(&U.c0, &U.c0, &X.c0, 3);
-    qv_sub(&O.c0, &Pr.c0, &O.c0, 3);               // cc - aa (meaningful on half 1)
-    qv_selh(&Pr.c0, &Pr.c0, &O.c0, 3);
-    qv_addsub(&F->c0, &Pr.c0, &U.c0, 3, 2);
+    qv_selh(qa(&U, 0), qa(&U, 0), qa(&X, 0), 3);
+    qv_sub(qa(&O, 0), qa(&Pr, 0), qa(&O, 0), 3);               // cc - aa (meaningful on half 1)
+    qv_selh(qa(&Pr, 0), qa(&Pr, 0), qa(&O, 0), 3);
+    qv_addsub(qa(F, 0), qa(&Pr, 0), qa(&U, 0), 3, 2);
 }
 // r = a * b   (fq12.go:198-213: aa = a0 b0 on half 0, bb = a1 b1 on half 1, and the six products of
 // (a0 + a1)(b0 + b1) split three and three: 9 rounds for 18 Fq2 products).  r may alias a or b.
@@ -378,43 +383,43 @@ HDN void q12_mul(q6 *r, const q6 *a, const q6 *b) {
     q6 Pr, SA, SB, O;
     qfp ia, ib, own, v0, v1, v2, m12, m01, m02, s;
     q6_mul(&Pr, a, b);
-    qv_xh(&O.c0, &a->c0, 3);
-    qv_add(&SA.c0, &a->c0, &O.c0, 3);
-    qv_xh(&O.c0, &b->c0, 3);
-    qv_add(&SB.c0, &b->c0, &O.c0, 3);
+    qv_xh(qa(&O, 0), qa(a, 0), 3);
+    qv_add(qa(&SA, 0), qa(a, 0), qa(&O, 0), 3);
+    qv_xh(qa(&O, 0), qa(b, 0), 3);
+    qv_add(qa(&SB, 0), qa(b, 0), qa(&O, 0), 3);
     // round 7: v0 = SA0 SB0 | (SA1 + SA2)(SB1 + SB2)
-    qv_add(&ia, &SA.c1, &SA.c2, 1); qv_add(&ib, &SB.c1, &SB.c2, 1);
-    qv_selh(&ia, &SA.c0, &ia, 1); qv_selh(&ib, &SB.c0, &ib, 1);
+    qv_add(&ia, qa(&SA, 1), qa(&SA, 2), 1); qv_add(&ib, qa(&SB, 1), qa(&SB, 2), 1);
+    qv_selh(&ia, qa(&SA, 0), &ia, 1); qv_selh(&ib, qa(&SB, 0), &ib, 1);
     q2_mul(&own, &ia, &ib);
     q_bcast(&v0, &m12, &own);
     // round 8: v1 = SA1 SB1 | (SA0 + SA1)(SB0 + SB1)
-    qv_add(&ia, &SA.c0, &SA.c1, 1); qv_add(&ib, &SB.c0, &SB.c1, 1);
-    qv_selh(&ia, &SA.c1, &ia, 1); qv_selh(&ib, &SB.c1, &ib, 1);
+    qv_add(&ia, qa(&SA, 0), qa(&SA, 1), 1); qv_add(&ib, qa(&SB, 0), qa(&SB, 1), 1);
+    qv_selh(&ia, qa(&SA, 1), &ia, 1); qv_selh(&ib, qa(&SB, 1), &ib, 1);
     q2_mul(&own, &ia, &ib);
     q_bcast(&v1, &m01, &own);
     // round 9: v2 = SA2 SB2 | (SA0 + SA2)(SB0 + SB2)
-    qv_add(&ia, &SA.c0, &SA.c2, 1); qv_add(&ib, &SB.c0, &SB.c2, 1);
-    qv_selh(&ia, &SA.c2, &ia, 1); qv_selh(&ib, &SB.c2, &ib, 1);
+    qv_add(&ia, qa(&SA, 0), qa(&SA, 2), 1); qv_add(&ib, qa(&SB, 0), qa(&SB, 2), 1);
+    qv_selh(&ia, qa(&SA, 2), &ia, 1); qv_selh(&ib, qa(&SB, 2), &ib, 1);
     q2_mul(&own, &ia, &ib);
     q_bcast(&v2, &m02, &own);
     // cc = (v0 + xi (m12 - v1 - v2), m01 - v0 - v1 + xi v2, m02 - v0 - v2 + v1)   (fq6.go:255-292)
     qv_sub(&m12, &m12, &v1, 1); qv_sub(&m12, &m12, &v2, 1);
     q2_mul_nr(&m12, &m12);
-    qv_add(&SA.c0, &m12, &v0, 1);
+    qv_add(qa(&SA, 0), &m12, &v0, 1);
     qv_sub(&m01, &m01, &v0, 1); qv_sub(&m01, &m01, &v1, 1);
     q2_mul_nr(&s, &v2);
-    qv_add(&SA.c1, &m01, &s, 1);
+    qv_add(qa(&SA, 1), &m01, &s, 1);
     qv_sub(&m02, &m02, &v0, 1); qv_sub(&m02, &m02, &v2, 1);
-    qv_add(&SA.c2, &m02, &v1, 1);
+    qv_add(qa(&SA, 2), &m02, &v1, 1);
     // c0 = aa + v bb   (half 0: Pr = aa, O = bb)        c1 = cc - aa - bb   (half 1: Pr = bb, O = aa)
-    qv_xh(&O.c0, &Pr.c0, 3);
+    qv_xh(qa(&O, 0), qa(&Pr, 0), 3);
     q6_mul_v(&SB, &O);
-    qv_add(&SB.c0, &Pr.c0, &SB.c0, 3);
-    qv_sub(&SA.c0, &SA.c0, &Pr.c0, 3);
-    qv_sub(&SA.c0, &SA.c0, &O.c0, 3);
-    qv_selh(&r->c0, &SB.c0, &SA.c0, 3);
+    qv_add(qa(&SB, 0), qa(&Pr, 0), qa(&SB, 0), 3);
+    qv_sub(qa(&SA, 0), qa(&SA, 0), qa(&Pr, 0), 3);
+    qv_sub(qa(&SA, 0), qa(&SA, 0), qa(&O, 0), 3);
+    qv_selh(qa(r, 0), qa(&SB, 0), qa(&SA, 0), 3);
 }
-HD void q12_conj(q6 *r, const q6 *a) { qv_neg(&r->c0, &a->c0, 3, 3); }     // fq12.go:27-29: c1 <- -c1
+HD void q12_conj(q6 *r, const q6 *a) { qv_neg(qa(r, 0), qa(a, 0), 3, 3); }     // fq12.go:27-29: c1 <- -c1
 HD void q12_set_one(q6 *r) {
     qfp one, z;
     q2_set_one(one); q_set_zero(z);
@@ -439,34 +444,34 @@ HD void q12_is_zero(bool r[QL], const q6 *a) {
 HDN void q12_frobenius(q6 *r, const q6 *a, int power) {
     q6 t = *a;
     qfp k, one;
-    if (power & 1) qv_neg(&t.c0, &t.c0, 3, 1);                               // fq2.go:156-158
+    if (power & 1) qv_neg(qa(&t, 0), qa(&t, 0), 3, 1);                               // fq2.go:156-158
     q2_load_tab(k, B381_TAB(frob6_c1) + power * 24);
-    q2_mul(&t.c1, &t.c1, &k);
+    q2_mul(qa(&t, 1), qa(&t, 1), &k);
     q2_load_tab(k, B381_TAB(frob6_c2) + power * 24);
-    q2_mul(&t.c2, &t.c2, &k);
+    q2_mul(qa(&t, 2), qa(&t, 2), &k);
     q2_load_tab(k, B381_TAB(frob12_c1) + power * 24);
     q2_set_one(one);
     qv_selh(&k, &one, &k, 1);
-    q2_mul(&t.c0, &t.c0, &k);
-    q2_mul(&t.c1, &t.c1, &k);
-    q2_mul(&t.c2, &t.c2, &k);
+    q2_mul(qa(&t, 0), qa(&t, 0), &k);
+    q2_mul(qa(&t, 1), qa(&t, 1), &k);
+    q2_mul(qa(&t, 2), qa(&t, 2), &k);
     *r = t;
 }
 // r = a^-1; ok = false (r untouched) for a == 0   (fq12.go:216-237)
 HDN void q12_inv(q6 *r, const q6 *a, bool ok[QL]) {
     q6 Pr, O, t0;
     q6_mul(&Pr, a, a);                             // c0^2 | c1^2
-    qv_xh(&O.c0, &Pr.c0, 3);
-    qv_selh(&t0.c0, &Pr.c0, &O.c0, 3);             // c0^2 on all lanes
-    qv_selh(&O.c0, &O.c0, &Pr.c0, 3);              // c1^2 on all lanes
+    qv_xh(qa(&O, 0), qa(&Pr, 0), 3);
+    qv_selh(qa(&t0, 0), qa(&Pr, 0), qa(&O, 0), 3);             // c0^2 on all lanes
+    qv_selh(qa(&O, 0), qa(&O, 0), qa(&Pr, 0), 3);              // c1^2 on all lanes
     q6_mul_v(&O, &O);
-    qv_sub(&t0.c0, &t0.c0, &O.c0, 3);
+    qv_sub(qa(&t0, 0), qa(&t0, 0), qa(&O, 0), 3);
     bool z[QL];
     q12_is_zero(z, &t0);                           // (both halves hold the same Fq6 value)
     QFOR ok[l_] = !z[l_];
     q6_inv(&t0, &t0);
     q6_mul(&Pr, a, &t0);                           // c0 t | c1 t
-    qv_neg(&r->c0, &Pr.c0, 3, 3);                  // (c0 t, -c1 t)
+    qv_neg(qa(r, 0), qa(&Pr, 0), 3, 3);                  // (c0 t, -c1 t)
 }
 
 // Squaring in the cyclotomic subgroup (Granger-Scott; fp12_cyclotomic_sqr of tower.cuh): nine Fq2 squarings in five rounds.
@@ -474,23 +479,23 @@ HDN void q12_inv(q6 *r, const q6 *a, bool ok[QL]) {
 HDN void q12_cyc_sqr(q6 *F) {
     q6 O, A, B;        // A = half 0's coefficients (z0, z4, z3), B = half 1's (z2, z1, z5), on all lanes
     qfp in, own, s, a2[3], b2[3], ab2[3], t;
-    qv_xh(&O.c0, &F->c0, 3);
-    qv_selh(&A.c0, &F->c0, &O.c0, 3);
-    qv_selh(&B.c0, &O.c0, &F->c0, 3);
+    qv_xh(qa(&O, 0), qa(F, 0), 3);
+    qv_selh(qa(&A, 0), qa(F, 0), qa(&O, 0), 3);
+    qv_selh(qa(&B, 0), qa(&O, 0), qa(F, 0), 3);
     // Fp4 pairs (a, b): (z0, z1) = (A0, B1), (z2, z3) = (B0, A2), (z4, z5) = (A1, B2)
-    qv_selh(&in, &A.c0, &B.c1, 1); q2_sqr(&own, &in); q_bcast(&a2[0], &b2[0], &own);
-    qv_add(&s, &A.c0, &B.c1, 1);
-    qv_selh(&in, &s, &B.c0, 1); q2_sqr(&own, &in); q_bcast(&ab2[0], &a2[1], &own);
-    qv_add(&s, &B.c0, &A.c2, 1);
-    qv_selh(&in, &A.c2, &s, 1); q2_sqr(&own, &in); q_bcast(&b2[1], &ab2[1], &own);
-    qv_selh(&in, &A.c1, &B.c2, 1); q2_sqr(&own, &in); q_bcast(&a2[2], &b2[2], &own);
-    qv_add(&s, &A.c1, &B.c2, 1);
+    qv_selh(&in, qa(&A, 0), qa(&B, 1), 1); q2_sqr(&own, &in); q_bcast(&a2[0], &b2[0], &own);
+    qv_add(&s, qa(&A, 0), qa(&B, 1), 1);
+    qv_selh(&in, &s, qa(&B, 0), 1); q2_sqr(&own, &in); q_bcast(&ab2[0], &a2[1], &own);
+    qv_add(&s, qa(&B, 0), qa(&A, 2), 1);
+    qv_selh(&in, qa(&A, 2), &s, 1); q2_sqr(&own, &in); q_bcast(&b2[1], &ab2[1], &own);
+    qv_selh(&in, qa(&A, 1), qa(&B, 2), 1); q2_sqr(&own, &in); q_bcast(&a2[2], &b2[2], &own);
+    qv_add(&s, qa(&A, 1), qa(&B, 2), 1);
     q2_sqr(&ab2[2], &s);                           // (both halves: the ninth squaring has no partner)
     // fp4_sqr: t0 = a^2 + xi b^2, t1 = (a + b)^2 - a^2 - b^2
     //   z0' = 3 t0(01) - 2 z0    z4' = 3 t0(23) - 2 z4    z3' = 3 t0(45) - 2 z3             (half 0: 3 T - 2 z)
     //   z2' = 3 xi t1(45) + 2 z2    z1' = 3 t1(01) + 2 z1    z5' = 3 t1(23) + 2 z5           (half 1: 3 T + 2 z)
     q6 T0, T1;
-    qfp *t0p[3] = {&T0.c0, &T0.c1, &T0.c2}, *t1p[3] = {&T1.c0, &T1.c1, &T1.c2};
+    qfp *t0p[3] = {qa(&T0, 0), qa(&T0, 1), qa(&T0, 2)}, *t1p[3] = {qa(&T1, 0), qa(&T1, 1), qa(&T1, 2)};
 #pragma unroll 1
     for (int i = 0; i < 3; i++) {
         q2_mul_nr(&t, &b2[i]);
@@ -498,14 +503,14 @@ HDN void q12_cyc_sqr(q6 *F) {
         qv_sub(&t, &ab2[i], &a2[i], 1);
         qv_sub(t1p[i], &t, &b2[i], 1);
     }
-    q2_mul_nr(&t, &T1.c2);
+    q2_mul_nr(&t, qa(&T1, 2));
     // half 0 rows (z0, z4, z3) take (t0(01), t0(23), t0(45)); half 1 rows (z2, z1, z5) take (xi t1(45), t1(01), t1(23))
     O.c0 = t; O.c1 = T1.c0; O.c2 = T1.c1;
-    qv_selh(&T0.c0, &T0.c0, &O.c0, 3);
+    qv_selh(qa(&T0, 0), qa(&T0, 0), qa(&O, 0), 3);
     // 3 T -+ 2 z = T + 2 (T -+ z)
-    qv_addsub(&O.c0, &T0.c0, &F->c0, 3, 3);
-    qv_dbl(&O.c0, &O.c0, 3);
-    qv_add(&F->c0, &O.c0, &T0.c0, 3);
+    qv_addsub(qa(&O, 0), qa(&T0, 0), qa(F, 0), 3, 3);
+    qv_dbl(qa(&O, 0), qa(&O, 0), 3);
+    qv_add(qa(F, 0), qa(&O, 0), qa(&T0, 0), 3);
 }
 
 // ---- global memory <-> lanes ---------------------------------------------------------------------------------------
@@ -678,8 +683,8 @@ HD void q_cyc_compress(qfp *G, const q6 *F) {
     // g2 = c1.c0 (half 1, F.c0), g3 = c0.c2 (half 0, F.c2), g4 = c0.c1 (half 0, F.c1), g5 = c1.c2 (half 1, F.c2)
     // half 0 holds (g2, g3) = (the other half's c0, own c2);  half 1 holds (g4, g5) = (the other half's c1, own c2)
     q6 O;
-    qv_xh(&O.c0, &F->c0, 3);
-    qv_selh(&G[0], &O.c0, &O.c1, 1);
+    qv_xh(qa(&O, 0), qa(F, 0), 3);
+    qv_selh(&G[0], qa(&O, 0), qa(&O, 1), 1);
     G[1] = F->c2;
 }
 // all four compressed coefficients (g2, g3, g4, g5) of the own quad on every lane
@@ -711,7 +716,7 @@ HD void q_cyc_place(q6 *F, const qfp *g0, const qfp *g1, const qfp *g) {
     qfp a[3], b[3];
     a[0] = *g0; a[1] = g[2]; a[2] = g[1];
     b[0] = g[0]; b[1] = *g1; b[2] = g[3];
-    qv_selh(&F->c0, a, b, 3);
+    qv_selh(qa(F, 0), a, b, 3);
 }
 // conj(f^x), square and multiply with Granger-Scott squarings (exp_by_x_gs of pairing.cuh); r must not alias f
 HDN void q_exp_by_x_gs(q6 *r, const q6 *f, uint64_t x) {
@@ -777,10 +782,10 @@ HDN void q_exp_by_x_main(q6 *r, bool bad[QL], const q6 *f, uint64_t x, int stage
         lo.c0 = g0; lo.c1 = gs[2]; lo.c2 = gs[1];          // the coefficients that live on half 0
         hi.c0 = gs[0]; hi.c1 = g1; hi.c2 = gs[3];          // the coefficients that live on half 1
         // half 0 keeps lo of value 0 and needs lo of value 1 (held by half 1); half 1 keeps hi of value 1, needs hi of value 0
-        qv_selh(&own.c0, &hi.c0, &lo.c0, 3);               // what the OTHER half is missing of my value
-        qv_xh(&oth.c0, &own.c0, 3);
-        qv_selh(&D0.c0, &lo.c0, &oth.c0, 3);               // value 0: half 0 own lo | half 1 receives hi of value 0
-        qv_selh(&D1.c0, &oth.c0, &hi.c0, 3);               // value 1: half 0 receives lo of value 1 | half 1 own hi
+        qv_selh(qa(&own, 0), qa(&hi, 0), qa(&lo, 0), 3);               // what the OTHER half is missing of my value
+        qv_xh(qa(&oth, 0), qa(&own, 0), 3);
+        qv_selh(qa(&D0, 0), qa(&lo, 0), qa(&oth, 0), 3);               // value 0: half 0 own lo | half 1 receives hi of value 0
+        qv_selh(qa(&D1, 0), qa(&oth, 0), qa(&hi, 0), 3);               // value 1: half 0 receives lo of value 1 | half 1 own hi
     }
     q_cyc_place(&D2, &h0, &h1, C[2]);
     if (stage == 1) { *r = D0; return; }

@@ -60,7 +60,7 @@ __global__ void k_test_fp6(int op, uint64_t arg, const uint64_t *a, const uint64
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     fp6 x, y, r;
-    fp *px = &x.c0.c0, *py = &y.c0.c0, *pr = &r.c0.c0;
+    fp *px = fp_array(&x), *py = fp_array(&y), *pr = fp_array(&r);
     for (int k = 0; k < 6; k++) { fp_load_u64(px[k], a + 36 * i + 6 * k); fp_load_u64(py[k], b + 36 * i + 6 * k); }
     r = x;
     switch (op) {

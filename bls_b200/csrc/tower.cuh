@@ -16,6 +16,12 @@ namespace b381 {
 struct fp2 { fp c0, c1; };
 struct fp6 { fp2 c0, c1, c2; };
 struct fp12 { fp6 c0, c1; };
+// The Fq coefficients of a tower element as an array, taken from the WHOLE object.  `&x->c0` followed by indexing past that
+// member is undefined behaviour, and cicc 12.9 exploits it: a callee that receives `&x->c0` is assumed to touch the first
+// coefficient only, so the caller keeps stale copies of the others in registers (device-only wrong values as soon as such a
+// call is out of line in a function that also reads the members; profiles/r02_experiments.md).
+template <class T> HD fp *fp_array(T *x) { return reinterpret_cast<fp *>(x); }
+template <class T> HD const fp *fp_array(const T *x) { return reinterpret_cast<const fp *>(x); }
 
 // C-ABI PODs (include/b381.h): Go's G1Affine / G2Affine structs incl. padding (g1.go:10-14, g2.go:12-16)
 struct g1_affine_pod { uint64_t x[6], y[6]; uint8_t inf; uint8_t pad[7]; };
@@ -198,12 +204,12 @@ HDN void fp_inv(fp *out, const fp *a) {
 // ---- Fq2 (fq2.go) ----------------------------------------------------------------------------
 // three-pointer entry points: ~170 call sites in the Miller loop each save the two constant arguments (length, mode) --
 // the kernel sits at the instruction-cache limit and call-site code is most of what is not a multiplier
-HDN void fp2_add_p(fp2 *r, const fp2 *a, const fp2 *b) { fpv_addsub(&r->c0, &a->c0, &b->c0, 2, 0); }
-HDN void fp2_sub_p(fp2 *r, const fp2 *a, const fp2 *b) { fpv_addsub(&r->c0, &a->c0, &b->c0, 2, 1); }
+HDN void fp2_add_p(fp2 *r, const fp2 *a, const fp2 *b) { fpv_addsub(fp_array(r), fp_array(a), fp_array(b), 2, 0); }
+HDN void fp2_sub_p(fp2 *r, const fp2 *a, const fp2 *b) { fpv_addsub(fp_array(r), fp_array(a), fp_array(b), 2, 1); }
 HD void fp2_add(fp2 &r, const fp2 &a, const fp2 &b) { fp2_add_p(&r, &a, &b); }            // fq2.go:104-107
 HD void fp2_sub(fp2 &r, const fp2 &a, const fp2 &b) { fp2_sub_p(&r, &a, &b); }            // fq2.go:110-113
 HD void fp2_dbl(fp2 &r, const fp2 &a) { fp2_add_p(&r, &a, &a); }                          // fq2.go:92-95
-HD void fp2_neg(fp2 &r, const fp2 &a) { fpv_neg(&r.c0, &a.c0, 2); }                       // fq2.go:98-101
+HD void fp2_neg(fp2 &r, const fp2 &a) { fpv_neg(fp_array(&r), fp_array(&a), 2); }                       // fq2.go:98-101
 HD void fp2_conj(fp2 &r, const fp2 &a) { r.c0 = a.c0; fp_neg(r.c1, a.c1); }
 HD bool fp2_is_zero(const fp2 &a) { return fp_is_zero(a.c0) && fp_is_zero(a.c1); }
 HD bool fp2_eq(const fp2 &a, const fp2 &b) { return fp_eq(a.c0, b.c0) && fp_eq(a.c1, b.c1); }
@@ -258,9 +264,9 @@ HDN void fp2_inv(fp2 *r, const fp2 *a) {
 }
 
 // ---- Fq6 (fq6.go) ------------------------------------------------------------------------------
-HD void fp6_add(fp6 *r, const fp6 *a, const fp6 *b) { fpv_add(&r->c0.c0, &a->c0.c0, &b->c0.c0, 6); }   // fq6.go:123-127
-HD void fp6_sub(fp6 *r, const fp6 *a, const fp6 *b) { fpv_sub(&r->c0.c0, &a->c0.c0, &b->c0.c0, 6); }   // fq6.go:130-134
-HD void fp6_neg(fp6 *r, const fp6 *a) { fpv_neg(&r->c0.c0, &a->c0.c0, 6); }                  // fq6.go:116-120
+HD void fp6_add(fp6 *r, const fp6 *a, const fp6 *b) { fpv_add(fp_array(r), fp_array(a), fp_array(b), 6); }   // fq6.go:123-127
+HD void fp6_sub(fp6 *r, const fp6 *a, const fp6 *b) { fpv_sub(fp_array(r), fp_array(a), fp_array(b), 6); }   // fq6.go:130-134
+HD void fp6_neg(fp6 *r, const fp6 *a) { fpv_neg(fp_array(r), fp_array(a), 6); }                  // fq6.go:116-120
 // r = a * v   (fq6.go:34-37)
 HD void fp6_mul_nr(fp6 *r, const fp6 *a) {
     fp2 t = a->c2, c0 = a->c0, c1 = a->c1;
@@ -376,14 +382,14 @@ HDN void fp6_frobenius(fp6 *r, const fp6 *a, int power) {
 
 // ---- Fq12 (fq12.go) ----------------------------------------------------------------------------
 HD void fp12_set_one(fp12 *r) {
-    fp *p = &r->c0.c0.c0;
+    fp *p = fp_array(r);
     fp z; fp_set_zero(z);
 #pragma unroll 1
     for (int i = 1; i < 12; i++) p[i] = z;
     fp_set_one(z); p[0] = z;
 }
 HD void fp12_copy(fp12 *r, const fp12 *a) {
-    const fp *pa = &a->c0.c0.c0; fp *pr = &r->c0.c0.c0;
+    const fp *pa = fp_array(a); fp *pr = fp_array(r);
 #pragma unroll 1
     for (int i = 0; i < 12; i++) { fp x = pa[i]; pr[i] = x; }
 }
@@ -392,7 +398,7 @@ HD void fp12_conj(fp12 *r, const fp12 *a) {   // fq12.go:27-29
     fp6_neg(&r->c1, &a->c1);
 }
 HD bool fp12_is_one(const fp12 *a) {           // fq12.go:56-58 against FQ12One
-    const fp *p = &a->c0.c0.c0;
+    const fp *p = fp_array(a);
     fp one; fp_set_one(one);
     bool ok = fp_eq(p[0], one);
 #pragma unroll 1
@@ -400,7 +406,7 @@ HD bool fp12_is_one(const fp12 *a) {           // fq12.go:56-58 against FQ12One
     return ok;
 }
 HD bool fp12_is_zero(const fp12 *a) {
-    const fp *p = &a->c0.c0.c0;
+    const fp *p = fp_array(a);
     bool z = true;
 #pragma unroll 1
     for (int i = 0; i < 12; i++) z = z && fp_is_zero(p[i]);
@@ -492,18 +498,18 @@ HD void fp4_sqr(fp2 &o0, fp2 &o1, const fp2 &a, const fp2 &b) {
     fp2_sqr(&t1, &b);
     // (direct calls of the add/sub loop: this runs in the final-exponentiation kernel, where the extra hop through the
     // three-pointer entry points costs more than their smaller call sites save)
-    fpv_add(&o1.c0, &a.c0, &b.c0, 2);
+    fpv_add(fp_array(&o1), fp_array(&a), fp_array(&b), 2);
     fp2_sqr(&o1, &o1);
-    fpv_sub(&o1.c0, &o1.c0, &o0.c0, 2);
-    fpv_sub(&o1.c0, &o1.c0, &t1.c0, 2);          // 2ab
+    fpv_sub(fp_array(&o1), fp_array(&o1), fp_array(&o0), 2);
+    fpv_sub(fp_array(&o1), fp_array(&o1), fp_array(&t1), 2);          // 2ab
     fp2_mul_nr(t1, t1);
-    fpv_add(&o0.c0, &o0.c0, &t1.c0, 2);          // a^2 + xi b^2
+    fpv_add(fp_array(&o0), fp_array(&o0), fp_array(&t1), 2);          // a^2 + xi b^2
 }
 // r = 3t - 2z (plus = 0) or 3t + 2z (plus = 1): the six output rows of the cyclotomic squaring as ONE pass each (three
 // separate add/sub/double passes cost three local-memory round trips per row)
 HDN void fp2_tri(fp2 *r, const fp2 *t, const fp2 *z, int plus) {
-    const fp *tp = &t->c0, *zp = &z->c0;
-    fp *rp = &r->c0;
+    const fp *tp = fp_array(t), *zp = fp_array(z);
+    fp *rp = fp_array(r);
 #pragma unroll 1
     for (int i = 0; i < 2; i++) {
         fp x = tp[i], y = zp[i], u;

@@ -258,7 +258,7 @@ def aggregate_extras(ctx, stream, dev, rank, world, torch, np, imad_peak):
         check("MSM result")
         ph = (ctypes.c_float * 5)()
         ctx.dev("b381_g1_msm_shard_phases_dev", dKp.data_ptr(), dKs.data_ptr(), ctypes.c_size_t(n_c), 0, 1, dOut.data_ptr(), ph)
-        c_bits = max(4, min(16, lg - 5)); W = (255 + c_bits - 1) // c_bits
+        c_bits = max(4, min(16, lg - 5)); W = (255 + c_bits) // c_bits          # signed digits: one more bit for the last carry
         macs = n_c * W * 10 * MACS_PER_FQ_MUL          # XYZZ mixed addition: 8 M + 2 S per point and window
         blk = {"n": n_c, "scalar_bits": 255, "window_bits": c_bits, "windows": W, "ms": t_msm, "points_per_s": n_c / (t_msm * 1e-3),
                "phases_ms": {k: float(v) for k, v in zip(PH, ph)},

@@ -98,9 +98,17 @@ __global__ void k_msm_hist(const uint64_t *__restrict__ k, msm_geom g, uint32_t 
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     uint64_t s[4] = {k[4 * i], k[4 * i + 1], k[4 * i + 2], k[4 * i + 3]};
-    for (int j = 0; j < g.nw; j++) {
-        uint32_t d = msm_digit(s, g.w0 + j * g.wstep, g.c);
-        if (d) atomicAdd(&count[(size_t)j * g.nb + d], 1u);
+    // signed digits, carry chain walked once over all windows up to this rank's last one
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (g.c - 1);
+    int j = 0;
+    for (int w = 0; j < g.nw; w++) {
+        uint32_t raw = msm_digit(s, w, g.c) + carry, mag;
+        if (raw > half) { mag = (1u << g.c) - raw; carry = 1; } else { mag = raw; carry = 0; }
+        if (w == g.w0 + j * g.wstep) {
+            if (mag) atomicAdd(&count[(size_t)j * g.nb + mag], 1u);
+            j++;
+        }
     }
 }
 
@@ -160,11 +168,19 @@ __global__ void k_msm_scatter(const uint64_t *__restrict__ k, msm_geom g, const 
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     uint64_t s[4] = {k[4 * i], k[4 * i + 1], k[4 * i + 2], k[4 * i + 3]};
-    for (int j = 0; j < g.nw; j++) {
-        uint32_t d = msm_digit(s, g.w0 + j * g.wstep, g.c);
-        if (!d) continue;
-        uint32_t slot = atomicSub(&count[(size_t)j * g.nb + d], 1u) - 1u;
-        idx[(size_t)j * g.n + bucket_off[(size_t)j * (g.nb + 1) + d] + slot] = (uint32_t)i;
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (g.c - 1);
+    int j = 0;
+    for (int w = 0; j < g.nw; w++) {
+        uint32_t raw = msm_digit(s, w, g.c) + carry, mag, neg;
+        if (raw > half) { mag = (1u << g.c) - raw; carry = 1; neg = MSM_NEG_BIT; } else { mag = raw; carry = 0; neg = 0; }
+        if (w == g.w0 + j * g.wstep) {
+            if (mag) {
+                uint32_t slot = atomicSub(&count[(size_t)j * g.nb + mag], 1u) - 1u;
+                idx[(size_t)j * g.n + bucket_off[(size_t)j * (g.nb + 1) + mag] + slot] = (uint32_t)i | neg;
+            }
+            j++;
+        }
     }
 }
 
@@ -196,7 +212,9 @@ template <class F, class APOD> __global__ void __launch_bounds__(128) k_msm_chun
             b = lo; bend = bo[b + 1];
         }
         typename F::T x, y; bool inf;
-        load_affine(x, y, inf, pts + ix[pos]);
+        const uint32_t e = ix[pos];
+        load_affine(x, y, inf, pts + (e & ~MSM_NEG_BIT));
+        if (e & MSM_NEG_BIT) F::neg(y, y);             // a negative digit adds -P
         if (!inf) xyzz_madd(acc, x, y);
     }
     uint32_t ci = co[b] + (q - bo[b] / MSM_CHUNK);

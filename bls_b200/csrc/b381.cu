@@ -1159,17 +1159,17 @@ static inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 template <class F, class APOD, class JPOD>
 static int msm_shard_dev(b381_ctx *ctx, const APOD *d_p, const b381_scalar *d_k, size_t n, int nbits, int rank, int nranks, JPOD *d_partial,
                          float *phase_ms = nullptr) {
-    if (!ctx || !d_partial || (n && (!d_p || !d_k)) || nranks < 1 || rank < 0 || rank >= nranks || n > 0xFFFFFFF0u || nbits < 1 || nbits > 255)
-        return B381_ERR_ARG;
+    if (!ctx || !d_partial || (n && (!d_p || !d_k)) || nranks < 1 || rank < 0 || rank >= nranks || n > 0x7FFFFFF0u || nbits < 1 || nbits > 255)
+        return B381_ERR_ARG;                         // (bit 31 of an index entry is the sign of the digit)
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (phase_ms) for (int i = 0; i < 6; i++) CK(cudaEventCreate(&ev[i]));
 #define MSM_MARK(i) do { if (phase_ms) CK(cudaEventRecord(ev[i], ctx->stream)); } while (0)
     bool whole = nranks == 1;
     msm_geom g;
     g.c = msm_window_bits(n);
-    int W = (nbits + g.c - 1) / g.c;
+    int W = msm_signed_windows(nbits, g.c);          // signed digits: 2^(c-1) buckets per window, one more bit for the last carry
     g.w0 = rank; g.wstep = nranks; g.nw = rank < W ? (W - rank + nranks - 1) / nranks : 0;
-    g.nb = 1u << g.c; g.n = n;
+    g.nb = (1u << (g.c - 1)) + MSM_SEG; g.n = n;     // digit magnitudes 1 .. 2^(c-1), rounded up to whole segments
     g.maxchunks = (uint32_t)(n / MSM_CHUNK) + g.nb + 2;      // runs of the sorted list + one more chunk per bucket boundary
     uint32_t nseg = g.nb / MSM_SEG;
     int nw = g.nw > 0 ? g.nw : 1;

@@ -354,13 +354,30 @@ HD int msm_window_bits(size_t n) {
     return c < 4 ? 4 : (c > 16 ? 16 : c);
 }
 HD int msm_num_windows(int c) { return (255 + c - 1) / c; }
+// Signed c-bit digits of a scalar of at most nbits bits: k = sum_w d_w 2^(c w) with -2^(c-1) < d_w <= 2^(c-1), so a window needs
+// 2^(c-1) buckets instead of 2^c - 1 (a negative digit adds -P: y -> Q - y).  W = msm_signed_windows(nbits, c) digits hold the
+// final carry.  Returns digit w; the carry chain from window 0 is recomputed (a few integer operations per window).
+HD int msm_signed_windows(int nbits, int c) { return (nbits + c) / c; }       // ceil((nbits + 1) / c)
+HD int32_t msm_signed_digit(const uint64_t *k, int w, int c) {
+    uint32_t carry = 0, half = 1u << (c - 1);
+    int32_t d = 0;
+    for (int v = 0; v <= w; v++) {
+        uint32_t raw = msm_digit(k, v, c) + carry;
+        if (raw > half) { d = (int32_t)raw - (int32_t)(1u << c); carry = 1; }
+        else { d = (int32_t)raw; carry = 0; }
+    }
+    return d;
+}
 
-// sum of the points idx[lo..hi) into acc (one bucket)
+// sum of the points idx[lo..hi) into acc (one bucket); bit 31 of an index entry = add the NEGATED point (signed digits)
+#define MSM_NEG_BIT 0x80000000u
 template <class F, class APOD> HD void msm_bucket_sum(xyzz<F> &acc, const APOD *pts, const uint32_t *idx, uint32_t lo, uint32_t hi) {
     xyzz_set_inf(acc);
     for (uint32_t j = lo; j < hi; j++) {
         typename F::T x, y; bool inf;
-        load_affine(x, y, inf, pts + idx[j]);
+        const uint32_t e = idx[j];
+        load_affine(x, y, inf, pts + (e & ~MSM_NEG_BIT));
+        if (e & MSM_NEG_BIT) F::neg(y, y);
         if (!inf) xyzz_madd(acc, x, y);
     }
 }

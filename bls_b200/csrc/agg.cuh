@@ -201,12 +201,14 @@ template <class F, class APOD> __global__ void __launch_bounds__(128) k_msm_chun
     xyzz<F> *cbase = chunks + (size_t)j * g.maxchunks;
     uint32_t *bbase = chunk_bucket + (size_t)j * g.maxchunks;
     uint32_t b = 0, bend = 0;
-    xyzz<F> acc;
-    xyzz_set_inf(acc);
+    typedef typename acc_policy<F>::type FA;           // same element type; G1: the two squarings of a mixed addition use fp_sqr_v
+    xyzz<FA> accv;
+    xyzz<F> &acc = reinterpret_cast<xyzz<F> &>(accv);
+    xyzz_set_inf(accv);
 #pragma unroll 1
     for (uint32_t pos = first; pos < last; pos++) {
         if (pos == bend || pos == first) {
-            if (pos != first) { uint32_t ci = co[b] + (q - bo[b] / MSM_CHUNK); cbase[ci] = acc; bbase[ci] = b; xyzz_set_inf(acc); }
+            if (pos != first) { uint32_t ci = co[b] + (q - bo[b] / MSM_CHUNK); cbase[ci] = acc; bbase[ci] = b; xyzz_set_inf(accv); }
             uint32_t lo = 0, hi = g.nb;            // the bucket of position pos: largest b with bo[b] <= pos (it is non-empty)
             while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (bo[mid] <= pos) lo = mid; else hi = mid; }
             b = lo; bend = bo[b + 1];
@@ -215,7 +217,7 @@ template <class F, class APOD> __global__ void __launch_bounds__(128) k_msm_chun
         const uint32_t e = ix[pos];
         load_affine(x, y, inf, pts + (e & ~MSM_NEG_BIT));
         if (e & MSM_NEG_BIT) F::neg(y, y);             // a negative digit adds -P
-        if (!inf) xyzz_madd(acc, x, y);
+        if (!inf) xyzz_madd(accv, x, y);
     }
     uint32_t ci = co[b] + (q - bo[b] / MSM_CHUNK);
     cbase[ci] = acc; bbase[ci] = b;

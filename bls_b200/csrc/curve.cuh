@@ -45,6 +45,9 @@ struct FpSqr : FpInl {
 #endif
     }
 };
+// policy of a long accumulation loop over F (MSM chunk sums): same element type, the dedicated squaring where there is one
+template <class F> struct acc_policy { typedef F type; };
+template <> struct acc_policy<FpInl> { typedef FpSqr type; };
 struct FpOut : FpInl {
     static HD void mul(T &r, const T &a, const T &b) { fp_mul_n(&r, &a, &b); }
     static HD void sqr(T &r, const T &a) { fp_sqr_n(&r, &a); }

@@ -144,6 +144,7 @@ HDN void q_bcast(qfp *r0, qfp *r1, const qfp *own) {
     *r0 = a; *r1 = b;
 }
 // lane-local Fq products: r[i] = a[i] * s (the Fq2 x Fq scalings of pairing.go:33-36 and the norm inversions)
+// (routing these through the two-product body like q2_sqr was measured and is slower: k_duo_miller_loop 23.8 -> 24.3 ms)
 HDN void qv_mul(qfp *r, const qfp *a, const qfp *s, int n) {
     qfp k = *s;
 #pragma unroll 1
@@ -175,6 +176,12 @@ HDN void q2_mul(qfp *r, const qfp *a, const qfp *b) {
 }
 // r = a^2   (fq2.go:75-89: (a0 + a1)(a0 - a1) on lane 0, a1 (2 a0) on lane 1; the operand sums stay unreduced, below 2Q)
 HDN void q2_sqr(qfp *r, const qfp *a) {
+#ifndef B381_LANE_SQR_FPMUL
+    // a0 a0 + a1 (Q - a1) | a1 a0 + a0 a1 through the two-product body: 144 wide MACs more per squaring than the form below, but
+    // the plain multiplier (6 KB) leaves the hot set of the lane kernels, which sit at the instruction-cache limit: measured at
+    // 2^16 pairings, two lanes k_duo_final_exp 27.1 -> 25.8 ms, four lanes 33.5 / 39.8 -> 31.9 / 36.0 ms (profiles/r02_experiments.md)
+    q2_mul(r, a, a); return;
+#endif
     qfp A = *a, AO, R;
     q_shfl(AO, A, 1);
     QFOR {

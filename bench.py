@@ -260,7 +260,7 @@ def aggregate_extras(ctx, stream, dev, rank, world, torch, np, imad_peak):
     # 144-byte partials + a fold on every rank; the speed-up is against the single-rank time measured in the same run.
     K, kvals = hg.splitmix_scalars(99, 1 << 12)
     hostPk2 = np.zeros(1, dtype=L.G1_JAC)
-    PH = ("sort", "chunk_sums", "chunk_tree", "bucket_reduce", "combine")
+    PH = ("sort", "chunk_sums", "chunk_fold", "bucket_reduce", "combine")
     for lg in (20, 22):
         n_c = 1 << lg
         dKp = dK if lg == 20 else up(np.resize(keys, n_c))

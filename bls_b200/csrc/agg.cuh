@@ -21,7 +21,8 @@ namespace b381 {
 
 #define MSM_CHUNK 64u       // points per chunk partial sum
 #define MSM_SEG 16u         // buckets per running-sum segment
-#define MSM_INLINE_CHUNKS 4u // up to this many chunks per bucket (uniform scalars: 2-3) are added where the bucket sum is consumed
+#define MSM_FOLD_MAX 16u    // up to this many chunk partials per bucket (uniform scalars: 2-5) are added by one thread per bucket (k_msm_bucket_fold);
+                            // beyond that (skewed scalars, up to every point in one bucket) the in-bucket tree rounds run first
 
 // ---- block tree over shared memory: the sum of every thread's acc ends up in thread 0 -------------
 template <class F, int BLOCK> __device__ void block_reduce_xyzz(xyzz<F> &acc, xyzz<F> *sm) {
@@ -228,7 +229,7 @@ template <class F, class APOD> __global__ void __launch_bounds__(128) k_msm_chun
 template <class F> __global__ void __launch_bounds__(128) k_msm_chunk_tree(xyzz<F> *__restrict__ chunks, const uint32_t *__restrict__ chunk_bucket,
                                                         const uint32_t *__restrict__ chunk_off, msm_geom g, int r,
                                                         const uint32_t *__restrict__ maxch) {
-    if ((1u << r) >= *maxch || *maxch <= MSM_INLINE_CHUNKS) return;      // few chunks per bucket: k_msm_segment_reduce adds them itself
+    if ((1u << r) >= *maxch || *maxch <= MSM_FOLD_MAX) return;           // few chunks per bucket: k_msm_bucket_fold adds them
     int j = blockIdx.y;
     const uint32_t *co = chunk_off + (size_t)j * (g.nb + 1);
     const uint32_t nchunks = co[g.nb];
@@ -243,10 +244,28 @@ template <class F> __global__ void __launch_bounds__(128) k_msm_chunk_tree(xyzz<
     }
 }
 
-// one thread per (window, segment of MSM_SEG buckets): sum_{d in segment} d * B[d]
+// one thread per (window, bucket): chunk 0 of the bucket absorbs its other partials.  With one thread per chunk and tree rounds
+// only every second / fourth lane works and every round is a launch over all chunks (4.0 ms at 2^22 points); here all lanes of a
+// warp fold a similar, small number of partials.
+template <class F> __global__ void __launch_bounds__(128) k_msm_bucket_fold(xyzz<F> *__restrict__ chunks, const uint32_t *__restrict__ chunk_off, msm_geom g,
+                                                         const uint32_t *__restrict__ maxch) {
+    if (*maxch > MSM_FOLD_MAX || *maxch < 2) return;                      // the tree rounds ran (or there is nothing to add)
+    int j = blockIdx.y;
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= g.nb) return;
+    const uint32_t *co = chunk_off + (size_t)j * (g.nb + 1);
+    const uint32_t c0 = co[b], c1 = co[b + 1];
+    if (c1 - c0 < 2) return;
+    xyzz<F> *base = chunks + (size_t)j * g.maxchunks;
+    xyzz<F> a = base[c0];
+#pragma unroll 1
+    for (uint32_t q = c0 + 1; q < c1; q++) { xyzz<F> t = base[q]; xyzz_add(a, t); }
+    base[c0] = a;
+}
+
+// one thread per (window, segment of MSM_SEG buckets): sum_{d in segment} d * B[d]; chunk 0 of a bucket holds its sum
 template <class F> __global__ void __launch_bounds__(128) k_msm_segment_reduce(const xyzz<F> *__restrict__ chunks, const uint32_t *__restrict__ chunk_off,
-                                                            msm_geom g, xyzz<F> *__restrict__ segsum, const uint32_t *__restrict__ maxch) {
-    const bool folded = *maxch > MSM_INLINE_CHUNKS;     // the chunk tree ran: chunk 0 of a bucket holds its sum
+                                                            msm_geom g, xyzz<F> *__restrict__ segsum) {
     int j = blockIdx.y;
     uint32_t nseg = g.nb / MSM_SEG;
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -258,8 +277,8 @@ template <class F> __global__ void __launch_bounds__(128) k_msm_segment_reduce(c
     xyzz<F> running, acc;
     xyzz_set_inf(running); xyzz_set_inf(acc);
     for (uint32_t d = hi; d-- > lo;) {
-        const uint32_t c0 = co[d], c1 = folded && co[d + 1] > c0 ? c0 + 1 : co[d + 1];
-        for (uint32_t q = c0; q < c1; q++) { xyzz<F> bsum = base[q]; xyzz_add(running, bsum); }
+        const uint32_t c0 = co[d];
+        if (co[d + 1] > c0) { xyzz<F> bsum = base[c0]; xyzz_add(running, bsum); }
         xyzz_add(acc, running);
     }
     if (lo > 1 && !xyzz_is_inf(running)) { xyzz_mul_small(running, lo - 1); xyzz_add(acc, running); }
@@ -277,14 +296,77 @@ template <class F> __global__ void __launch_bounds__(128) k_msm_window_sum(const
     if (threadIdx.x == 0) winsum[j] = acc;
 }
 
-// thread j shifts its window sum to its weight 2^(c * w_j); then a tree adds them; thread 0 writes the
-// result -- normalised (z = 1) for a complete MSM, plain Jacobian for a bucket-sharded partial
-template <class F, class JPOD> __global__ void __launch_bounds__(64) k_msm_combine(const xyzz<F> *__restrict__ winsum, msm_geom g, int normalise,
+// The window shift 2^(c w) is a chain of up to 240 doublings, the one serial stretch of the MSM (1.8 ms on one thread: 7.9 us per
+// doubling, a quarter of what an 8-GPU shard takes).  A group of FOUR lanes holding the same Jacobian point runs the seven
+// multiplications of a doubling (jac_dbl above, same formulas, same values) as three levels:
+//   A = X^2 | B = Y^2 | T = Y Z      ->      C = B^2 | S = (X + B)^2 | F = (3A)^2      ->      M = 3A (D - X3)   on every lane
+// with the level results exchanged by SHFL (3 x 12 words per level).  Returns with every lane of the group holding the result.
+__device__ __noinline__ void jac_dbl_chain_lanes(fp &X, fp &Y, fp &Z, int shifts) {
+    const unsigned lane = threadIdx.x & 31u, sub = lane & 3u, base = lane & ~3u, mask = 0xFu << base;
+#pragma unroll 1
+    for (int i = 0; i < shifts; i++) {
+        if (fp_is_zero(Z)) break;                  // infinity stays infinity (the same on every lane of the group)
+        fp p, q, r, A, B, T, C, S, Fv, E, D, t;
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            p.l[k] = sub == 0 ? X.l[k] : Y.l[k];
+            q.l[k] = sub == 0 ? X.l[k] : (sub == 1 ? Y.l[k] : Z.l[k]);
+        }
+        r = fp_mul_v(p, q);
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            A.l[k] = __shfl_sync(mask, r.l[k], base); B.l[k] = __shfl_sync(mask, r.l[k], base + 1); T.l[k] = __shfl_sync(mask, r.l[k], base + 2);
+        }
+        fp_add(E, A, A); fp_add(E, E, A);          // E = 3A
+        fp_add(t, X, B);
+#pragma unroll
+        for (int k = 0; k < 12; k++) p.l[k] = sub == 0 ? B.l[k] : (sub == 1 ? t.l[k] : E.l[k]);
+        r = fp_mul_v(p, p);
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            C.l[k] = __shfl_sync(mask, r.l[k], base); S.l[k] = __shfl_sync(mask, r.l[k], base + 1); Fv.l[k] = __shfl_sync(mask, r.l[k], base + 2);
+        }
+        fp_sub(D, S, A); fp_sub(D, D, C); fp_add(D, D, D);      // D = 2((X + B)^2 - A - C)
+        fp_sub(X, Fv, D); fp_sub(X, X, D);                      // X3 = F - 2D
+        fp_add(Z, T, T);                                        // Z3 = 2 Y Z
+        fp_sub(t, D, X);
+        r = fp_mul_v(E, t);
+        fp_add(C, C, C); fp_add(C, C, C); fp_add(C, C, C);
+        fp_sub(Y, r, C);                                        // Y3 = E (D - X3) - 8C
+    }
+}
+template <class F> struct lane_shift { static constexpr bool value = false; };
+template <> struct lane_shift<FpInl> { static constexpr bool value = true; };
+
+// window j is shifted to its weight 2^(c * w_j) -- G1: by the four lanes 4j .. 4j+3 together, otherwise by thread j --, then a
+// tree adds the windows; thread 0 writes the result: normalised (z = 1) for a complete MSM, plain Jacobian for a bucket-sharded partial
+template <class F, class JPOD, int BLOCK> __global__ void __launch_bounds__(BLOCK) k_msm_combine(const xyzz<F> *__restrict__ winsum, msm_geom g, int normalise,
                                                     JPOD *__restrict__ out) {
-    __shared__ xyzz<F> sm[64];
+    __shared__ xyzz<F> sm[BLOCK];
     xyzz<F> acc;
     xyzz_set_inf(acc);
-    for (int j = threadIdx.x; j < g.nw; j += 64) {
+    if constexpr (lane_shift<F>::value) {
+        const int grp = threadIdx.x >> 2;
+        for (int j0 = 0; j0 < g.nw; j0 += BLOCK / 4) {   // uniform over the block: the shuffles of a group need its four lanes
+            const int j = j0 + grp;
+            const bool have = j < g.nw;
+            xyzz<F> s;
+            if (have) s = winsum[j]; else xyzz_set_inf(s);
+            int shifts = have ? g.c * (g.w0 + j * g.wstep) : 0;
+            if (!xyzz_is_inf(s) && shifts) {
+                fp x, y, z;
+                F::mul(x, s.x, s.zz);              // (X ZZ, Y ZZZ, ZZ) is the same point in Jacobian form
+                F::mul(y, s.y, s.zzz);
+                z = s.zz;
+                jac_dbl_chain_lanes(x, y, z, shifts);
+                s.x = x; s.y = y;
+                F::sqr(s.zz, z);
+                F::mul(s.zzz, s.zz, z);
+            }
+            if ((threadIdx.x & 3) == 0) xyzz_add(acc, s);
+        }
+    } else {
+    for (int j = threadIdx.x; j < g.nw; j += BLOCK) {
         xyzz<F> s = winsum[j];
         int shifts = g.c * (g.w0 + j * g.wstep);
         if (!xyzz_is_inf(s) && shifts) {           // the shift is a chain of doublings: Jacobian form (2M + 5S each),
@@ -301,7 +383,8 @@ template <class F, class JPOD> __global__ void __launch_bounds__(64) k_msm_combi
         }
         xyzz_add(acc, s);
     }
-    block_reduce_xyzz<F, 64>(acc, sm);
+    }
+    block_reduce_xyzz<F, BLOCK>(acc, sm);
     if (threadIdx.x == 0) {
         typename F::T ox, oy, oz;
         if (normalise) xyzz_to_jac_normalised(ox, oy, oz, acc);

@@ -1201,9 +1201,12 @@ static int msm_shard_dev(b381_ctx *ctx, const APOD *d_p, const b381_scalar *d_k,
             k_msm_chunk_tree<F><<<tg, 128, 0, ctx->stream>>>(chunks, cb, coff, g, r, maxch);
             ctx->launches++;
         }
+        dim3 fg(grid_for(g.nb, 128), g.nw);
+        k_msm_bucket_fold<F><<<fg, 128, 0, ctx->stream>>>(chunks, coff, g, maxch);
+        ctx->launches++;
         dim3 sg(grid_for(nseg, 128), g.nw);
         MSM_MARK(3);
-        k_msm_segment_reduce<F><<<sg, 128, 0, ctx->stream>>>(chunks, coff, g, seg, maxch);
+        k_msm_segment_reduce<F><<<sg, 128, 0, ctx->stream>>>(chunks, coff, g, seg);
         k_msm_window_sum<F><<<g.nw, 128, 0, ctx->stream>>>(seg, nseg, win);
         ctx->launches += 2;
         MSM_MARK(4);
@@ -1211,7 +1214,8 @@ static int msm_shard_dev(b381_ctx *ctx, const APOD *d_p, const b381_scalar *d_k,
         g.nw = 0;
         for (int i = 0; i < 5; i++) MSM_MARK(i);
     }
-    k_msm_combine<F><<<1, 64, 0, ctx->stream>>>(win, g, whole ? 1 : 0, d_partial);
+    constexpr int CB = lane_shift<F>::value ? 128 : 64;        // G1: four lanes per window, up to 32 windows in one pass
+    k_msm_combine<F, JPOD, CB><<<1, CB, 0, ctx->stream>>>(win, g, whole ? 1 : 0, d_partial);
     ctx->launches++;
     MSM_MARK(5);
     CK(cudaGetLastError());

@@ -17,7 +17,7 @@ K[:, 3] &= np.uint64((1 << 62) - 1)                      # < 2^254 < r: canonica
 up = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).to(dev)
 dP, dK = up(P), up(K)
 dO = torch.empty(144, dtype=torch.uint8, device=dev)
-res = {}
+res = {}; phases = {}
 for spec in sys.argv[2:]:
     r, nr = map(int, spec.split(":"))
     best = None
@@ -28,4 +28,7 @@ for spec in sys.argv[2:]:
         e1.record(st); torch.cuda.synchronize()
         t = e0.elapsed_time(e1); best = t if best is None else min(best, t)
     res[spec] = best
-print(json.dumps({"log2n": lg, "ms": res}))
+    ph = (ctypes.c_float * 5)()
+    ctx.dev("b381_g1_msm_shard_phases_dev", dP.data_ptr(), dK.data_ptr(), ctypes.c_size_t(n), ctypes.c_int(r), ctypes.c_int(nr), dO.data_ptr(), ph)
+    phases[spec] = dict(zip(["sort", "chunk_sums", "chunk_fold", "bucket_reduce", "combine"], [round(float(x), 3) for x in ph]))
+print(json.dumps({"log2n": lg, "ms": res, "phases_ms": phases}))

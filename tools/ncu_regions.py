@@ -39,3 +39,10 @@ print("%-6s %-6s %7s %7s %7s %6s %6s %6s  mix" % ("start", "instrs", "KB", "exec
 for e, a, b, c, smp, ni, ls, w in out[:40]:
     print("%-6d %-6d %7.1f %7.2f %7.2f %6.1f %6.1f %6.1f  %s" % (a, b - a, (b - a) * 16 / 1024, 100 * e / tot, 100 * smp / tots, 100 * ni / max(smp, 1), 100 * ls / max(smp, 1),
           100 * w / max(smp, 1), " ".join("%s:%d" % kv for kv in c.most_common(5))))
+# hot set: how much static code holds 50 / 80 / 90 / 95 / 99 % of the executed instructions (the instruction-cache question)
+order = sorted(range(len(ex)), key=lambda i: -ex[i]); cum = 0.0; marks = [0.5, 0.8, 0.9, 0.95, 0.99]; mi = 0
+print("static instructions %d (%.1f KB), executed %.3e" % (len(ex), len(ex) * 16 / 1024, tot))
+for k, i in enumerate(order):
+    cum += ex[i]
+    while mi < len(marks) and cum >= marks[mi] * tot:
+        print("hot set: %2.0f %% of the executed instructions in %.1f KB" % (100 * marks[mi], (k + 1) * 16 / 1024)); mi += 1

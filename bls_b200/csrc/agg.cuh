@@ -21,7 +21,7 @@ namespace b381 {
 
 #define MSM_CHUNK 64u       // points per chunk partial sum
 #define MSM_SEG 16u         // buckets per running-sum segment
-#define MSM_FOLD_MAX 16u    // up to this many chunk partials per bucket (uniform scalars: 2-5) are added by one thread per bucket (k_msm_bucket_fold);
+#define MSM_FOLD_MAX 64u    // up to this many chunk partials per bucket (uniform scalars: 2-5) are added by one thread per bucket (k_msm_bucket_fold);
                             // beyond that (skewed scalars, up to every point in one bucket) the in-bucket tree rounds run first
 
 // ---- block tree over shared memory: the sum of every thread's acc ends up in thread 0 -------------

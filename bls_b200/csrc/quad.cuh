@@ -30,6 +30,9 @@
 #pragma once
 #include "pairing.cuh"
 
+#ifndef LANE_SQR_DOT2_MIN_BLOCKS
+#define LANE_SQR_DOT2_MIN_BLOCKS 800u   // 64-thread blocks in the grid (148 SMs x 5.4) from which the lane kernels square through the two-product body
+#endif
 namespace b381 {
 namespace quad {
 
@@ -174,13 +177,22 @@ HDN void q2_mul(qfp *r, const qfp *a, const qfp *b) {
     }
     *r = R;
 }
+#if !defined(__CUDA_ARCH__)
+inline bool &host_sqr_dot2() { static bool on = true; return on; }     // host emulation: which squaring form q2_sqr runs (tests flip it)
+#endif
 // r = a^2   (fq2.go:75-89: (a0 + a1)(a0 - a1) on lane 0, a1 (2 a0) on lane 1; the operand sums stay unreduced, below 2Q)
 HDN void q2_sqr(qfp *r, const qfp *a) {
 #ifndef B381_LANE_SQR_FPMUL
-    // a0 a0 + a1 (Q - a1) | a1 a0 + a0 a1 through the two-product body: 144 wide MACs more per squaring than the form below, but
-    // the plain multiplier (6 KB) leaves the hot set of the lane kernels, which sit at the instruction-cache limit: measured at
-    // 2^16 pairings, two lanes k_duo_final_exp 27.1 -> 25.8 ms, four lanes 33.5 / 39.8 -> 31.9 / 36.0 ms (profiles/r02_experiments.md)
-    q2_mul(r, a, a); return;
+    // On a loaded machine: a0 a0 + a1 (Q - a1) | a1 a0 + a0 a1 through the two-product body -- 144 wide MACs more per squaring than
+    // the form below, but the plain multiplier (6 KB) leaves the hot set of the lane kernels, which sit at the instruction-cache
+    // limit: at 2^16 pairings k_duo_final_exp 27.1 -> 25.8 ms, four lanes 33.5 / 39.8 -> 31.9 / 36.0 ms.  A batch that leaves
+    // the machine mostly empty is latency-bound and fetches do not contend, so it keeps the shorter form (64 pairings on four
+    // lanes: 7.29 ms against 7.49; profiles/r02_experiments.md).  The host emulation runs the form the test selects.
+#if defined(__CUDA_ARCH__)
+    if (gridDim.x >= LANE_SQR_DOT2_MIN_BLOCKS) { q2_mul(r, a, a); return; }
+#else
+    if (host_sqr_dot2()) { q2_mul(r, a, a); return; }
+#endif
 #endif
     qfp A = *a, AO, R;
     q_shfl(AO, A, 1);

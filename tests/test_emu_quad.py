@@ -11,10 +11,14 @@ from bls_b200 import hostgen as hg, layout as L
 U64 = np.uint64
 
 
-@pytest.fixture(scope="module")
-def emu():
+@pytest.fixture(scope="module", params=["sqr_dot2", "sqr_plain"])
+def emu(request):
+    """both forms of the lane Fq2 squaring (the kernels pick one by how full the machine is, quad.cuh::q2_sqr)"""
     import __graft_entry__ as g
-    return ctypes.CDLL(g.build_emu())
+    lib = ctypes.CDLL(g.build_emu())
+    lib.emu_set_lane_sqr_dot2(1 if request.param == "sqr_dot2" else 0)
+    yield lib
+    lib.emu_set_lane_sqr_dot2(1)
 
 
 def _p(a):

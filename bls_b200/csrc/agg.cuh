@@ -21,6 +21,7 @@ namespace b381 {
 
 #define MSM_CHUNK 64u       // points per chunk partial sum
 #define MSM_SEG 16u         // buckets per running-sum segment
+#define MSM_LANE_REDUCE_MAX_SEGS 8192u   // windows x segments on this rank up to which the G1 bucket reduction runs four lanes per segment
 #define MSM_FOLD_MAX 64u    // up to this many chunk partials per bucket (uniform scalars: 2-5) are added by one thread per bucket (k_msm_bucket_fold);
                             // beyond that (skewed scalars, up to every point in one bucket) the in-bucket tree rounds run first
 
@@ -263,37 +264,158 @@ template <class F> __global__ void __launch_bounds__(128) k_msm_bucket_fold(xyzz
     base[c0] = a;
 }
 
+// ---- G1 group law on a group of FOUR LANES holding the same operands ------------------------------------------------------
+// The reductions behind the chunk sums (bucket running sums, window sums, window shifts) are chains of dependent additions with
+// little parallel work: a thread advances one Fq multiplication per ~1 us, an XYZZ addition is 14 of them.  Four lanes run the
+// independent multiplications of an addition / doubling side by side (4 / 3 levels instead of 14 / 9) and exchange the results
+// by SHFL; every lane of the group ends with the same value, bit-identical to xyzz_add / xyzz_dbl (same formulas).
+struct lane_grp { unsigned sub, base, mask; };
+__device__ __forceinline__ lane_grp lane_group() {
+    const unsigned lane = threadIdx.x & 31u;
+    lane_grp g; g.sub = lane & 3u; g.base = lane & ~3u; g.mask = 0xFu << g.base; return g;
+}
+__device__ __forceinline__ void lane_pick(fp &r, unsigned sub, const fp &a0, const fp &a1, const fp &a2, const fp &a3) {
+#pragma unroll
+    for (int k = 0; k < 12; k++) r.l[k] = sub == 0 ? a0.l[k] : (sub == 1 ? a1.l[k] : (sub == 2 ? a2.l[k] : a3.l[k]));
+}
+__device__ __forceinline__ void lane_bcast(fp &r, const fp &v, const lane_grp &g, unsigned src) {
+#pragma unroll
+    for (int k = 0; k < 12; k++) r.l[k] = __shfl_sync(g.mask, v.l[k], g.base + src);
+}
+// p = 2p (dbl-2008-s-1 as xyzz_dbl_body): V = U^2 | M = X^2  ->  W = U V | S = X V | MM = (3M)^2 | ZZ3 = V ZZ  ->
+// W Y | 3M (S - X3) | W ZZZ
+__device__ __noinline__ void xyzz_dbl_lanes(xyzz<FpInl> &p) {
+    if (xyzz_is_inf(p)) return;
+    const lane_grp g = lane_group();
+    fp u, a, b, r, v, m, w, s, mm, zz3, t, wy, zzz3;
+    fp_add(u, p.y, p.y);
+    lane_pick(a, g.sub, u, p.x, u, p.x);
+    r = fp_mul_v(a, a);
+    lane_bcast(v, r, g, 0); lane_bcast(m, r, g, 1);
+    fp_add(t, m, m); fp_add(m, t, m);                  // 3 X^2
+    lane_pick(a, g.sub, u, p.x, m, v); lane_pick(b, g.sub, v, v, m, p.zz);
+    r = fp_mul_v(a, b);
+    lane_bcast(w, r, g, 0); lane_bcast(s, r, g, 1); lane_bcast(mm, r, g, 2); lane_bcast(zz3, r, g, 3);
+    fp_sub(mm, mm, s); fp_sub(mm, mm, s);              // X3
+    fp_sub(t, s, mm);
+    lane_pick(a, g.sub, w, m, w, w); lane_pick(b, g.sub, p.y, t, p.zzz, p.zzz);
+    r = fp_mul_v(a, b);
+    lane_bcast(wy, r, g, 0); lane_bcast(t, r, g, 1); lane_bcast(zzz3, r, g, 2);
+    p.x = mm; fp_sub(p.y, t, wy); p.zz = zz3; p.zzz = zzz3;
+}
+// p += q (add-2008-s as xyzz_add_body, same case split): U1 | U2 | S1 | S2  ->  PP | RR | ZZ1 ZZ2 | ZZZ1 ZZZ2  ->
+// PPP | Q | ZZ3  ->  R (Q - X3) | S1 PPP | ZZZ3
+__device__ __noinline__ void xyzz_add_lanes(xyzz<FpInl> &p, const xyzz<FpInl> &q) {
+    if (xyzz_is_inf(q)) return;
+    if (xyzz_is_inf(p)) { p = q; return; }
+    const lane_grp g = lane_group();
+    fp a, b, r, u1, u2, s1, s2, pp, rr, zz12, zzz12, ppp, qq, zz3, t, ya, yb, zzz3;
+    lane_pick(a, g.sub, p.x, q.x, p.y, q.y); lane_pick(b, g.sub, q.zz, p.zz, q.zzz, p.zzz);
+    r = fp_mul_v(a, b);
+    lane_bcast(u1, r, g, 0); lane_bcast(u2, r, g, 1); lane_bcast(s1, r, g, 2); lane_bcast(s2, r, g, 3);
+    fp_sub(u2, u2, u1);                                // P
+    fp_sub(s2, s2, s1);                                // R
+    if (fp_is_zero(u2)) {                              // the same on every lane of the group
+        if (fp_is_zero(s2)) xyzz_dbl_lanes(p); else xyzz_set_inf(p);
+        return;
+    }
+    lane_pick(a, g.sub, u2, s2, p.zz, p.zzz); lane_pick(b, g.sub, u2, s2, q.zz, q.zzz);
+    r = fp_mul_v(a, b);
+    lane_bcast(pp, r, g, 0); lane_bcast(rr, r, g, 1); lane_bcast(zz12, r, g, 2); lane_bcast(zzz12, r, g, 3);
+    lane_pick(a, g.sub, u2, u1, zz12, zz12);
+    r = fp_mul_v(a, pp);
+    lane_bcast(ppp, r, g, 0); lane_bcast(qq, r, g, 1); lane_bcast(zz3, r, g, 2);
+    fp_sub(t, rr, ppp); fp_sub(t, t, qq); fp_sub(t, t, qq);   // X3 = R^2 - PPP - 2Q
+    p.x = t;
+    fp_sub(t, qq, t);
+    lane_pick(a, g.sub, s2, s1, zzz12, zzz12); lane_pick(b, g.sub, t, ppp, ppp, ppp);
+    r = fp_mul_v(a, b);
+    lane_bcast(ya, r, g, 0); lane_bcast(yb, r, g, 1); lane_bcast(zzz3, r, g, 2);
+    fp_sub(p.y, ya, yb); p.zz = zz3; p.zzz = zzz3;
+}
+// p = k p, double-and-add MSB first from the top set bit (the value of xyzz_mul_small)
+__device__ void xyzz_mul_small_lanes(xyzz<FpInl> &p, uint32_t k) {
+    xyzz<FpInl> acc;
+    xyzz_set_inf(acc);
+#pragma unroll 1
+    for (int b = 31 - __clz(k | 1u); b >= 0; b--) {
+        xyzz_dbl_lanes(acc);
+        if ((k >> b) & 1) xyzz_add_lanes(acc, p);
+    }
+    p = acc;
+}
+
+// the G1 reductions below run on four lanes per unit of work
+template <class F> struct lane_shift { static constexpr bool value = false; };
+template <> struct lane_shift<FpInl> { static constexpr bool value = true; };
+
 // one thread per (window, segment of MSM_SEG buckets): sum_{d in segment} d * B[d]; chunk 0 of a bucket holds its sum
-template <class F> __global__ void __launch_bounds__(128) k_msm_segment_reduce(const xyzz<F> *__restrict__ chunks, const uint32_t *__restrict__ chunk_off,
+// LANES (G1 only): FOUR lanes per segment, see above; the grid is sized accordingly by msm_shard_dev.  The lane form shortens the
+// chain of a segment by a third but executes twice the instructions, so it is used when the reduction is latency-bound (few
+// windows on this rank: a bucket-sharded MSM, or a small one) -- measured at 2^22 points: two windows 1.20 -> 0.90 ms, sixteen
+// windows 1.52 -> 2.34 ms.
+template <class F, bool LANES> __global__ void __launch_bounds__(128) k_msm_segment_reduce(const xyzz<F> *__restrict__ chunks, const uint32_t *__restrict__ chunk_off,
                                                             msm_geom g, xyzz<F> *__restrict__ segsum) {
+    static_assert(!LANES || lane_shift<F>::value, "the lane form exists for G1");
     int j = blockIdx.y;
     uint32_t nseg = g.nb / MSM_SEG;
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nseg) return;
+    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) / (LANES ? 4u : 1u);
+    if (s >= nseg) return;                             // whole groups leave together (128 is a multiple of 4)
     const uint32_t *co = chunk_off + (size_t)j * (g.nb + 1);
     const xyzz<F> *base = chunks + (size_t)j * g.maxchunks;
     uint32_t lo = s * MSM_SEG, hi = lo + MSM_SEG;
     if (lo == 0) lo = 1;
     xyzz<F> running, acc;
     xyzz_set_inf(running); xyzz_set_inf(acc);
-    for (uint32_t d = hi; d-- > lo;) {
-        const uint32_t c0 = co[d];
-        if (co[d + 1] > c0) { xyzz<F> bsum = base[c0]; xyzz_add(running, bsum); }
-        xyzz_add(acc, running);
+    if constexpr (LANES) {
+#pragma unroll 1
+        for (uint32_t d = hi; d-- > lo;) {
+            const uint32_t c0 = co[d];
+            if (co[d + 1] > c0) { xyzz<F> bsum = base[c0]; xyzz_add_lanes(running, bsum); }
+            xyzz_add_lanes(acc, running);
+        }
+        if (lo > 1 && !xyzz_is_inf(running)) { xyzz_mul_small_lanes(running, lo - 1); xyzz_add_lanes(acc, running); }
+        if ((threadIdx.x & 3u) == 0) segsum[(size_t)j * nseg + s] = acc;
+    } else {
+        for (uint32_t d = hi; d-- > lo;) {
+            const uint32_t c0 = co[d];
+            if (co[d + 1] > c0) { xyzz<F> bsum = base[c0]; xyzz_add(running, bsum); }
+            xyzz_add(acc, running);
+        }
+        if (lo > 1 && !xyzz_is_inf(running)) { xyzz_mul_small(running, lo - 1); xyzz_add(acc, running); }
+        segsum[(size_t)j * nseg + s] = acc;
     }
-    if (lo > 1 && !xyzz_is_inf(running)) { xyzz_mul_small(running, lo - 1); xyzz_add(acc, running); }
-    segsum[(size_t)j * nseg + s] = acc;
 }
 
 // one block per window: winsum[j] = sum of its segment sums
-template <class F> __global__ void __launch_bounds__(128) k_msm_window_sum(const xyzz<F> *__restrict__ segsum, uint32_t nseg, xyzz<F> *__restrict__ winsum) {
+// (LANES: launched with 512 threads = 128 groups of four lanes; otherwise 128 threads)
+template <class F, bool LANES> __global__ void __launch_bounds__(LANES ? 512 : 128) k_msm_window_sum(const xyzz<F> *__restrict__ segsum, uint32_t nseg, xyzz<F> *__restrict__ winsum) {
     __shared__ xyzz<F> sm[128];
     int j = blockIdx.x;
     xyzz<F> acc;
     xyzz_set_inf(acc);
-    for (uint32_t s = threadIdx.x; s < nseg; s += 128) { xyzz<F> q = segsum[(size_t)j * nseg + s]; xyzz_add(acc, q); }
-    block_reduce_xyzz<F, 128>(acc, sm);
-    if (threadIdx.x == 0) winsum[j] = acc;
+    if constexpr (LANES) {
+        const unsigned grp = threadIdx.x >> 2, sub = threadIdx.x & 3u;
+#pragma unroll 1
+        for (uint32_t s = grp; s < nseg; s += 128) { xyzz<F> q = segsum[(size_t)j * nseg + s]; xyzz_add_lanes(acc, q); }
+        if (sub == 0) sm[grp] = acc;
+        __syncthreads();
+#pragma unroll 1
+        for (unsigned w = 64; w > 0; w >>= 1) {
+            if (grp < w) {                             // whole groups (and, from w = 8 down, part of one warp) take the branch together
+                xyzz<F> a = sm[grp], b = sm[grp + w];
+                __syncwarp(0xFu << (threadIdx.x & 28u));   // the four lanes hold their copies before lane 0 overwrites the slot
+                xyzz_add_lanes(a, b);
+                if (sub == 0) sm[grp] = a;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) winsum[j] = sm[0];
+    } else {
+        for (uint32_t s = threadIdx.x; s < nseg; s += 128) { xyzz<F> q = segsum[(size_t)j * nseg + s]; xyzz_add(acc, q); }
+        block_reduce_xyzz<F, 128>(acc, sm);
+        if (threadIdx.x == 0) winsum[j] = acc;
+    }
 }
 
 // The window shift 2^(c w) is a chain of up to 240 doublings, the one serial stretch of the MSM (1.8 ms on one thread: 7.9 us per
@@ -335,8 +457,6 @@ __device__ __noinline__ void jac_dbl_chain_lanes(fp &X, fp &Y, fp &Z, int shifts
         fp_sub(Y, r, C);                                        // Y3 = E (D - X3) - 8C
     }
 }
-template <class F> struct lane_shift { static constexpr bool value = false; };
-template <> struct lane_shift<FpInl> { static constexpr bool value = true; };
 
 // window j is shifted to its weight 2^(c * w_j) -- G1: by the four lanes 4j .. 4j+3 together, otherwise by thread j --, then a
 // tree adds the windows; thread 0 writes the result: normalised (z = 1) for a complete MSM, plain Jacobian for a bucket-sharded partial

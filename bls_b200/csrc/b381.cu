@@ -1204,10 +1204,21 @@ static int msm_shard_dev(b381_ctx *ctx, const APOD *d_p, const b381_scalar *d_k,
         dim3 fg(grid_for(g.nb, 128), g.nw);
         k_msm_bucket_fold<F><<<fg, 128, 0, ctx->stream>>>(chunks, coff, g, maxch);
         ctx->launches++;
-        dim3 sg(grid_for(nseg, 128), g.nw);
         MSM_MARK(3);
-        k_msm_segment_reduce<F><<<sg, 128, 0, ctx->stream>>>(chunks, coff, g, seg);
-        k_msm_window_sum<F><<<g.nw, 128, 0, ctx->stream>>>(seg, nseg, win);
+        bool lanes = false;
+        if constexpr (lane_shift<F>::value) lanes = (size_t)g.nw * nseg <= MSM_LANE_REDUCE_MAX_SEGS;   // latency-bound: four lanes per segment
+        if constexpr (lane_shift<F>::value) {
+            if (lanes) {
+                dim3 sg(grid_for((size_t)nseg * 4, 128), g.nw);
+                k_msm_segment_reduce<F, true><<<sg, 128, 0, ctx->stream>>>(chunks, coff, g, seg);
+                k_msm_window_sum<F, true><<<g.nw, 512, 0, ctx->stream>>>(seg, nseg, win);
+            }
+        }
+        if (!lanes) {
+            dim3 sg(grid_for(nseg, 128), g.nw);
+            k_msm_segment_reduce<F, false><<<sg, 128, 0, ctx->stream>>>(chunks, coff, g, seg);
+            k_msm_window_sum<F, false><<<g.nw, 128, 0, ctx->stream>>>(seg, nseg, win);
+        }
         ctx->launches += 2;
         MSM_MARK(4);
     } else {

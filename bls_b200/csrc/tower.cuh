@@ -227,6 +227,17 @@ HD void fp2_mul_nr(fp2 &r, const fp2 &a) { fp2_mul_nr_p(&r, &a); }
 // r = a * b   (fq2.go:116-130: same value; the two rows are two-product dot products with one reduction each,
 // 888 wide MACs and no Karatsuba fix-up additions instead of 900 + five additions)
 HDN void fp2_mul(fp2 *r, const fp2 *a, const fp2 *b) {
+#ifdef B381_FP2_MUL_KARATSUBA
+    {   // A/B: three plain products (the two-product body leaves the hot instruction set); measured slower, profiles/r02_experiments.md
+        fp a0 = a->c0, a1 = a->c1, b0 = b->c0, b1v = b->c1, v0, v1, s, t;
+        fp_add_nr(s, a0, a1); fp_add_nr(t, b0, b1v);
+        fp_mul(v0, a0, b0); fp_mul(v1, a1, b1v); fp_mul(s, s, t);
+        fp_sub(s, s, v0); fp_sub(s, s, v1);
+        fp_sub(v0, v0, v1);
+        r->c0 = v0; r->c1 = s;
+        return;
+    }
+#endif
     fp nb1, b1 = b->c1, c0;
     fp_qminus(nb1, b1);
     fp_dot2_p(&c0, &a->c0, &b->c0, &a->c1, &nb1);      // c0 is a temporary: r may alias a or b
@@ -235,6 +246,9 @@ HDN void fp2_mul(fp2 *r, const fp2 *a, const fp2 *b) {
 }
 // r = a^2   (fq2.go:75-89; complex squaring, 2 Fq mul; the operand sums stay unreduced, below 2Q)
 HDN void fp2_sqr(fp2 *r, const fp2 *a) {
+#ifdef B381_FP2_SQR_DOT2
+    { fp2_mul(r, a, a); return; }                      // A/B: the plain multiplier leaves the hot instruction set (+288 wide MACs per squaring)
+#endif
     fp a0 = a->c0, a1 = a->c1, s, d, na1, t;
     fp_add_nr(s, a0, a1);
     fp_qminus(na1, a1);

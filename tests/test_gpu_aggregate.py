@@ -159,6 +159,33 @@ def test_g1_msm_bucket_sharded(ctx, orc, nranks):
     assert got.tobytes() == ctx.g1_msm(P, K).tobytes()
 
 
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_g1_msm_exceptional_cases_in_the_reductions(ctx, orc, nranks):
+    """bucket sums that are EQUAL (the running sums of the bucket reduction must double, g1.go:506-509) or OPPOSITE (they pass
+    through infinity), in every window a 255-bit scalar touches: the lane-cooperative additions of the latency-bound reduction
+    (small and bucket-sharded MSMs) and the one-thread-per-segment form both take these branches"""
+    P = hg.g1_mul(0xABCDEF12345); Q = hg.g1_mul(0x1234567)
+    pts = np.concatenate([P, P, hg.g1_neg(P), Q, Q, Q, hg.g1_neg(Q), P])
+    rng = np.random.RandomState(3)
+    ks = [5, 3, 4, 7, 6, 2, 6, 1]                                       # window 0: B5 = P, B3 = P, B4 = -P, B7 = B6... = Q, -Q + Q
+    top = [int(x) for x in rng.randint(1, 1 << 30, size=8)]
+    vals = []
+    for i, k in enumerate(ks):                                          # the same small digits again in a high window + noise between
+        vals.append(k | (top[i % 2] << 64) | (k << 200))
+    K = np.concatenate([L.scalar_from_int(v % L.R_ORDER).reshape(1, 4) for v in vals])
+    want = orc.g1_msm_naive(pts, K, threads=2)
+    parts = np.concatenate([ctx.g1_msm_shard(pts, K, r, nranks) for r in range(nranks)])
+    got = ctx.g1_fold(parts)
+    assert _same_point(orc, orc.g1, got, want)
+    assert got.tobytes() == ctx.g1_msm(pts, K).tobytes()
+    # many copies: every bucket of a window holds the same point sum
+    n = 3000
+    same = np.resize(P, n)
+    K2, _ = hg.splitmix_scalars(11, n)
+    parts = np.concatenate([ctx.g1_msm_shard(same, K2, r, nranks) for r in range(nranks)])
+    assert _same_point(orc, orc.g1, ctx.g1_fold(parts), orc.g1_msm_naive(same, K2, threads=8))
+
+
 def _attestations(orc, nreg, natt, committee, nmsg, seed):
     """registry of pk_i = sk_i G1 with sk_i = s + i d; messages as points H_j = h_j G2 (stand-ins for
     HashG2WithDomain outputs, which the Go host computes); sig_a = (sum of the committee's sk) * H_j"""

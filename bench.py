@@ -225,6 +225,37 @@ def aggregate_extras(ctx, stream, dev, rank, world, torch, np, imad_peak):
         "roofline": {"kernels": "k_attest_pairs + k_miller_loop2 + k_final_exp_is_one", "fq_mul_per_attestation": w_att,
                      "achieved": natt * w_att * MACS_PER_FQ_MUL / (t_att * 1e-3) / 1e12, "peak": imad_peak / 1e12,
                      "unit": "T wide-MAC/s", "frac": natt * w_att * MACS_PER_FQ_MUL / (t_att * 1e-3) / imad_peak}}
+    # (b'') the same attestation batch as ONE boolean: random linear combination grouped by message (nmsg + 1 Miller loops and one
+    # final exponentiation per batch; what scales with the batch is the committee sums, one 64-bit scalar multiplication per
+    # attestation, the group-by-message sum and a 64-bit-weight G2 MSM).  Timed on the all-valid batch (must be accepted); the
+    # batch with the corrupted template must be rejected.
+    sig_ok = []
+    for t in range(ntmpl):
+        sk = sum(s0 + int(i) * d0 for i in tk[t]) % L.R_ORDER
+        sig_ok.append(hg.g2_mul(sk * hs[t % 8]))
+    dSigOk = up(np.tile(np.concatenate(sig_ok), natt // ntmpl))
+    wts = np.zeros((natt, 4), np.uint64)
+    wts[:, 0] = np.random.Generator(np.random.PCG64(7 + rank)).integers(1, 1 << 64, size=natt, dtype=np.uint64)
+    dW = up(wts)
+    dOk1 = torch.zeros(1, dtype=torch.uint8, device=dev)
+    ctx.call("b381_set_rlc_weight_bits", ctypes.c_int(64))
+
+    def att_rlc(sig_buf):
+        ctx.dev("b381_verify_aggregate_common_rlc_dev", dA[0].data_ptr(), dA[1].data_ptr(), dA[2].data_ptr(), sig_buf.data_ptr(), dA[4].data_ptr(),
+                dA[5].data_ptr(), dW.data_ptr(), ctypes.c_size_t(natt), ctypes.c_size_t(keys.size), ctypes.c_size_t(Hs.size), dOk1.data_ptr())
+    att_rlc(dA[3]); torch.cuda.synchronize()
+    assert int(dOk1.item()) == 0, "the batch with corrupted attestations must be rejected"
+    t_rlc = timed(lambda: att_rlc(dSigOk), reps=3)
+    assert int(dOk1.item()) == 1, "the all-valid attestation batch must be accepted"
+    tr = torch.tensor([t_rlc], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+    out["attestation_batch_2^15_x_128_keys_one_boolean"] = {
+        "ms": float(tr.item()), "aggregate_verifies_per_s": world * natt / (float(tr.item()) * 1e-3), "distinct_messages": int(Hs.size),
+        "weight_bits": 64, "note": "b381_verify_aggregate_common_rlc_dev: batch verification by a random linear combination grouped by message "
+                                   "(soundness error 2^-64 per batch); on rejection the per-attestation call above locates the offenders"}
+    ctx.call("b381_set_rlc_weight_bits", ctypes.c_int(255))
+    del dSigOk, dW
     # (b') g1pubs.VerifyWithDomain from wire bytes: 2^16 (public key, message hash, signature) triples per GPU; deserialisation,
     # subgroup checks, HashG2WithDomain and the 2-pair check all on the device.  Inputs are made with the engine itself
     # (PrivToPub / SignWithDomain / Serialize batches, each parity-tested against the oracle); one triple in 64 is corrupted.

@@ -213,6 +213,25 @@ class Ctx:
                   ctypes.c_size_t(msg_hash.size), dok.ptr)
         return self.from_device(dok, np.uint8, n)
 
+    def verify_aggregate_common_rlc(self, registry, key_idx, key_off, sig, msg_hash, msg_idx, weights=None):
+        """ONE boolean for a batch of VerifyAggregateCommon checks (random linear combination grouped by message) --
+        b381_verify_aggregate_common_rlc_dev.  weights: one non-zero 64-bit value per attestation; None draws them here."""
+        registry = np.ascontiguousarray(registry, dtype=L.G1_AFFINE)
+        key_idx = np.ascontiguousarray(key_idx, dtype=np.uint32); key_off = np.ascontiguousarray(key_off, dtype=np.uint32)
+        sig = np.ascontiguousarray(sig, dtype=L.G2_AFFINE); msg_hash = np.ascontiguousarray(msg_hash, dtype=L.G2_AFFINE)
+        msg_idx = np.ascontiguousarray(msg_idx, dtype=np.uint32)
+        n = sig.size
+        assert key_off.size == n + 1 and msg_idx.size == n
+        weights = self.rlc_weights(n) if weights is None else np.asarray(weights, np.uint64)
+        assert weights.size == n, "one 64-bit weight per attestation"
+        self.set_rlc_weight_bits(64)
+        r = np.zeros((n, 4), np.uint64); r[:, 0] = weights.reshape(-1)
+        bufs = [self.to_device(a) for a in (registry, key_idx, key_off, sig, msg_hash, msg_idx, r)]
+        dok = self.dev_empty(1)
+        self.call("b381_verify_aggregate_common_rlc_dev", *[b.ptr for b in bufs], ctypes.c_size_t(n), ctypes.c_size_t(registry.size),
+                  ctypes.c_size_t(msg_hash.size), dok.ptr)
+        return bool(self.from_device(dok, np.uint8, 1)[0])
+
     # -- wire formats and scalar multiplication (csrc/codec.cuh) --------------------------------------------------
     def _decompress(self, name, data, nbytes, dtype, check_subgroup):
         raw = np.frombuffer(bytes(data), np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, np.uint8).reshape(-1)

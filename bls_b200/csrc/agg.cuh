@@ -20,8 +20,11 @@ namespace b381 {
 #if defined(__CUDACC__)
 
 #define MSM_CHUNK 64u       // points per chunk partial sum
-#define MSM_SEG 16u         // buckets per running-sum segment
+#define MSM_SEG 16u         // buckets per running-sum segment (the padding of the bucket count; msm_geom::seg is the length in use)
+#define MSM_SEG_SMALL 4u    // ... of a small MSM (MSM_SMALL_CHUNKS): its bucket reduction is one dependent chain per segment, shorter segments shorten it
 #define MSM_LANE_REDUCE_MAX_SEGS 8192u   // windows x segments on this rank up to which the G1 bucket reduction runs four lanes per segment
+#define MSM_SMALL_CHUNKS 32768u // an MSM with at most this many chunk partials in all takes the tree rounds beyond MSM_FOLD_SMALL partials per bucket:
+#define MSM_FOLD_SMALL 4u       // its rounds are small launches, while a serial fold of a few big buckets (group-by sums, the short top window of 64-bit weights) is one long chain
 #define MSM_FOLD_MAX 64u    // up to this many chunk partials per bucket (uniform scalars: 2-5) are added by one thread per bucket (k_msm_bucket_fold);
                             // beyond that (skewed scalars, up to every point in one bucket) the in-bucket tree rounds run first
 
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(128) k_g1_fold(const g1_jac_pod *__restrict__ 
 
 // ---- Pippenger MSM over G1 ------------------------------------------------------------------------
 // windows handled by a call: w = w0 + j * wstep, j < nw (wstep = number of ranks when bucket-sharded)
-struct msm_geom { int c, w0, wstep, nw; uint32_t nb; uint32_t maxchunks; size_t n; };
+struct msm_geom { int c, w0, wstep, nw; uint32_t nb; uint32_t maxchunks; uint32_t seg; size_t n; };   // seg: buckets per running-sum segment
 
 __global__ void k_msm_hist(const uint64_t *__restrict__ k, msm_geom g, uint32_t *__restrict__ count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -229,8 +232,8 @@ template <class F, class APOD> __global__ void __launch_bounds__(128) k_msm_chun
 // uniform scalars need two rounds, the launches of the remaining ones (a single bucket may hold every point) exit at once.
 template <class F> __global__ void __launch_bounds__(128) k_msm_chunk_tree(xyzz<F> *__restrict__ chunks, const uint32_t *__restrict__ chunk_bucket,
                                                         const uint32_t *__restrict__ chunk_off, msm_geom g, int r,
-                                                        const uint32_t *__restrict__ maxch) {
-    if ((1u << r) >= *maxch || *maxch <= MSM_FOLD_MAX) return;           // few chunks per bucket: k_msm_bucket_fold adds them
+                                                        const uint32_t *__restrict__ maxch, uint32_t fold_max) {
+    if ((1u << r) >= *maxch || *maxch <= fold_max) return;               // few chunks per bucket: k_msm_bucket_fold adds them
     int j = blockIdx.y;
     const uint32_t *co = chunk_off + (size_t)j * (g.nb + 1);
     const uint32_t nchunks = co[g.nb];
@@ -249,8 +252,8 @@ template <class F> __global__ void __launch_bounds__(128) k_msm_chunk_tree(xyzz<
 // only every second / fourth lane works and every round is a launch over all chunks (4.0 ms at 2^22 points); here all lanes of a
 // warp fold a similar, small number of partials.
 template <class F> __global__ void __launch_bounds__(128) k_msm_bucket_fold(xyzz<F> *__restrict__ chunks, const uint32_t *__restrict__ chunk_off, msm_geom g,
-                                                         const uint32_t *__restrict__ maxch) {
-    if (*maxch > MSM_FOLD_MAX || *maxch < 2) return;                      // the tree rounds ran (or there is nothing to add)
+                                                         const uint32_t *__restrict__ maxch, uint32_t fold_max) {
+    if (*maxch > fold_max || *maxch < 2) return;                          // the tree rounds ran (or there is nothing to add)
     int j = blockIdx.y;
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= g.nb) return;
@@ -358,12 +361,12 @@ template <class F, bool LANES> __global__ void __launch_bounds__(128) k_msm_segm
                                                             msm_geom g, xyzz<F> *__restrict__ segsum) {
     static_assert(!LANES || lane_shift<F>::value, "the lane form exists for G1");
     int j = blockIdx.y;
-    uint32_t nseg = g.nb / MSM_SEG;
+    uint32_t nseg = g.nb / g.seg;
     uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) / (LANES ? 4u : 1u);
     if (s >= nseg) return;                             // whole groups leave together (128 is a multiple of 4)
     const uint32_t *co = chunk_off + (size_t)j * (g.nb + 1);
     const xyzz<F> *base = chunks + (size_t)j * g.maxchunks;
-    uint32_t lo = s * MSM_SEG, hi = lo + MSM_SEG;
+    uint32_t lo = s * g.seg, hi = lo + g.seg;
     if (lo == 0) lo = 1;
     xyzz<F> running, acc;
     xyzz_set_inf(running); xyzz_set_inf(acc);
@@ -558,6 +561,47 @@ __global__ void __launch_bounds__(128) k_attest_pairs(const g1_affine_pod *__res
     Q[2 * a] = sig[a];
     Q[2 * a + 1] = msg_hash[msg_idx[a] < nmsg ? msg_idx[a] : 0];
     valid[a] = (good && !inf) ? 1 : 0;
+}
+// ---- attestation-level random-linear-combination check: helpers ---------------------------------------------------------------
+// the group key of attestation a as a scalar: message index + 1 (0 = no bucket; an index outside the table is flagged by k_attest_pairs)
+__global__ void k_group_keys(const uint32_t *__restrict__ msg_idx, size_t n, size_t nmsg, uint64_t *__restrict__ k) {
+    size_t a = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const uint32_t m = msg_idx[a];
+    k[4 * a] = m < nmsg ? (uint64_t)m + 1 : 0; k[4 * a + 1] = 0; k[4 * a + 2] = 0; k[4 * a + 3] = 0;
+}
+// any attestation that k_attest_pairs rejected, or a weight that is zero or wider than `bits`, makes the whole check false
+__global__ void k_attest_rlc_valid(const uint8_t *__restrict__ valid, const uint64_t *__restrict__ r, int bits, size_t n, uint32_t *__restrict__ any_bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t any = 0, over = 0;
+    for (int l = 0; l < 4; l++) {
+        uint64_t w = r[4 * i + l];
+        any |= w;
+        int lo = 64 * l;
+        if (bits <= lo) over |= w; else if (bits < lo + 64) over |= w >> (bits - lo);
+    }
+    if (!valid[i] || any == 0 || over != 0) atomicOr(any_bad, 1u);
+}
+// pair m of the check: (-(sum of bucket m + 1), H_m); the buckets hold sums of r_a (-pk_a), so the pair is (sum r_a pk_a, H_m).
+// A message no attestation refers to gives the point at infinity (its pair contributes the factor 1).
+__global__ void __launch_bounds__(64) k_group_pairs(const xyzz<FpInl> *__restrict__ chunks, const uint32_t *__restrict__ chunk_off, uint32_t nmsg,
+                                                    const g2_affine_pod *__restrict__ msg_hash, g1_affine_pod *__restrict__ P,
+                                                    g2_affine_pod *__restrict__ Q) {
+    uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nmsg) return;
+    xyzz<FpInl> acc;
+    const uint32_t c0 = chunk_off[m + 1];
+    if (chunk_off[m + 2] > c0) acc = chunks[c0]; else xyzz_set_inf(acc);
+    fp ox, oy, oz;
+    xyzz_to_jac_normalised(ox, oy, oz, acc);
+    const bool inf = fp_is_zero(oz);
+    fp_neg(oy, oy);
+    if (inf) { fp_set_zero(ox); fp_set_one(oy); }     // G1AffineZero = (0, 1, true), g1.go:22
+    fp_store_u64(P[m].x, ox); fp_store_u64(P[m].y, oy);
+    P[m].inf = inf ? 1 : 0;
+    for (int i = 0; i < 7; i++) P[m].pad[i] = 0;
+    Q[m] = msg_hash[m];
 }
 // ok[i] &= valid[i]
 __global__ void k_and_bytes2(uint8_t *__restrict__ ok, const uint8_t *__restrict__ valid, size_t n) {

@@ -338,8 +338,8 @@ struct b381_ctx {
     uint64_t launches;
     char err[256];
     // grow-only device scratch
-    void *scratch[32];
-    size_t scratch_bytes[32];
+    void *scratch[40];
+    size_t scratch_bytes[40];
     // warp-cooperative VM programs resident on the device (csrc/vm.cuh)
     struct { uint4 *code, *consts; int lanes, nsteps, nslots, spill_fq; } vm[3];
     int path;                // -1 by batch size, 0 one pairing per thread, 1 warp-cooperative VM, 2 four lanes per pairing
@@ -366,7 +366,8 @@ enum { VM_ML1 = 0, VM_FE_A = 1, VM_FE_C = 2 };
 //   15-18  wire-level verify: decoded keys, decoded signatures, message points, status + validity bytes
 //   19, 20  wire-level verify host staging (inputs, verdicts)                       21  largest group size (tree product)
 //   22  group offsets of the random-linear-combination check                        23  its G2 sum + "any invalid" flag
-//   24  validity bytes of an attestation batch        25, 26  group offsets / verdicts of b381_pairing_product_is_one        27-31  prepared G2 points
+//   24  validity bytes of an attestation batch        25, 26  group offsets / verdicts of b381_pairing_product_is_one        27, 28  prepared G2 points
+//   32-35  attestation-level random-linear-combination check: weighted keys, group keys as scalars, per-message pairs (G1, G2)
 static int scratch_get(b381_ctx *ctx, int slot, size_t bytes, void **out) {
     if (ctx->scratch_bytes[slot] < bytes) {
         if (ctx->scratch[slot]) {
@@ -490,7 +491,7 @@ void b381_free(b381_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 32; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < 40; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     for (int i = 0; i < 3; i++) { if (ctx->vm[i].code) cudaFree(ctx->vm[i].code); if (ctx->vm[i].consts) cudaFree(ctx->vm[i].consts); }
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -1156,22 +1157,28 @@ static inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 // weights of the random-linear-combination check): only ceil(nbits / c) windows are formed
 // phase_ms (optional, host, 5 floats): sort (histogram + scan + scatter), chunk sums, chunk tree, bucket reduction (segments +
 // window sums), window combine -- CUDA events on the stream; asking for them synchronises the stream at the end
+// buckets (optional): stop after the bucket sums of ONE window of group_c bits over the low bits of the scalars and hand them
+// out (chunk 0 of bucket d, at chunks[chunk_off[d]] when chunk_off[d + 1] > chunk_off[d], holds the sum of the points whose
+// scalar is d): the group-by-key sum the attestation-level random-linear-combination check needs (key = message index + 1).
+template <class F> struct msm_buckets { const xyzz<F> *chunks; const uint32_t *chunk_off; msm_geom g; };
 template <class F, class APOD, class JPOD>
 static int msm_shard_dev(b381_ctx *ctx, const APOD *d_p, const b381_scalar *d_k, size_t n, int nbits, int rank, int nranks, JPOD *d_partial,
-                         float *phase_ms = nullptr) {
-    if (!ctx || !d_partial || (n && (!d_p || !d_k)) || nranks < 1 || rank < 0 || rank >= nranks || n > 0x7FFFFFF0u || nbits < 1 || nbits > 255)
+                         float *phase_ms = nullptr, int group_c = 0, msm_buckets<F> *buckets = nullptr) {
+    if (!ctx || (!d_partial && !buckets) || (n && (!d_p || !d_k)) || nranks < 1 || rank < 0 || rank >= nranks || n > 0x7FFFFFF0u || nbits < 1 ||
+        nbits > 255 || (buckets && (group_c < 2 || group_c > 24 || phase_ms)))
         return B381_ERR_ARG;                         // (bit 31 of an index entry is the sign of the digit)
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (phase_ms) for (int i = 0; i < 6; i++) CK(cudaEventCreate(&ev[i]));
 #define MSM_MARK(i) do { if (phase_ms) CK(cudaEventRecord(ev[i], ctx->stream)); } while (0)
     bool whole = nranks == 1;
     msm_geom g;
-    g.c = msm_window_bits(n);
-    int W = msm_signed_windows(nbits, g.c);          // signed digits: 2^(c-1) buckets per window, one more bit for the last carry
+    g.c = buckets ? group_c : msm_window_bits(n);
+    int W = buckets ? 1 : msm_signed_windows(nbits, g.c);   // signed digits: 2^(c-1) buckets per window, one more bit for the last carry
     g.w0 = rank; g.wstep = nranks; g.nw = rank < W ? (W - rank + nranks - 1) / nranks : 0;
     g.nb = (1u << (g.c - 1)) + MSM_SEG; g.n = n;     // digit magnitudes 1 .. 2^(c-1), rounded up to whole segments
     g.maxchunks = (uint32_t)(n / MSM_CHUNK) + g.nb + 2;      // runs of the sorted list + one more chunk per bucket boundary
-    uint32_t nseg = g.nb / MSM_SEG;
+    g.seg = (size_t)g.maxchunks * (size_t)(g.nw > 0 ? g.nw : 1) <= MSM_SMALL_CHUNKS ? MSM_SEG_SMALL : MSM_SEG;   // (MSM_SEG_SMALL divides MSM_SEG)
+    uint32_t nseg = g.nb / g.seg;
     int nw = g.nw > 0 ? g.nw : 1;
     // carve one scratch block
     size_t o_count = 0, o_boff = o_count + up256((size_t)nw * g.nb * 4), o_coff = o_boff + up256((size_t)nw * (g.nb + 1) * 4);
@@ -1196,14 +1203,16 @@ static int msm_shard_dev(b381_ctx *ctx, const APOD *d_p, const b381_scalar *d_k,
         k_msm_chunk_sum<F><<<cg, 128, 0, ctx->stream>>>(d_p, idx, g, boff, coff, chunks, cb);
         ctx->launches += 4;
         MSM_MARK(2);
+        const uint32_t fold_max = (size_t)g.maxchunks * (size_t)g.nw <= MSM_SMALL_CHUNKS ? MSM_FOLD_SMALL : MSM_FOLD_MAX;
         dim3 tg((unsigned)ctx->sms * 8u < cg.x ? (unsigned)ctx->sms * 8u : cg.x, g.nw);
         for (int r = 0; ((size_t)MSM_CHUNK << r) < n + MSM_CHUNK; r++) {
-            k_msm_chunk_tree<F><<<tg, 128, 0, ctx->stream>>>(chunks, cb, coff, g, r, maxch);
+            k_msm_chunk_tree<F><<<tg, 128, 0, ctx->stream>>>(chunks, cb, coff, g, r, maxch, fold_max);
             ctx->launches++;
         }
         dim3 fg(grid_for(g.nb, 128), g.nw);
-        k_msm_bucket_fold<F><<<fg, 128, 0, ctx->stream>>>(chunks, coff, g, maxch);
+        k_msm_bucket_fold<F><<<fg, 128, 0, ctx->stream>>>(chunks, coff, g, maxch, fold_max);
         ctx->launches++;
+        if (buckets) { buckets->chunks = chunks; buckets->chunk_off = coff; buckets->g = g; CK(cudaGetLastError()); return B381_OK; }
         MSM_MARK(3);
         bool lanes = false;
         if constexpr (lane_shift<F>::value) lanes = (size_t)g.nw * nseg <= MSM_LANE_REDUCE_MAX_SEGS;   // latency-bound: four lanes per segment
@@ -1222,6 +1231,11 @@ static int msm_shard_dev(b381_ctx *ctx, const APOD *d_p, const b381_scalar *d_k,
         ctx->launches += 2;
         MSM_MARK(4);
     } else {
+        if (buckets) {                               // no points: every bucket is empty
+            CK(cudaMemsetAsync(base, 0, o_idx, ctx->stream));
+            buckets->chunks = chunks; buckets->chunk_off = coff; buckets->g = g;
+            return B381_OK;
+        }
         g.nw = 0;
         for (int i = 0; i < 5; i++) MSM_MARK(i);
     }
@@ -1375,6 +1389,68 @@ static int verify_wire_dev(b381_ctx *ctx, int mode, const uint8_t *d_pub, const 
     rc = pairs2_product_is_one(ctx, (b381_g1_affine *)P, (b381_g2_affine *)Q, n, (uint32_t *)off, d_ok);
     if (rc) return rc;
     k_and_bytes<<<grid_for(n, 256), 256, 0, ctx->stream>>>(d_ok, valid, n);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B381_OK;
+}
+// ---- attestation batches as ONE random-linear-combination check, grouped by message -------------------------------------------
+// ok = [ e(-G1One, sum_a r_a sig_a) * prod_m e(sum_{a: msg(a) = m} r_a pk_a, H_m) == 1 ]: with independent random r_a this accepts
+// iff every e(G1One, sig_a) == e(pk_a, H_msg(a)) holds (VerifyAggregateCommon, g1pubs/bls.go:287-297), except with probability
+// ~2^-bits(r).  nmsg + 1 Miller loops and one final exponentiation for the whole batch instead of two loops and one
+// exponentiation per attestation; the work that scales with the batch is the committee sums, one short scalar multiplication
+// per attestation, a group-by-message sum (the bucket machinery of the MSM, keyed by message) and a 64-bit-weight G2 MSM.
+extern "C" int b381_verify_aggregate_common_rlc_dev(b381_ctx *ctx, const b381_g1_affine *d_registry, const uint32_t *d_key_idx,
+                                                    const uint32_t *d_key_off, const b381_g2_affine *d_sig, const b381_g2_affine *d_msg_hash,
+                                                    const uint32_t *d_msg_idx, const b381_scalar *d_r, size_t nattest, size_t nkeys, size_t nmsg,
+                                                    uint8_t *d_ok) {
+    if (!ctx || !d_ok || nattest > 0x7FFFFFF0u || nmsg > (1u << 22)) return B381_ERR_ARG;
+    if (!nattest) { CK(cudaMemsetAsync(d_ok, 1, 1, ctx->stream)); return B381_OK; }       // the empty product
+    if (!d_registry || !d_key_idx || !d_key_off || !d_sig || !d_msg_hash || !d_msg_idx || !d_r || !nkeys || !nmsg) return B381_ERR_ARG;
+    const int rlc_bits = ctx->rlc_bits;
+    void *P2, *Q2, *off2, *valid, *W, *keys, *P, *Q, *S, *off, *bad;
+    int rc = scratch_get(ctx, 24, nattest, &valid); if (rc) return rc;
+    rc = scratch_get(ctx, 2, 2 * nattest * sizeof(b381_g1_affine), &P2); if (rc) return rc;
+    rc = scratch_get(ctx, 3, 2 * nattest * sizeof(b381_g2_affine), &Q2); if (rc) return rc;
+    rc = scratch_get(ctx, 6, (nattest + 1) * sizeof(uint32_t), &off2); if (rc) return rc;
+    rc = scratch_get(ctx, 32, nattest * sizeof(b381_g1_affine), &W); if (rc) return rc;
+    rc = scratch_get(ctx, 33, nattest * sizeof(b381_scalar), &keys); if (rc) return rc;
+    rc = scratch_get(ctx, 34, (nmsg + 1) * sizeof(b381_g1_affine), &P); if (rc) return rc;
+    rc = scratch_get(ctx, 35, (nmsg + 1) * sizeof(b381_g2_affine), &Q); if (rc) return rc;
+    rc = scratch_get(ctx, 23, sizeof(b381_g2_jac) + 64, &S); if (rc) return rc;
+    rc = scratch_get(ctx, 22, 2 * sizeof(uint32_t), &off); if (rc) return rc;
+    bad = (char *)S + sizeof(b381_g2_jac);
+    CK(cudaMemsetAsync(bad, 0, sizeof(uint32_t), ctx->stream));
+    // committee sums: P2[2a + 1] = -pk_a, valid[a] (indices in range, committee not empty, pk_a and sig_a finite)
+    k_attest_pairs<<<grid_for(nattest, 128), 128, 0, ctx->stream>>>((const g1_affine_pod *)d_registry, d_key_idx, d_key_off,
+                                                                    (const g2_affine_pod *)d_sig, (const g2_affine_pod *)d_msg_hash,
+                                                                    d_msg_idx, nattest, nkeys, nmsg, (g1_affine_pod *)P2, (g2_affine_pod *)Q2,
+                                                                    (uint32_t *)off2, (uint8_t *)valid);
+    k_attest_rlc_valid<<<grid_for(nattest, 256), 256, 0, ctx->stream>>>((const uint8_t *)valid, (const uint64_t *)d_r, rlc_bits, nattest, (uint32_t *)bad);
+    k_group_keys<<<grid_for(nattest, 256), 256, 0, ctx->stream>>>(d_msg_idx, nattest, nmsg, (uint64_t *)keys);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    // W_a = r_a (-pk_a): leading zero windows of a short weight cost nothing (the ladder doubles infinity)
+    k_point_mul<G1Codec, false><<<grid_for(nattest, 64), 64, 0, ctx->stream>>>((const g1_affine_pod *)P2 + 1, 2, (const uint64_t *)d_r, 1, nattest,
+                                                                               (g1_affine_pod *)W);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    // group by message: the bucket sums of one window wide enough for nmsg + 1 keys
+    int gc = 2;
+    while ((1ull << (gc - 1)) < nmsg + 1) gc++;
+    msm_buckets<FpInl> bk;
+    rc = msm_shard_dev<FpInl, g1_affine_pod, g1_jac_pod>(ctx, (const g1_affine_pod *)W, (const b381_scalar *)keys, nattest, 64, 0, 1, nullptr, nullptr, gc, &bk);
+    if (rc) return rc;
+    k_group_pairs<<<grid_for(nmsg, 64), 64, 0, ctx->stream>>>(bk.chunks, bk.chunk_off, (uint32_t)nmsg, (const g2_affine_pod *)d_msg_hash,
+                                                              (g1_affine_pod *)P, (g2_affine_pod *)Q);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    // T = sum_a r_a sig_a (the MSM work area is free again), closing pair (-G1One, T)
+    rc = msm_shard_dev<Fp2Out>(ctx, (const g2_affine_pod *)d_sig, d_r, nattest, rlc_bits, 0, 1, (g2_jac_pod *)S); if (rc) return rc;
+    k_rlc_close<<<1, 128, 0, ctx->stream>>>((const g2_jac_pod *)S, (g1_affine_pod *)P + nmsg, (g2_affine_pod *)Q + nmsg, (uint32_t *)off, (uint32_t)nmsg);
+    ctx->launches++;
+    rc = b381_pairing_product_is_one_dev(ctx, (const b381_g1_affine *)P, (const b381_g2_affine *)Q, nmsg + 1, (const uint32_t *)off, 1, d_ok);
+    if (rc) return rc;
+    k_rlc_finish<<<1, 32, 0, ctx->stream>>>(d_ok, (const uint32_t *)bad);
     ctx->launches++;
     CK(cudaGetLastError());
     return B381_OK;

@@ -346,3 +346,148 @@ func VerifyWithDomainRLC(pubs [][48]byte, msgs [][32]byte, domain [8]byte, sigs 
 		(*C.b381_scalar)(unsafe.Pointer(&w[0])), C.size_t(n), &ok))
 	return ok != 0
 }
+
+// KeyRegistry is a table of validated public keys resident on the device (BASELINE config 5: the validator registry).
+// Attestations refer to its entries by index, so a batch moves only indices, signatures and message points.
+type KeyRegistry struct {
+	dev unsafe.Pointer
+	n   int
+}
+
+// NewKeyRegistry uploads the keys once (b381_dev_alloc + b381_h2d).  Keys must be group elements
+// (DeserializePublicKey / DecompressG1Batch with the subgroup check).
+func NewKeyRegistry(keys []G1Affine) *KeyRegistry {
+	c, leave := enter()
+	defer leave()
+	r := &KeyRegistry{n: len(keys)}
+	if len(keys) == 0 {
+		return r
+	}
+	bytes := C.size_t(len(keys)) * C.size_t(unsafe.Sizeof(keys[0]))
+	must(C.b381_dev_alloc(c, bytes, &r.dev))
+	must(C.b381_h2d(c, r.dev, unsafe.Pointer(&keys[0]), bytes))
+	must(C.b381_sync(c))
+	return r
+}
+
+// Free releases the device table.
+func (r *KeyRegistry) Free() {
+	c, leave := enter()
+	defer leave()
+	if r.dev != nil {
+		C.b381_dev_free(c, r.dev)
+		r.dev = nil
+	}
+}
+
+// attestationBatch stages the per-batch arrays on the device: CSR committees, signatures, message points, message indices
+// (and the weights of the one-boolean form).  The caller holds the engine lock.
+type attestationBatch struct {
+	ptr [6]unsafe.Pointer
+}
+
+func (b *attestationBatch) free(c *C.b381_ctx) {
+	for _, p := range b.ptr {
+		if p != nil {
+			C.b381_dev_free(c, p)
+		}
+	}
+}
+
+func upload(c *C.b381_ctx, host unsafe.Pointer, bytes int) unsafe.Pointer {
+	var d unsafe.Pointer
+	if bytes == 0 {
+		bytes = 8
+		must(C.b381_dev_alloc(c, C.size_t(bytes), &d))
+		return d
+	}
+	must(C.b381_dev_alloc(c, C.size_t(bytes), &d))
+	must(C.b381_h2d(c, d, host, C.size_t(bytes)))
+	return d
+}
+
+func stageAttestations(c *C.b381_ctx, committees [][]uint32, sigs []G2Affine, msgPoints []G2Affine, msgIdx []uint32) *attestationBatch {
+	keyOff := make([]uint32, 1, len(committees)+1)
+	keyIdx := make([]uint32, 0, 128*len(committees))
+	for _, cm := range committees {
+		keyIdx = append(keyIdx, cm...)
+		keyOff = append(keyOff, uint32(len(keyIdx)))
+	}
+	b := &attestationBatch{}
+	var ki unsafe.Pointer
+	if len(keyIdx) > 0 {
+		ki = unsafe.Pointer(&keyIdx[0])
+	}
+	b.ptr[0] = upload(c, ki, 4*len(keyIdx))
+	b.ptr[1] = upload(c, unsafe.Pointer(&keyOff[0]), 4*len(keyOff))
+	b.ptr[2] = upload(c, unsafe.Pointer(&sigs[0]), len(sigs)*int(unsafe.Sizeof(sigs[0])))
+	b.ptr[3] = upload(c, unsafe.Pointer(&msgPoints[0]), len(msgPoints)*int(unsafe.Sizeof(msgPoints[0])))
+	b.ptr[4] = upload(c, unsafe.Pointer(&msgIdx[0]), 4*len(msgIdx))
+	return b
+}
+
+// VerifyAttestations: ok[a] == sigs[a].VerifyAggregateCommon(keys of committees[a], message msgIdx[a])
+// (g1pubs/bls.go:287-290) for a batch of attestations over the registry; msgPoints are the distinct hashed messages
+// (HashG2Batch / HashG2WithDomainBatch).  An empty committee, an index outside the tables, an infinite signature or
+// aggregate key give false.
+func (r *KeyRegistry) VerifyAttestations(committees [][]uint32, sigs []G2Affine, msgPoints []G2Affine, msgIdx []uint32) []bool {
+	n := len(sigs)
+	if n == 0 {
+		return []bool{}
+	}
+	if len(committees) != n || len(msgIdx) != n || len(msgPoints) == 0 || r.n == 0 {
+		panic("bls: attestation batch arrays do not match")
+	}
+	c, leave := enter()
+	defer leave()
+	b := stageAttestations(c, committees, sigs, msgPoints, msgIdx)
+	defer b.free(c)
+	b.ptr[5] = upload(c, nil, n)
+	must(C.b381_verify_aggregate_common_batch_dev(c, (*C.b381_g1_affine)(r.dev), (*C.uint32_t)(b.ptr[0]), (*C.uint32_t)(b.ptr[1]),
+		(*C.b381_g2_affine)(b.ptr[2]), (*C.b381_g2_affine)(b.ptr[3]), (*C.uint32_t)(b.ptr[4]), C.size_t(n), C.size_t(r.n),
+		C.size_t(len(msgPoints)), (*C.uint8_t)(b.ptr[5])))
+	st := make([]uint8, n)
+	must(C.b381_d2h(c, unsafe.Pointer(&st[0]), b.ptr[5], C.size_t(n)))
+	ok := make([]bool, n)
+	for i, s := range st {
+		ok[i] = s != 0
+	}
+	return ok
+}
+
+// VerifyAttestationsOneBoolean is the batch as a single check (random linear combination grouped by message,
+// b381_verify_aggregate_common_rlc_dev): true iff every attestation of VerifyAttestations is true, up to a false-accept
+// probability of 2^-64; len(msgPoints) + 1 Miller loops and one final exponentiation for the whole batch.  The weights are
+// drawn here, after the batch is fixed, from rnd (a cryptographic source).  On false, VerifyAttestations locates the offenders.
+func (r *KeyRegistry) VerifyAttestationsOneBoolean(committees [][]uint32, sigs []G2Affine, msgPoints []G2Affine, msgIdx []uint32, rnd io.Reader) bool {
+	n := len(sigs)
+	if n == 0 {
+		return true
+	}
+	if len(committees) != n || len(msgIdx) != n || len(msgPoints) == 0 || r.n == 0 {
+		return false
+	}
+	w := make([]FRRepr, n)
+	var buf [8]byte
+	for i := range w {
+		if _, err := io.ReadFull(rnd, buf[:]); err != nil {
+			panic(err)
+		}
+		w[i][0] = binary.LittleEndian.Uint64(buf[:]) | 1
+	}
+	c, leave := enter()
+	defer leave()
+	b := stageAttestations(c, committees, sigs, msgPoints, msgIdx)
+	defer b.free(c)
+	b.ptr[5] = upload(c, unsafe.Pointer(&w[0]), n*int(unsafe.Sizeof(w[0])))
+	var dok unsafe.Pointer
+	must(C.b381_dev_alloc(c, 8, &dok))
+	defer C.b381_dev_free(c, dok)
+	must(C.b381_set_rlc_weight_bits(c, 64))
+	must(C.b381_verify_aggregate_common_rlc_dev(c, (*C.b381_g1_affine)(r.dev), (*C.uint32_t)(b.ptr[0]), (*C.uint32_t)(b.ptr[1]),
+		(*C.b381_g2_affine)(b.ptr[2]), (*C.b381_g2_affine)(b.ptr[3]), (*C.uint32_t)(b.ptr[4]), (*C.b381_scalar)(b.ptr[5]),
+		C.size_t(n), C.size_t(r.n), C.size_t(len(msgPoints)), (*C.uint8_t)(dok)))
+	var ok uint8
+	must(C.b381_d2h(c, unsafe.Pointer(&ok), dok, 1))
+	return ok != 0
+}

@@ -172,6 +172,18 @@ int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *
                                            const uint32_t *d_key_idx, const uint32_t *d_key_off,
                                            const b381_g2_affine *d_sig, const b381_g2_affine *d_msg_hash,
                                            const uint32_t *d_msg_idx, size_t nattest, size_t nkeys, size_t nmsg, uint8_t *d_ok);
+/* The same batch as ONE boolean (batch verification by a random linear combination, grouped by message):
+ * *d_ok = [ e(-G1One, sum_a r_a sig[a]) * prod_m e(sum_{a: msg_idx[a] = m} r_a pk_a, msg_hash[m]) == 1 ], which holds iff every
+ * attestation verifies, except with probability ~2^-bits for weights r_a drawn independently by the VERIFIER after the batch
+ * is fixed (b381_set_rlc_weight_bits; a zero or over-wide weight, an index outside the tables, an empty committee, an
+ * infinite signature or aggregate key make it false).  nmsg + 1 Miller loops and one FinalExponentiation per batch instead of
+ * two and one per attestation (pairing.go:16-129); on a false result the caller locates the offender with the per-attestation
+ * call above.  No reference counterpart: the reference verifies one aggregate at a time (g1pubs/bls.go:287-297). */
+int b381_verify_aggregate_common_rlc_dev(b381_ctx *ctx, const b381_g1_affine *d_registry,
+                                         const uint32_t *d_key_idx, const uint32_t *d_key_off,
+                                         const b381_g2_affine *d_sig, const b381_g2_affine *d_msg_hash,
+                                         const uint32_t *d_msg_idx, const b381_scalar *d_r, size_t nattest, size_t nkeys,
+                                         size_t nmsg, uint8_t *d_ok);
 /* The same batch as the attestations arrive on the wire: compressed aggregate signatures (n x 96 bytes) and 32-byte
  * message hashes (nmsg DISTINCT messages, msg_idx[a] selects one) with one 8-byte domain.  On the device:
  * DeserializeSignature with the subgroup check (g1pubs/bls.go:38-45), HashG2WithDomain per distinct message

@@ -219,6 +219,52 @@ def test_verify_aggregate_common_batch(ctx, orc):
         assert int(good) == expect[a] == int(ok[a])
 
 
+def test_attestation_batch_as_one_random_linear_combination(ctx, orc):
+    """b381_verify_aggregate_common_rlc_dev: one boolean for the batch == AND of the per-attestation VerifyAggregateCommon
+    verdicts (which are checked against the oracle above); ragged committees, several messages, a message nobody signs,
+    every single corrupted position, bad weights, bad indices"""
+    reg, kidx, koff, sig, H, midx, expect = _attestations(orc, 64, 24, 9, 3, 5)
+    good = [a for a, e in enumerate(expect) if e]                      # the construction corrupts every fourth signature
+    assert len(good) < len(expect)
+    assert ctx.verify_aggregate_common_rlc(reg, kidx, koff, sig, H, midx) is False
+    assert ctx.verify_aggregate_common_batch(reg, kidx, koff, sig, H, midx).tolist() == expect
+
+    def subset(idx):
+        ki = np.concatenate([kidx[koff[a]:koff[a + 1]] for a in idx]).astype(np.uint32)
+        ko = np.concatenate([[0], np.cumsum([koff[a + 1] - koff[a] for a in idx])]).astype(np.uint32)
+        return ki, ko, sig[idx], midx[idx]
+    ki, ko, sg, mi = subset(good)
+    H4 = np.concatenate([H, hg.g2_mul(0x4242)])                        # a fourth message that no attestation refers to
+    assert ctx.verify_aggregate_common_rlc(reg, ki, ko, sg, H4, mi) is True
+    assert ctx.verify_aggregate_common_rlc(reg, ki, ko, sg, H4, mi, weights=np.arange(1, len(good) + 1)) is True
+    # one bad attestation anywhere makes the batch false
+    bad_a = next(a for a, e in enumerate(expect) if not e)
+    for pos in (0, len(good) // 2, len(good)):
+        idx = good[:pos] + [bad_a] + good[pos:]
+        ki2, ko2, sg2, mi2 = subset(idx)
+        assert ctx.verify_aggregate_common_rlc(reg, ki2, ko2, sg2, H4, mi2) is False, pos
+    # two corruptions that cancel without weights: sig_0 + D and sig_1 - D for the same message are caught by random weights
+    same = [a for a in good if midx[a] == midx[good[0]]][:2]
+    assert len(same) == 2
+    ki3, ko3, sg3, mi3 = subset(same)
+    s0, d0, h = 0x1000 + 5, 0x2B, 0x77 + 5 * int(midx[same[0]])       # the discrete logs _attestations(seed = 5) used
+    sks = [sum(s0 + int(i) * d0 for i in kidx[koff[a]:koff[a + 1]]) for a in same]
+    assert hg.g2_mul(sks[0] * h % L.R_ORDER).tobytes() == sg3[0:1].tobytes()
+    sg3 = np.concatenate([hg.g2_mul((sks[0] * h + 0x999) % L.R_ORDER), hg.g2_mul((sks[1] * h - 0x999) % L.R_ORDER)])
+    assert ctx.verify_aggregate_common_rlc(reg, ki3, ko3, sg3, H4, mi3, weights=[1, 1]) is True       # the forgery equal weights admit
+    assert ctx.verify_aggregate_common_rlc(reg, ki3, ko3, sg3, H4, mi3) is False                      # ... and random ones reject
+    # fail closed: zero weight, over-wide weight (bits = 64 is set by the wrapper), message / key index outside the tables, empty batch
+    w = np.arange(1, len(good) + 1).astype(np.uint64); w[3] = 0
+    assert ctx.verify_aggregate_common_rlc(reg, ki, ko, sg, H4, mi, weights=w) is False
+    mi_bad = mi.copy(); mi_bad[2] = 77
+    assert ctx.verify_aggregate_common_rlc(reg, ki, ko, sg, H4, mi_bad) is False
+    ki_bad = ki.copy(); ki_bad[5] = 64
+    assert ctx.verify_aggregate_common_rlc(reg, ki_bad, ko, sg, H4, mi) is False
+    sg_inf = sg.copy(); sg_inf["inf"][1] = 1
+    assert ctx.verify_aggregate_common_rlc(reg, ki, ko, sg_inf, H4, mi) is False
+    assert ctx.verify_aggregate_common_rlc(reg, np.zeros(0, np.uint32), np.zeros(1, np.uint32), sg[:0], H4, mi[:0]) is True
+
+
 def test_verify_aggregate_empty_committee_and_batch(ctx, orc):
     """an empty committee aggregates to the zero key (the reference panics in MillerLoop; the
     engine treats the infinity pair as the factor 1, so the check reduces to e(G1, sig) == 1: false)"""

@@ -394,15 +394,17 @@ func (b *attestationBatch) free(c *C.b381_ctx) {
 	}
 }
 
+// upload allocates bytes on the device (at least 8) and, when host is not nil, copies them from host.
 func upload(c *C.b381_ctx, host unsafe.Pointer, bytes int) unsafe.Pointer {
 	var d unsafe.Pointer
-	if bytes == 0 {
-		bytes = 8
-		must(C.b381_dev_alloc(c, C.size_t(bytes), &d))
-		return d
+	alloc := bytes
+	if alloc < 8 {
+		alloc = 8
 	}
-	must(C.b381_dev_alloc(c, C.size_t(bytes), &d))
-	must(C.b381_h2d(c, d, host, C.size_t(bytes)))
+	must(C.b381_dev_alloc(c, C.size_t(alloc), &d))
+	if host != nil && bytes > 0 {
+		must(C.b381_h2d(c, d, host, C.size_t(bytes)))
+	}
 	return d
 }
 

@@ -178,7 +178,7 @@ int b381_verify_aggregate_common_batch_dev(b381_ctx *ctx, const b381_g1_affine *
  * is fixed (b381_set_rlc_weight_bits; a zero or over-wide weight, an index outside the tables, an empty committee, an
  * infinite signature or aggregate key make it false).  nmsg + 1 Miller loops and one FinalExponentiation per batch instead of
  * two and one per attestation (pairing.go:16-129); on a false result the caller locates the offender with the per-attestation
- * call above.  No reference counterpart: the reference verifies one aggregate at a time (g1pubs/bls.go:287-297). */
+ * call above.  nmsg <= 2^22.  No reference counterpart: the reference verifies one aggregate at a time (g1pubs/bls.go:287-297). */
 int b381_verify_aggregate_common_rlc_dev(b381_ctx *ctx, const b381_g1_affine *d_registry,
                                          const uint32_t *d_key_idx, const uint32_t *d_key_off,
                                          const b381_g2_affine *d_sig, const b381_g2_affine *d_msg_hash,

@@ -335,6 +335,8 @@ struct b381_ctx {
     int sms;
     cudaStream_t own_stream;
     cudaStream_t stream;
+    cudaStream_t side_stream;        // a second stream of the ctx's own for work that is independent of the main chain (fork / join by events)
+    cudaEvent_t side_fork, side_join;
     uint64_t launches;
     char err[256];
     // grow-only device scratch
@@ -368,6 +370,7 @@ enum { VM_ML1 = 0, VM_FE_A = 1, VM_FE_C = 2 };
 //   22  group offsets of the random-linear-combination check                        23  its G2 sum + "any invalid" flag
 //   24  validity bytes of an attestation batch        25, 26  group offsets / verdicts of b381_pairing_product_is_one        27, 28  prepared G2 points
 //   32-35  attestation-level random-linear-combination check: weighted keys, group keys as scalars, per-message pairs (G1, G2)
+//   36  work area of the G2 MSM that runs on the side stream
 static int scratch_get(b381_ctx *ctx, int slot, size_t bytes, void **out) {
     if (ctx->scratch_bytes[slot] < bytes) {
         if (ctx->scratch[slot]) {
@@ -447,6 +450,9 @@ int b381_init(int device, b381_ctx **out) {
     cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, device);
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return B381_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
+    if (cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->side_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->side_join, cudaEventDisableTiming) != cudaSuccess) { b381_free(ctx); return B381_ERR_CUDA; }
     // the tower state of a pairing lives in local memory: prefer L1 over shared memory
     if (cudaFuncSetAttribute(k_miller_loop, cudaFuncAttributePreferredSharedMemoryCarveout, 0) != cudaSuccess ||
         cudaFuncSetAttribute(k_miller_loop2, cudaFuncAttributePreferredSharedMemoryCarveout, 0) != cudaSuccess ||
@@ -493,7 +499,10 @@ void b381_free(b381_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 40; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     for (int i = 0; i < 3; i++) { if (ctx->vm[i].code) cudaFree(ctx->vm[i].code); if (ctx->vm[i].consts) cudaFree(ctx->vm[i].consts); }
-    cudaStreamDestroy(ctx->own_stream);
+    if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+    if (ctx->side_fork) cudaEventDestroy(ctx->side_fork);
+    if (ctx->side_join) cudaEventDestroy(ctx->side_join);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
 
@@ -1163,7 +1172,7 @@ static inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 template <class F> struct msm_buckets { const xyzz<F> *chunks; const uint32_t *chunk_off; msm_geom g; };
 template <class F, class APOD, class JPOD>
 static int msm_shard_dev(b381_ctx *ctx, const APOD *d_p, const b381_scalar *d_k, size_t n, int nbits, int rank, int nranks, JPOD *d_partial,
-                         float *phase_ms = nullptr, int group_c = 0, msm_buckets<F> *buckets = nullptr) {
+                         float *phase_ms = nullptr, int group_c = 0, msm_buckets<F> *buckets = nullptr, int scratch_slot = 5) {
     if (!ctx || (!d_partial && !buckets) || (n && (!d_p || !d_k)) || nranks < 1 || rank < 0 || rank >= nranks || n > 0x7FFFFFF0u || nbits < 1 ||
         nbits > 255 || (buckets && (group_c < 2 || group_c > 24 || phase_ms)))
         return B381_ERR_ARG;                         // (bit 31 of an index entry is the sign of the digit)
@@ -1186,7 +1195,7 @@ static int msm_shard_dev(b381_ctx *ctx, const APOD *d_p, const b381_scalar *d_k,
     size_t o_chunks = o_cb + up256((size_t)nw * g.maxchunks * 4), o_seg = o_chunks + up256((size_t)nw * g.maxchunks * sizeof(xyzz<F>));
     size_t o_win = o_seg + up256((size_t)nw * nseg * sizeof(xyzz<F>)), total = o_win + up256((size_t)nw * sizeof(xyzz<F>));
     char *base;
-    int rc = scratch_get(ctx, 5, total, (void **)&base);
+    int rc = scratch_get(ctx, scratch_slot, total, (void **)&base);
     if (rc) return rc;
     uint32_t *count = (uint32_t *)(base + o_count), *boff = (uint32_t *)(base + o_boff), *coff = (uint32_t *)(base + o_coff);
     uint32_t *maxch = (uint32_t *)(base + o_max), *idx = (uint32_t *)(base + o_idx), *cb = (uint32_t *)(base + o_cb);
@@ -1393,6 +1402,25 @@ static int verify_wire_dev(b381_ctx *ctx, int mode, const uint8_t *d_pub, const 
     CK(cudaGetLastError());
     return B381_OK;
 }
+// S = sum_i r_i sig_i on the ctx's SIDE stream, forked from the main stream here and joined by the caller with side_join():
+// the G2 MSM of a random-linear-combination check depends on nothing the G1 side computes, and both are chains of small,
+// latency-bound launches at these sizes, so they overlap.  Its work area is a slot of its own (36), not the main MSM's.
+static int g2_msm_on_side_stream(b381_ctx *ctx, const b381_g2_affine *d_sig, const b381_scalar *d_r, size_t n, int bits, g2_jac_pod *S) {
+    CK(cudaEventRecord(ctx->side_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->side_stream, ctx->side_fork, 0));
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = ctx->side_stream;
+    int rc = msm_shard_dev<Fp2Out>(ctx, (const g2_affine_pod *)d_sig, d_r, n, bits, 0, 1, S, nullptr, 0, nullptr, 36);
+    cudaError_t e = cudaEventRecord(ctx->side_join, ctx->side_stream);
+    ctx->stream = main_stream;
+    if (rc) return rc;
+    CK(e);
+    return B381_OK;
+}
+static int side_join(b381_ctx *ctx) {
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->side_join, 0));
+    return B381_OK;
+}
 // ---- attestation batches as ONE random-linear-combination check, grouped by message -------------------------------------------
 // ok = [ e(-G1One, sum_a r_a sig_a) * prod_m e(sum_{a: msg(a) = m} r_a pk_a, H_m) == 1 ]: with independent random r_a this accepts
 // iff every e(G1One, sig_a) == e(pk_a, H_msg(a)) holds (VerifyAggregateCommon, g1pubs/bls.go:287-297), except with probability
@@ -1420,6 +1448,8 @@ extern "C" int b381_verify_aggregate_common_rlc_dev(b381_ctx *ctx, const b381_g1
     rc = scratch_get(ctx, 22, 2 * sizeof(uint32_t), &off); if (rc) return rc;
     bad = (char *)S + sizeof(b381_g2_jac);
     CK(cudaMemsetAsync(bad, 0, sizeof(uint32_t), ctx->stream));
+    // T = sum_a r_a sig_a runs beside everything up to the closing pair
+    rc = g2_msm_on_side_stream(ctx, d_sig, d_r, nattest, rlc_bits, (g2_jac_pod *)S); if (rc) return rc;
     // committee sums: P2[2a + 1] = -pk_a, valid[a] (indices in range, committee not empty, pk_a and sig_a finite)
     k_attest_pairs<<<grid_for(nattest, 128), 128, 0, ctx->stream>>>((const g1_affine_pod *)d_registry, d_key_idx, d_key_off,
                                                                     (const g2_affine_pod *)d_sig, (const g2_affine_pod *)d_msg_hash,
@@ -1444,8 +1474,8 @@ extern "C" int b381_verify_aggregate_common_rlc_dev(b381_ctx *ctx, const b381_g1
                                                               (g1_affine_pod *)P, (g2_affine_pod *)Q);
     ctx->launches++;
     CK(cudaGetLastError());
-    // T = sum_a r_a sig_a (the MSM work area is free again), closing pair (-G1One, T)
-    rc = msm_shard_dev<Fp2Out>(ctx, (const g2_affine_pod *)d_sig, d_r, nattest, rlc_bits, 0, 1, (g2_jac_pod *)S); if (rc) return rc;
+    // closing pair (-G1One, T)
+    rc = side_join(ctx); if (rc) return rc;
     k_rlc_close<<<1, 128, 0, ctx->stream>>>((const g2_jac_pod *)S, (g1_affine_pod *)P + nmsg, (g2_affine_pod *)Q + nmsg, (uint32_t *)off, (uint32_t)nmsg);
     ctx->launches++;
     rc = b381_pairing_product_is_one_dev(ctx, (const b381_g1_affine *)P, (const b381_g2_affine *)Q, nmsg + 1, (const uint32_t *)off, 1, d_ok);
@@ -1473,6 +1503,8 @@ static int verify_rlc_core(b381_ctx *ctx, const b381_g1_affine *d_pub, const b38
     rc = scratch_get(ctx, 22, 2 * sizeof(uint32_t), &off); if (rc) return rc;
     bad = (char *)S + sizeof(b381_g2_jac);          // (slot 21 is the tree product's own scalar)
     CK(cudaMemsetAsync(bad, 0, sizeof(uint32_t), ctx->stream));
+    // S = sum_i r_i sig_i as one Pippenger MSM over G2 (the weights are scalars like any other), beside the G1 scalar multiplications
+    rc = g2_msm_on_side_stream(ctx, d_sig, d_r, n, rlc_bits, (g2_jac_pod *)S); if (rc) return rc;
     if (n) {
         k_rlc_valid<<<grid_for(n, 256), 256, 0, ctx->stream>>>((const g1_affine_pod *)d_pub, (const g2_affine_pod *)d_sig, d_pub_status,
                                                                d_sig_status, (const uint64_t *)d_r, rlc_bits, n, (uint32_t *)bad);
@@ -1480,8 +1512,7 @@ static int verify_rlc_core(b381_ctx *ctx, const b381_g1_affine *d_pub, const b38
         rc = b381_g1_mul_batch_dev(ctx, d_pub, 1, d_r, 1, n, (b381_g1_affine *)P); if (rc) return rc;
         CK(cudaMemcpyAsync(Q, d_h, n * sizeof(b381_g2_affine), cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    // S = sum_i r_i sig_i as one Pippenger MSM over G2 (the weights are scalars like any other)
-    rc = msm_shard_dev<Fp2Out>(ctx, (const g2_affine_pod *)d_sig, d_r, n, rlc_bits, 0, 1, (g2_jac_pod *)S); if (rc) return rc;
+    rc = side_join(ctx); if (rc) return rc;
     k_rlc_close<<<1, 128, 0, ctx->stream>>>((const g2_jac_pod *)S, (g1_affine_pod *)P + n, (g2_affine_pod *)Q + n, (uint32_t *)off, (uint32_t)n);
     ctx->launches++;
     if (d_partial) {

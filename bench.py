@@ -4,8 +4,10 @@
 One "step" = one pass of the hot path (fused Miller loop kernel + final-exponentiation kernel)
 over a batch of 2^16 synthetic (P_i, Q_i) pairs with known discrete logs.
   value : whole-job pairings/s, inputs already resident in HBM (CUDA events, max over ranks)
-  e2e   : the same batch through the public C-ABI call b381_pairing_batch with pinned HOST buffers
-          (H2D of 2^16 x 304 B and D2H of 2^16 x 576 B inside the timed region)
+  e2e   : the same steps through the public C-ABI with pinned HOST buffers: b381_pairing_batch_stream, one call for all
+          steps, one batch per step (H2D of 2^16 x 304 B and D2H of 2^16 x 576 B per step inside the timed region, the
+          copies of neighbouring steps overlapped with the kernels); e2e.one_call_per_step is b381_pairing_batch once per
+          step (copies and kernels in series)
   roofline : integer-pipe roofline of the dominant kernel -- wide multiply-accumulates per second
           against the IMAD.WIDE.U32 issue rate measured on this GPU in the same run
           (MEASURED_PEAKS.json has no integer peak; SURVEY.md section 8d names IMAD as the bound)
@@ -517,7 +519,29 @@ def run_engine(args):
     te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_single = world * n * e2e_steps / float(te.item())
+    # the same steps as ONE call of the streaming form: every step's inputs go up from pinned host memory and its results come
+    # down inside the timed region, the copies of neighbouring steps overlapped with the kernels (b381_pairing_batch_stream)
+    hPs = torch.empty(e2e_steps * P.nbytes, dtype=torch.uint8).pin_memory(); hQs = torch.empty(e2e_steps * Q.nbytes, dtype=torch.uint8).pin_memory()
+    hOs = torch.empty(e2e_steps * n * 576, dtype=torch.uint8).pin_memory()
+    for k in range(e2e_steps):
+        hPs.numpy()[k * P.nbytes:(k + 1) * P.nbytes] = hP.numpy(); hQs.numpy()[k * Q.nbytes:(k + 1) * Q.nbytes] = hQ.numpy()
+
+    def e2e_stream():
+        ctx.call("b381_pairing_batch_stream", ctypes.c_void_p(hPs.data_ptr()), ctypes.c_void_p(hQs.data_ptr()), ctypes.c_size_t(e2e_steps * n),
+                 ctypes.c_size_t(n), ctypes.c_void_p(hOs.data_ptr()))
+    e2e_stream()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_stream()
+    barrier()
+    t_e2s = time.perf_counter() - t0
+    assert hOs.numpy()[-n * 576:].tobytes() == hOut.numpy().tobytes(), "streamed results differ from the single-batch call"
+    te = torch.tensor([t_e2s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / float(te.item())
+    del hPs, hQs, hOs
 
     extras = aggregate_extras(ctx, stream, dev, rank, world, torch, np, imad_peak) if not args.no_aggregate else None
     # ---- result check (sample vs the oracle) + CPU baseline on rank 0 ---------------------------
@@ -545,7 +569,9 @@ def run_engine(args):
                        "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (104 + 200),
                     "d2h_bytes_per_step": n * 576, "steps": e2e_steps,
-                    "api": "b381_pairing_batch (host pointers, pinned)"},
+                    "api": "b381_pairing_batch_stream (host pointers, pinned; one call for all steps, batch = one step, copies of "
+                           "neighbouring steps overlapped with the kernels)",
+                    "one_call_per_step": {"value": e2e_single, "api": "b381_pairing_batch (host pointers, pinned; H2D, kernels, D2H in series)"}},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {

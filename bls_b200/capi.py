@@ -125,6 +125,14 @@ class Ctx:
         self.call("b381_pairing_batch", _hp(p), _hp(q), ctypes.c_size_t(p.size), _hp(out))
         return out
 
+    def pairing_batch_stream(self, p, q, batch):
+        """the pairings of n pairs, `batch` per launch, copies overlapped with the kernels -- b381_pairing_batch_stream"""
+        p = np.ascontiguousarray(p, dtype=L.G1_AFFINE); q = np.ascontiguousarray(q, dtype=L.G2_AFFINE)
+        assert p.size == q.size
+        out = np.empty(p.size, dtype=L.FP12)
+        self.call("b381_pairing_batch_stream", _hp(p), _hp(q), ctypes.c_size_t(p.size), ctypes.c_size_t(batch), _hp(out))
+        return out
+
     def miller_loop_batch(self, p, q):
         p = np.ascontiguousarray(p, dtype=L.G1_AFFINE); q = np.ascontiguousarray(q, dtype=L.G2_AFFINE)
         assert p.size == q.size

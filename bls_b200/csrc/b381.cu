@@ -337,6 +337,7 @@ struct b381_ctx {
     cudaStream_t stream;
     cudaStream_t side_stream;        // a second stream of the ctx's own for work that is independent of the main chain (fork / join by events)
     cudaEvent_t side_fork, side_join;
+    cudaEvent_t pipe_in[2], pipe_done[2], pipe_out[2];   // double-buffered host streaming (b381_pairing_batch_stream)
     uint64_t launches;
     char err[256];
     // grow-only device scratch
@@ -370,7 +371,7 @@ enum { VM_ML1 = 0, VM_FE_A = 1, VM_FE_C = 2 };
 //   22  group offsets of the random-linear-combination check                        23  its G2 sum + "any invalid" flag
 //   24  validity bytes of an attestation batch        25, 26  group offsets / verdicts of b381_pairing_product_is_one        27, 28  prepared G2 points
 //   32-35  attestation-level random-linear-combination check: weighted keys, group keys as scalars, per-message pairs (G1, G2)
-//   36  work area of the G2 MSM that runs on the side stream
+//   36  work area of the G2 MSM that runs on the side stream        37-39  double buffers of b381_pairing_batch_stream (G1, G2, Fq12)
 static int scratch_get(b381_ctx *ctx, int slot, size_t bytes, void **out) {
     if (ctx->scratch_bytes[slot] < bytes) {
         if (ctx->scratch[slot]) {
@@ -453,6 +454,10 @@ int b381_init(int device, b381_ctx **out) {
     if (cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->side_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->side_join, cudaEventDisableTiming) != cudaSuccess) { b381_free(ctx); return B381_ERR_CUDA; }
+    for (int i = 0; i < 2; i++)
+        if (cudaEventCreateWithFlags(&ctx->pipe_in[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->pipe_done[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->pipe_out[i], cudaEventDisableTiming) != cudaSuccess) { b381_free(ctx); return B381_ERR_CUDA; }
     // the tower state of a pairing lives in local memory: prefer L1 over shared memory
     if (cudaFuncSetAttribute(k_miller_loop, cudaFuncAttributePreferredSharedMemoryCarveout, 0) != cudaSuccess ||
         cudaFuncSetAttribute(k_miller_loop2, cudaFuncAttributePreferredSharedMemoryCarveout, 0) != cudaSuccess ||
@@ -502,6 +507,11 @@ void b381_free(b381_ctx *ctx) {
     if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
     if (ctx->side_fork) cudaEventDestroy(ctx->side_fork);
     if (ctx->side_join) cudaEventDestroy(ctx->side_join);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->pipe_in[i]) cudaEventDestroy(ctx->pipe_in[i]);
+        if (ctx->pipe_done[i]) cudaEventDestroy(ctx->pipe_done[i]);
+        if (ctx->pipe_out[i]) cudaEventDestroy(ctx->pipe_out[i]);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -1076,6 +1086,53 @@ int b381_pairing_batch(b381_ctx *ctx, const b381_g1_affine *p, const b381_g2_aff
 }
 int b381_miller_loop_batch(b381_ctx *ctx, const b381_g1_affine *p, const b381_g2_affine *q, size_t n, b381_fp12 *out) {
     return pairing_host(ctx, p, q, n, out, false);
+}
+// A stream of batches from host memory: out[i] = Pairing(p[i], q[i]) for n pairs, computed `batch` pairs at a time with the
+// copies of neighbouring batches overlapped with the kernels (two device buffers per array; the inputs of batch k + 1 go up and
+// the results of batch k - 1 come down on the ctx's side stream while batch k computes).  With page-locked host memory the copies
+// cost nothing after the first batch in and the last batch out; the values are those of b381_pairing_batch.
+int b381_pairing_batch_stream(b381_ctx *ctx, const b381_g1_affine *p, const b381_g2_affine *q, size_t n, size_t batch, b381_fp12 *out) {
+    if (!ctx || !batch || (n && (!p || !q || !out))) return B381_ERR_ARG;
+    if (!n) return B381_OK;
+    if (batch > n) batch = n;
+    CK(cudaSetDevice(ctx->device));
+    void *dp, *dq, *dout;
+    int rc = scratch_get(ctx, 37, 2 * batch * sizeof(b381_g1_affine), &dp); if (rc) return rc;
+    rc = scratch_get(ctx, 38, 2 * batch * sizeof(b381_g2_affine), &dq); if (rc) return rc;
+    rc = scratch_get(ctx, 39, 2 * batch * sizeof(b381_fp12), &dout); if (rc) return rc;
+    b381_g1_affine *dP[2] = {(b381_g1_affine *)dp, (b381_g1_affine *)dp + batch};
+    b381_g2_affine *dQ[2] = {(b381_g2_affine *)dq, (b381_g2_affine *)dq + batch};
+    b381_fp12 *dO[2] = {(b381_fp12 *)dout, (b381_fp12 *)dout + batch};
+    const size_t K = (n + batch - 1) / batch;
+    cudaStream_t M = ctx->stream, S = ctx->side_stream;
+    auto len = [&](size_t k) { return k + 1 < K ? batch : n - k * batch; };
+    auto upload = [&](size_t k) -> int {
+        const int b = (int)(k & 1);
+        CK(cudaMemcpyAsync(dP[b], p + k * batch, len(k) * sizeof(b381_g1_affine), cudaMemcpyHostToDevice, S));
+        CK(cudaMemcpyAsync(dQ[b], q + k * batch, len(k) * sizeof(b381_g2_affine), cudaMemcpyHostToDevice, S));
+        CK(cudaEventRecord(ctx->pipe_in[b], S));
+        return B381_OK;
+    };
+    CK(cudaEventRecord(ctx->side_fork, M));                    // the side stream starts after whatever the main stream holds
+    CK(cudaStreamWaitEvent(S, ctx->side_fork, 0));
+    rc = upload(0); if (rc) return rc;
+    for (size_t k = 0; k < K; k++) {
+        const int b = (int)(k & 1);
+        if (k + 1 < K) {
+            if (k >= 1) CK(cudaStreamWaitEvent(S, ctx->pipe_done[b ^ 1], 0));   // batch k - 1 has read the buffers batch k + 1 goes into
+            rc = upload(k + 1); if (rc) return rc;
+        }
+        CK(cudaStreamWaitEvent(M, ctx->pipe_in[b], 0));
+        if (k >= 2) CK(cudaStreamWaitEvent(M, ctx->pipe_out[b], 0));            // the results of batch k - 2 have left this buffer
+        rc = b381_pairing_batch_dev(ctx, dP[b], dQ[b], len(k), dO[b]); if (rc) return rc;
+        CK(cudaEventRecord(ctx->pipe_done[b], M));
+        CK(cudaStreamWaitEvent(S, ctx->pipe_done[b], 0));
+        CK(cudaMemcpyAsync(out + k * batch, dO[b], len(k) * sizeof(b381_fp12), cudaMemcpyDeviceToHost, S));
+        CK(cudaEventRecord(ctx->pipe_out[b], S));
+    }
+    CK(cudaStreamSynchronize(S));
+    CK(cudaStreamSynchronize(M));
+    return B381_OK;
 }
 int b381_final_exp_batch(b381_ctx *ctx, const b381_fp12 *in, size_t n, b381_fp12 *out, uint8_t *ok) {
     if (!ctx || (n && (!in || !out))) return B381_ERR_ARG;

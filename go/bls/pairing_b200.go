@@ -202,8 +202,9 @@ func PairingBatch(ps []*G1Affine, qs []*G2Affine) []*FQ12 {
 	out := make([]C.b381_fp12, n)
 	engine.mu.Lock()
 	defer engine.mu.Unlock()
-	rc := C.b381_pairing_batch(ctx(), (*C.b381_g1_affine)(unsafe.Pointer(&p[0])),
-		(*C.b381_g2_affine)(unsafe.Pointer(&q[0])), C.size_t(n), &out[0])
+	// batches of 2^16 pairs per launch; with more than one batch the copies overlap the kernels (b381_pairing_batch_stream)
+	rc := C.b381_pairing_batch_stream(ctx(), (*C.b381_g1_affine)(unsafe.Pointer(&p[0])),
+		(*C.b381_g2_affine)(unsafe.Pointer(&q[0])), C.size_t(n), C.size_t(1<<16), &out[0])
 	if rc != C.B381_OK {
 		panic(C.GoString(C.b381_last_error(ctx())))
 	}

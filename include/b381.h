@@ -99,6 +99,12 @@ int b381_pairing_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_
 /* out[i] = bls.MillerLoop({p[i], G2AffineToPrepared(q[i])})        (pairing.go:16-75, g2.go:650-801) */
 int b381_miller_loop_batch(b381_ctx *ctx, const b381_g1_affine *p, const b381_g2_affine *q, size_t n,
                            b381_fp12 *out);
+/* A stream of batches from host memory: out[i] = Pairing(p[i], q[i]) for n pairs, `batch` pairs per launch, the copies of
+ * neighbouring batches overlapped with the kernels (double buffers on the device, a second stream of the ctx).  Same values as
+ * b381_pairing_batch; with page-locked host memory only the first copy in and the last copy out are not hidden.  This is the
+ * host-buffer form of a caller that verifies batch after batch (pairing.go:131-138 once per pair in the reference). */
+int b381_pairing_batch_stream(b381_ctx *ctx, const b381_g1_affine *p, const b381_g2_affine *q, size_t n, size_t batch,
+                              b381_fp12 *out);
 int b381_miller_loop_batch_dev(b381_ctx *ctx, const b381_g1_affine *d_p, const b381_g2_affine *d_q,
                                size_t n, b381_fp12 *d_out);
 /* out[i] = bls.FinalExponentiation(in[i]); ok[i] = 0 where the reference returns nil (in[i] == 0),

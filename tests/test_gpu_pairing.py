@@ -67,6 +67,21 @@ def test_final_exp_of_zero_and_random(ctx, orc):
             assert (fe[i] == exp).all(), i
 
 
+def test_pairing_batch_stream_matches_single_batches(ctx, orc):
+    """b381_pairing_batch_stream (double-buffered host streaming) == b381_pairing_batch == the oracle, for batch sizes that
+    divide n, leave a short last batch, exceed n, and for a single pair per batch"""
+    n = 45
+    P = hg.g1_progression(0x51, 7, n); Q = hg.g2_progression(0x29, 3, n)
+    P["inf"][4] = 1
+    want = ctx.pairing_batch(P, Q)
+    assert want.tobytes() == orc.pairing_batch(P, Q).tobytes()
+    for batch in (9, 16, 44, 45, 100, 1):
+        assert ctx.pairing_batch_stream(P, Q, batch).tobytes() == want.tobytes(), batch
+    assert ctx.pairing_batch_stream(P[:0], Q[:0], 8).size == 0
+    with pytest.raises(Exception):
+        ctx.pairing_batch_stream(P, Q, 0)
+
+
 def test_empty_batch(ctx):
     P = np.zeros(0, dtype=L.G1_AFFINE); Q = np.zeros(0, dtype=L.G2_AFFINE)
     assert ctx.pairing_batch(P, Q).shape[0] == 0
